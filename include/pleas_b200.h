@@ -1,0 +1,170 @@
+/* pleas_b200 — C ABI of the B200-native PLeaS-Merging merge hot path.
+ *
+ * Plain pointers, sizes and a CUDA stream handle; no torch types, no exceptions, no
+ * allocation of caller-visible memory.  All pointers are DEVICE pointers unless a
+ * parameter is documented as host memory.  Every function enqueues on `stream` (a
+ * cudaStream_t passed as void*; NULL = legacy default stream), is safe to capture in a
+ * CUDA graph unless noted, and returns
+ *     0   success
+ *    <0   invalid argument (PLB_EINVAL ...)
+ *    >0   CUDA error code (cudaError_t) raised while launching
+ * plb_last_error_string() describes the last failure on the calling thread.
+ *
+ * The reference (SewoongLab/PLeaS-Merging) is pure Python; each entry point names the
+ * reference code it replaces.  INTEGRATION.md shows the ctypes binding a reference
+ * maintainer would add.
+ */
+#ifndef PLEAS_B200_H
+#define PLEAS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLB_OK 0
+#define PLB_EINVAL (-1)
+#define PLB_ESIZE (-2)   /* problem too large for the kernel's on-chip working set */
+#define PLB_EALIGN (-3)  /* pointer / leading dimension not aligned as required */
+
+/* cross-statistic modes (pleas/methods/activation_matching.py:14-46) */
+#define PLB_MODE_INNER 0      /* G = X Y^T            cross_features_inner_product :14-28 */
+#define PLB_MODE_NEG_CDIST 1  /* -sqrt(max(qa+qb-2G,0)) cross_features_cdist      :31-46 */
+
+int plb_version(void);
+const char *plb_last_error_string(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Packed operand planes.
+ *
+ * A logical operand is a row-major view X[rows, K] of a tensor laid out as
+ * [outer][rows][inner] (K = outer*inner, k = o*inner + i): the reference's
+ * `movedim(x, a, 0).reshape(x.shape[a], -1)` (activation_matching.py:26-27, 44-45) without
+ * the transposed copy.  plb_pack_split writes it as two fp32 planes hi = tf32(x) and
+ * lo = tf32(x - hi) in the tcgen05 K-major no-swizzle core-matrix order
+ *     plane[kb][g][j][r][e],  row = 8 g + r,  k = 16 kb + 4 j + e
+ * with `row_groups` (a multiple of 16) groups of 8 rows per 16-wide k-block, so that any
+ * (128·t rows x 16 k) operand tile is one contiguous run that a single cp.async.bulk can
+ * land in shared memory ready for tcgen05.mma.  Rows >= rows and k >= K are written as 0.
+ * --------------------------------------------------------------------------------------- */
+
+/* bytes of ONE plane for a [rows, K] operand; *row_groups / *k_blocks receive the padded
+ * geometry (row_groups = 16*ceil(rows/128), k_blocks = ceil(K/16)).  Host-only helper. */
+int64_t plb_plane_bytes(int64_t rows, int64_t K, int32_t *row_groups, int32_t *k_blocks);
+
+/* Splits and packs one operand; optionally accumulates per-row sum of squares and sum into
+ * fp64 vectors (atomic adds: zero them first).  `row_index` (may be NULL) gathers rows:
+ * packed row r reads source row row_index[r] (int64) — used to apply a permutation on the
+ * fly (utils.py:233-246 without the index_select copy).  kb_offset places the operand at
+ * k-block kb_offset of a plane holding several K-concatenated operands (weight matching's
+ * sum over state axes, weight_matching.py:66-75). */
+int plb_pack_split(const float *x, int64_t outer, int64_t src_rows, int64_t inner,
+                   const int64_t *row_index, int64_t rows,
+                   float *hi, float *lo, int32_t row_groups, int32_t kb_offset,
+                   double *row_sumsq, double *row_sum, void *stream);
+
+/* Two-source gather-average + im2col pack for the PLeaS normal equations
+ * (pleas_merging.py:116-123, 146-147: X-bar = cat[(x1[bi1]+x2[bi2])/2, x1[bi1c], x2[bi2c]]).
+ * Packed row f = (c, dy, dx) of the merged layer input, k = (n, ho, wo).  chan1/chan2 give,
+ * per merged channel c, the source channel in x1 / x2 (-1 = absent) and scale1/scale2 the
+ * weights (0.5/0.5 merged, 1/0 or 0/1 separate).  x1, x2: [N, Cin, H, W].  With
+ * ones_row != 0 one extra all-ones row (the bias feature) is appended. */
+int plb_pack_im2col(const float *x1, const float *x2, int64_t N, int64_t cin_src, int64_t H, int64_t W,
+                    const int32_t *chan1, const int32_t *chan2, const float *scale1, const float *scale2,
+                    int64_t cmerged, int32_t kh, int32_t kw, int32_t stride_h, int32_t stride_w,
+                    int32_t pad_h, int32_t pad_w, int32_t dil_h, int32_t dil_w, int64_t Ho, int64_t Wo,
+                    int32_t ones_row, float *hi, float *lo, int32_t row_groups, int32_t kb_offset,
+                    void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * 3xTF32 tcgen05 GEMM over packed planes:  partial[s] = A[:, Ks] B[:, Ks]^T per K split s.
+ * One table entry per problem; problems sharing a tile width are launched together
+ * (grouped launch).  The table lives in DEVICE memory (build it once per plan).
+ * --------------------------------------------------------------------------------------- */
+typedef struct PlbGemmProblem {
+  const float *a_hi, *a_lo; /* A planes */
+  const float *b_hi, *b_lo; /* B planes */
+  float *partial;           /* [splits][m_tiles*128][n_tiles*bn] fp32 */
+  int32_t a_row_groups, b_row_groups;
+  int32_t k_blocks;         /* 16-wide k-blocks to contract */
+  int32_t m_tiles, n_tiles, splits;
+  int32_t cta_begin;        /* first CTA of this problem in the grouped grid */
+  int32_t symmetric;        /* 1: A and B are the same operand; only tiles with n0+bn > m0 run */
+} PlbGemmProblem;
+
+/* bn in {64,128,256}.  total_ctas = sum over problems of m_tiles*n_tiles*splits.
+ * impl: 0 = tcgen05 3xTF32 (product path), 1 = SIMT fp32 FMA reference kernel on the same
+ * planes (debug / cross-check only). */
+int plb_gemm_grouped(const PlbGemmProblem *problems_dev, int32_t n_problems, int32_t total_ctas,
+                     int32_t bn, int32_t impl, void *stream);
+
+/* Sums the K-split partials and applies the cross-statistic epilogue
+ *   cost[i, j] (+)= f(G_ij, qa_i, qb_j)      i < M, j < N
+ * (activation_matching.py:28, 46; per-group accumulation :129-134).  accumulate = 0
+ * overwrites.  cost64 != NULL selects an fp64 accumulator (normal equations). */
+int plb_cross_finalize(const float *partial, int32_t splits, int64_t ld_m, int64_t ld_n,
+                       int64_t M, int64_t N, const double *qa, const double *qb, int32_t mode,
+                       float *cost, double *cost64, int64_t ldc, int32_t accumulate, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Batched linear sum assignment — replaces scipy_solve_lsa (pleas/core/solvers.py:18-33,
+ * SciPy's Crouse shortest-augmenting-path in float64) including its tie-breaking rules, so
+ * the returned assignment is identical to SciPy's.  One CTA per problem.
+ * cost[p]: [n_p, n_p] fp32 row-major with leading dimension ld_p; col4row[p]: int64[n_p];
+ * objective[p]: sum_i cost[i, col4row[i]] in fp64; status[p]: 0 ok, 1 infeasible, 2 NaN/-inf.
+ * The four arrays-of-pointers / sizes are DEVICE arrays of length n_problems. n_p <= 4096.
+ * --------------------------------------------------------------------------------------- */
+int plb_lap_solve_batched(const float *const *cost, const int32_t *n, const int32_t *ld,
+                          int64_t *const *col4row, double *objective, int32_t *status,
+                          int32_t n_problems, int32_t max_n, int32_t maximize, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * partial_merge building blocks (pleas/methods/partial_matching.py:47-176)
+ * --------------------------------------------------------------------------------------- */
+
+/* get_blocks for one group (:76-86): c_i = cost[i, P_i] (P = arange when identity != 0),
+ * threshold = torch.quantile(c, ratio) (linear interpolation, fp32), mask = c >= threshold;
+ * writes the order-preserving index lists Q[mask], P[mask], Q[~mask], P[~mask] (int64,
+ * capacity n each) and counts[0] = number merged.  n <= 4096. */
+int plb_get_blocks(const float *cost, int64_t ldc, const int64_t *perm, int32_t n, float ratio,
+                   int32_t identity, int64_t *q_merged, int64_t *p_merged, int64_t *q_sep,
+                   int64_t *p_sep, int32_t *counts, void *stream);
+
+/* build_partial_merge_model's tensor assembly (:112-176) for one tensor viewed as
+ * [O, I, R] (R = trailing elements per (o, i), e.g. kh*kw).  Output [no+2mo, ni+2mi, R].
+ * Index lists may be NULL (= that axis is not in a permutation group: identity, no
+ * separate part).  in_axis_only != 0 selects the 1-axis concatenation along axis 1 (:122-129),
+ * where separate input units are copied un-halved. */
+int plb_block_merge(const float *w1, const float *w2, int64_t O, int64_t I, int64_t R,
+                    const int64_t *bo1, const int64_t *bo2, const int64_t *bo1c, const int64_t *bo2c,
+                    int64_t no, int64_t mo,
+                    const int64_t *bi1, const int64_t *bi2, const int64_t *bi1c, const int64_t *bi2c,
+                    int64_t ni, int64_t mi, int32_t in_axis_only, float *out, void *stream);
+
+/* apply_perm for one state axis (pleas/core/utils.py:244): out[o, p, i] = in[o, P[p], i]. */
+int plb_gather_axis(const float *in, float *out, int64_t outer, int64_t n, int64_t inner,
+                    const int64_t *P, void *stream);
+
+/* perm composition (weight_matching.py:85): out[i] = a[b[i]] on int64. */
+int plb_compose_perm(const int64_t *a, const int64_t *b, int64_t *out, int64_t n, void *stream);
+
+/* weight_matching's progress test (weight_matching.py:80-81): *flag |= (sum_i A[i,P_i] >
+ * sum_i A[i,i] + 1e-12), sums in fp64 of the fp32 entries. */
+int plb_wm_progress(const float *A, int64_t ld, const int64_t *P, int32_t n, int32_t *flag,
+                    double *gain, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * PLeaS closed form: solve (G + ridge*I) X = B for symmetric positive definite G (fp64,
+ * column/row symmetric so layout-agnostic), in place: G is overwritten by its Cholesky
+ * factor (lower), B [n, nrhs] row-major by the solution.  Replaces the Adam loop of
+ * pleas/methods/pleas_merging.py:357-375.  info (device int32): 0 ok, k>0 = pivot k-1 was
+ * not positive (after the ridge).  Not graph-capturable (launch count depends on n).
+ * --------------------------------------------------------------------------------------- */
+int plb_chol_solve(double *G, int64_t n, double *B, int64_t nrhs, double ridge, int32_t *info,
+                   void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLEAS_B200_H */

@@ -1,0 +1,58 @@
+// Split-K reduction + cross-statistic epilogue.
+//   cost[i, j] (+)= f(G_ij, qa_i, qb_j),   G = sum over K splits of the GEMM partial tiles
+// f = identity            : cross_features_inner_product (activation_matching.py:14-28) and the
+//                           weight-matching / normal-equation Grams
+// f = -sqrt(max(.,0))     : cross_features_cdist (activation_matching.py:31-46) — ATen's
+//                           _euclidean_dist: qa_i + qb_j - 2 G_ij, clamp_min(0), sqrt, then neg
+// Splits are summed in a fixed order, so the result is deterministic.  HBM-bound: reads
+// splits*M*N fp32, writes M*N.
+#include "common.cuh"
+
+namespace plb {
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) cross_finalize_kernel(const float *__restrict__ partial, int splits,
+                                                             int64_t ld_m, int64_t ld_n, int64_t M, int64_t N,
+                                                             const double *__restrict__ qa,
+                                                             const double *__restrict__ qb, int mode,
+                                                             OutT *__restrict__ cost, int64_t ldc, int accumulate) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j >= N) return;
+  const int64_t split_stride = ld_m * ld_n;
+  const float *p = partial + i * ld_n + j;
+  double gs = 0.0;  // fp64 sum of the (short-chain) split partials
+  for (int s = 0; s < splits; ++s) gs += (double)p[(int64_t)s * split_stride];
+  const float g = (float)gs;
+  float v = g;
+  if (mode == PLB_MODE_NEG_CDIST) {
+    const float d2 = ((float)qa[i] + (float)qb[j]) - 2.0f * g;
+    v = -sqrtf(fmaxf(d2, 0.f));
+  }
+  OutT *c = cost + i * ldc + j;
+  const OutT add = (sizeof(OutT) == 8 && mode == PLB_MODE_INNER) ? (OutT)gs : (OutT)v;
+  *c = accumulate ? (OutT)(*c + add) : add;
+}
+
+}  // namespace plb
+
+extern "C" int plb_cross_finalize(const float *partial, int32_t splits, int64_t ld_m, int64_t ld_n, int64_t M,
+                                  int64_t N, const double *qa, const double *qb, int32_t mode, float *cost,
+                                  double *cost64, int64_t ldc, int32_t accumulate, void *stream) {
+  using namespace plb;
+  PLB_REQUIRE(partial && (cost || cost64), PLB_EINVAL, "plb_cross_finalize: null pointer");
+  PLB_REQUIRE(splits > 0 && M > 0 && N > 0 && M <= ld_m && N <= ld_n && ldc >= N, PLB_EINVAL,
+              "plb_cross_finalize: bad geometry");
+  PLB_REQUIRE(mode == PLB_MODE_INNER || (mode == PLB_MODE_NEG_CDIST && qa && qb), PLB_EINVAL,
+              "plb_cross_finalize: mode needs row norms");
+  PLB_REQUIRE(M <= 65535, PLB_ESIZE, "plb_cross_finalize: M too large");
+  dim3 grid((unsigned)ceil_div(N, 256), (unsigned)M);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cost64)
+    cross_finalize_kernel<double><<<grid, 256, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost64, ldc,
+                                                       accumulate);
+  else
+    cross_finalize_kernel<float><<<grid, 256, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost, ldc,
+                                                      accumulate);
+  return launch_status("cross_finalize_kernel");
+}

@@ -1,0 +1,263 @@
+// Batched linear sum assignment on the GPU — replaces scipy_solve_lsa
+// (pleas/core/solvers.py:18-33), i.e. SciPy's Crouse shortest-augmenting-path solver run in
+// float64 on the float32 cost matrix (negated for maximize), behind a D2H copy and sync.
+//
+// One CTA per problem, all problems of a call in one launch (activation matching solves its
+// 37 / 71 groups together; weight matching one at a time).  The algorithm is SciPy's, step
+// for step, so the answer is the same assignment even when optima tie:
+//   * rows are inserted in order; each insertion is a Dijkstra search over reduced costs
+//     r = ((min + c[i,j]) - u[i]) - v[j] in fp64 with the same association order;
+//   * the not-yet-scanned columns live in a list `todo` filled in reverse and compacted by
+//     moving its last element into the freed slot;
+//   * among columns at the minimum tentative distance an unassigned one wins (the LAST such
+//     list position), otherwise the FIRST list position.
+// What is parallel: the per-iteration relaxation + arg-min over the todo list (one column per
+// thread-stride, warp-shuffle (value, rank) min, one shared-memory combine), the dual
+// updates and the initialisation.  What is sequential: the Dijkstra iterations themselves
+// and the final path flip (one thread).  All solver state lives in shared memory
+// (45 B per column: n <= 4096 fits the 227 KB CTA limit); only the cost row is read from
+// global/L2 per iteration, coalesced.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace plb {
+
+struct LapSmem {  // carved from dynamic shared memory for a given n
+  double *u, *v, *dist;
+  int *pred, *row4col, *col4row, *todo, *rows_seen, *cols_seen;
+};
+
+__device__ __forceinline__ LapSmem carve(uint8_t *base, int n) {
+  LapSmem s;
+  s.u = (double *)base;
+  s.v = s.u + n;
+  s.dist = s.v + n;
+  s.pred = (int *)(s.dist + n);
+  s.row4col = s.pred + n;
+  s.col4row = s.row4col + n;
+  s.todo = s.col4row + n;
+  s.rows_seen = s.todo + n;
+  s.cols_seen = s.rows_seen + n;
+  return s;
+}
+static inline size_t lap_smem_bytes(int n) { return (size_t)n * (3 * 8 + 6 * 4) + 64; }
+
+struct Cand {
+  double d;
+  int rank;  // smaller wins among equal d: sinks get [0,n) by descending list position, others [n,2n) ascending
+};
+__device__ __forceinline__ bool better(const Cand &a, const Cand &b) {
+  return a.d < b.d || (a.d == b.d && a.rank < b.rank);
+}
+__device__ __forceinline__ Cand shfl_xor(const Cand &c, int m) {
+  Cand o;
+  o.d = __shfl_xor_sync(0xffffffffu, c.d, m);
+  o.rank = __shfl_xor_sync(0xffffffffu, c.rank, m);
+  return o;
+}
+
+__global__ void __launch_bounds__(1024, 1) lap_kernel(const float *const *__restrict__ costs,
+                                                      const int32_t *__restrict__ ns,
+                                                      const int32_t *__restrict__ lds, int64_t *const *__restrict__ outs,
+                                                      double *__restrict__ objective, int32_t *__restrict__ status,
+                                                      int maximize) {
+  extern __shared__ __align__(16) uint8_t lap_smem[];
+  __shared__ Cand warp_best[32];
+  __shared__ double sh_min;
+  __shared__ int sh_row, sh_sink, sh_ntodo, sh_nrows, sh_ncols, sh_bad;
+
+  const int prob = blockIdx.x;
+  const int n = ns[prob];
+  const int64_t ld = lds[prob];
+  const float *__restrict__ C = costs[prob];
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = nthr >> 5;
+  const double sgn = maximize ? -1.0 : 1.0;
+  LapSmem s = carve(lap_smem, n);
+
+  if (tid == 0) sh_bad = 0;
+  for (int k = tid; k < n; k += nthr) {
+    s.u[k] = 0.0;
+    s.v[k] = 0.0;
+    s.pred[k] = -1;
+    s.row4col[k] = -1;
+    s.col4row[k] = -1;
+  }
+  __syncthreads();
+  // NaN / -inf screen (SciPy returns an error for those)
+  {
+    int bad = 0;
+    for (int i = 0; i < n; ++i) {
+      const float *__restrict__ crow = C + (int64_t)i * ld;
+      for (int j = tid; j < n; j += nthr) {
+        const double x = sgn * (double)__ldg(crow + j);
+        if (x != x || x == -INFINITY) bad = 1;
+      }
+    }
+    if (bad) sh_bad = 1;
+  }
+  __syncthreads();
+  if (sh_bad) {
+    if (tid == 0) {
+      status[prob] = 2;
+      objective[prob] = 0.0;
+    }
+    return;
+  }
+
+  int result = 0;
+  for (int cur = 0; cur < n; ++cur) {
+    for (int k = tid; k < n; k += nthr) {
+      s.dist[k] = INFINITY;
+      s.todo[k] = n - 1 - k;
+    }
+    if (tid == 0) {
+      sh_min = 0.0;
+      sh_row = cur;
+      sh_sink = -1;
+      sh_ntodo = n;
+      sh_nrows = 0;
+      sh_ncols = 0;
+    }
+    __syncthreads();
+
+    while (true) {
+      const int row = sh_row;
+      const int ntodo = sh_ntodo;
+      const double min_val = sh_min;
+      const double u_row = s.u[row];
+      const float *__restrict__ crow = C + (int64_t)row * ld;
+      Cand best;
+      best.d = INFINITY;
+      best.rank = 0x7fffffff;
+      for (int t = tid; t < ntodo; t += nthr) {
+        const int j = s.todo[t];
+        const double c = sgn * (double)__ldg(crow + j);
+        const double r = __dsub_rn(__dsub_rn(__dadd_rn(min_val, c), u_row), s.v[j]);
+        double dj = s.dist[j];
+        if (r < dj) {
+          s.pred[j] = row;
+          s.dist[j] = r;
+          dj = r;
+        }
+        Cand c2;
+        c2.d = dj;
+        c2.rank = (s.row4col[j] < 0) ? (n - 1 - t) : (n + t);
+        if (better(c2, best)) best = c2;
+      }
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        const Cand o = shfl_xor(best, m);
+        if (better(o, best)) best = o;
+      }
+      if (lane == 0) warp_best[warp] = best;
+      __syncthreads();
+      if (warp == 0) {
+        Cand b = (lane < nwarps) ? warp_best[lane] : Cand{INFINITY, 0x7fffffff};
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+          const Cand o = shfl_xor(b, m);
+          if (better(o, b)) b = o;
+        }
+        if (lane == 0) {
+          if (b.d == INFINITY) {
+            sh_sink = -2;  // infeasible
+          } else {
+            const int t = (b.rank < n) ? (n - 1 - b.rank) : (b.rank - n);
+            const int j = s.todo[t];
+            s.rows_seen[sh_nrows++] = row;
+            s.cols_seen[sh_ncols++] = j;
+            sh_min = b.d;
+            if (s.row4col[j] < 0) sh_sink = j; else sh_row = s.row4col[j];
+            s.todo[t] = s.todo[ntodo - 1];
+            sh_ntodo = ntodo - 1;
+          }
+        }
+      }
+      __syncthreads();
+      if (sh_sink != -1) break;
+    }
+    if (sh_sink == -2) {
+      result = 1;
+      break;
+    }
+
+    // dual update (rows_seen[0] == cur; row k>0 was reached through column cols_seen[k-1])
+    const double min_val = sh_min;
+    const int nrows = sh_nrows, ncols = sh_ncols;
+    for (int k = tid; k < nrows; k += nthr) {
+      const int i = s.rows_seen[k];
+      if (k == 0) s.u[i] = __dadd_rn(s.u[i], min_val);
+      else s.u[i] = __dadd_rn(s.u[i], __dsub_rn(min_val, s.dist[s.col4row[i]]));
+    }
+    for (int k = tid; k < ncols; k += nthr) {
+      const int j = s.cols_seen[k];
+      s.v[j] = __dsub_rn(s.v[j], __dsub_rn(min_val, s.dist[j]));
+    }
+    __syncthreads();
+    if (tid == 0) {  // flip the augmenting path
+      int j = sh_sink;
+      while (true) {
+        const int i = s.pred[j];
+        s.row4col[j] = i;
+        const int prev = s.col4row[i];
+        s.col4row[i] = j;
+        j = prev;
+        if (i == cur) break;
+      }
+    }
+    __syncthreads();
+  }
+
+  if (result != 0) {
+    if (tid == 0) {
+      status[prob] = result;
+      objective[prob] = 0.0;
+    }
+    return;
+  }
+  // outputs: int64 column per row + fp64 objective on the caller's (un-negated) costs
+  int64_t *out = outs[prob];
+  double part = 0.0;
+  for (int i = tid; i < n; i += nthr) {
+    const int j = s.col4row[i];
+    out[i] = (int64_t)j;
+    part += (double)C[(int64_t)i * ld + j];
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+  if (lane == 0) warp_best[warp].d = part;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int wq = 0; wq < nwarps; ++wq) tot += warp_best[wq].d;
+    objective[prob] = tot;
+    status[prob] = 0;
+  }
+}
+
+}  // namespace plb
+
+extern "C" int plb_lap_solve_batched(const float *const *cost, const int32_t *n, const int32_t *ld,
+                                     int64_t *const *col4row, double *objective, int32_t *status,
+                                     int32_t n_problems, int32_t max_n, int32_t maximize, void *stream) {
+  using namespace plb;
+  PLB_REQUIRE(cost && n && ld && col4row && objective && status, PLB_EINVAL, "plb_lap_solve_batched: null pointer");
+  PLB_REQUIRE(n_problems > 0 && max_n > 0, PLB_EINVAL, "plb_lap_solve_batched: empty batch");
+  PLB_REQUIRE(max_n <= 4096, PLB_ESIZE, "plb_lap_solve_batched: n > 4096 exceeds the shared-memory working set");
+  const size_t smem = lap_smem_bytes(max_n);
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(lap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(lap_kernel, %zu): %s", smem, cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = smem;
+  }
+  int threads = (int)(ceil_div(max_n, 64) * 32);  // ~2 columns per thread
+  threads = threads < 64 ? 64 : (threads > 1024 ? 1024 : threads);
+  lap_kernel<<<n_problems, threads, smem, (cudaStream_t)stream>>>(cost, n, ld, col4row, objective, status, maximize);
+  return launch_status("lap_kernel");
+}

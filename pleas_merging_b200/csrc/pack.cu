@@ -1,0 +1,212 @@
+// Operand packing for the 3xTF32 tcgen05 GEMM (gemm.cu): one pass over the source tensor
+// that (a) replaces the reference's `movedim(x, a, 0).reshape(C, -1)` transposed copy
+// (activation_matching.py:26-27, 44-45), (b) splits every fp32 value into tf32 hi + tf32 lo,
+// (c) writes both in tcgen05's K-major core-matrix order and (d) accumulates the per-row
+// sum of squares / sum the -cdist and correlation epilogues need, so the activation is read
+// from HBM exactly once.
+//
+// Thread mapping: a warp owns one (8 rows x 16 k) panel per iteration; lane = 8*jj + r reads
+// 4 consecutive k of row r (jj-th 16-byte chunk) and writes them as one float4, so a warp's
+// store is one contiguous 512-byte panel per plane and its load is 8 rows x 64 contiguous
+// bytes; the 8 warps of a block walk consecutive k-blocks, i.e. 512 contiguous bytes per row.
+#include "common.cuh"
+
+namespace plb {
+
+constexpr int kKbPerBlock = 64;
+
+__device__ __forceinline__ void split_store(const float (&v)[4], float *hi, float *lo, int64_t off) {
+  float4 h, l;
+  h.x = to_tf32(v[0]); l.x = to_tf32(v[0] - h.x);
+  h.y = to_tf32(v[1]); l.y = to_tf32(v[1] - h.y);
+  h.z = to_tf32(v[2]); l.z = to_tf32(v[2] - h.z);
+  h.w = to_tf32(v[3]); l.w = to_tf32(v[3] - h.w);
+  *reinterpret_cast<float4 *>(hi + off) = h;
+  *reinterpret_cast<float4 *>(lo + off) = l;
+}
+
+// block-level reduction of the per-thread row statistics and one fp64 atomic per row per block
+__device__ __forceinline__ void reduce_row_stats(float s2, float s1, int row, int rows, double *sumsq, double *sum) {
+  __shared__ float red[2][8][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+  s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 8);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  if (lane < 8) {
+    red[0][warp][lane] = s2;
+    red[1][warp][lane] = s1;
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && row < rows) {
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) {
+      a += (double)red[0][wq][threadIdx.x];
+      b += (double)red[1][wq][threadIdx.x];
+    }
+    if (sumsq) atomicAdd(sumsq + row, a);
+    if (sum) atomicAdd(sum + row, b);
+  }
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(256) pack_split_kernel(const float *__restrict__ x, int64_t src_rows, uint32_t inner,
+                                                         uint32_t K, const int64_t *__restrict__ row_index, int rows,
+                                                         float *__restrict__ hi, float *__restrict__ lo,
+                                                         int row_groups, int kb_offset, int k_blocks,
+                                                         double *__restrict__ sumsq, double *__restrict__ sum) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = lane & 7, jj = lane >> 3;
+  const int g = blockIdx.y;
+  const int row = g * 8 + r;
+  const bool row_ok = row < rows;
+  const int64_t src_row = row_ok ? (row_index ? row_index[row] : (int64_t)row) : 0;
+  const int kb_end = min(k_blocks, (int)(blockIdx.x + 1) * kKbPerBlock);
+  float s2 = 0.f, s1 = 0.f;
+#pragma unroll 2
+  for (int kb = blockIdx.x * kKbPerBlock + warp; kb < kb_end; kb += 8) {
+    const uint32_t k = (uint32_t)kb * kPackK + jj * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row_ok) {
+      if (VEC4) {
+        if (k < K) {
+          const uint32_t o = k / inner, i = k - o * inner;
+          const float4 t = __ldg(reinterpret_cast<const float4 *>(x + ((int64_t)o * src_rows + src_row) * inner + i));
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t ke = k + e;
+          if (ke < K) {
+            const uint32_t o = ke / inner, i = ke - o * inner;
+            v[e] = __ldg(x + ((int64_t)o * src_rows + src_row) * inner + i);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      s2 = fmaf(v[e], v[e], s2);
+      s1 += v[e];
+    }
+    split_store(v, hi, lo, panel_offset(kb_offset + kb, g, row_groups) + (jj * 8 + r) * 4);
+  }
+  if (sumsq || sum) reduce_row_stats(s2, s1, g * 8 + (int)threadIdx.x, rows, sumsq, sum);
+}
+
+struct Im2colGeom {
+  int64_t N, cin_src, H, W, Ho, Wo, cmerged;
+  int kh, kw, sh, sw, ph, pw, dh, dw, ones_row;
+};
+
+__global__ void __launch_bounds__(256) pack_im2col_kernel(const float *__restrict__ x1, const float *__restrict__ x2,
+                                                          const int32_t *__restrict__ chan1,
+                                                          const int32_t *__restrict__ chan2,
+                                                          const float *__restrict__ scale1,
+                                                          const float *__restrict__ scale2, Im2colGeom gm, int rows,
+                                                          uint32_t K, float *__restrict__ hi, float *__restrict__ lo,
+                                                          int row_groups, int kb_offset, int k_blocks) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = lane & 7, jj = lane >> 3;
+  const int g = blockIdx.y;
+  const int row = g * 8 + r;
+  const int taps = gm.kh * gm.kw;
+  const int feat_rows = (int)gm.cmerged * taps;
+  // decode the feature row once: (c, dy, dx)
+  int c1 = -1, c2 = -1, dy = 0, dx = 0;
+  float w1 = 0.f, w2 = 0.f;
+  const bool is_ones = gm.ones_row && row == feat_rows;
+  if (row < feat_rows) {
+    const int c = row / taps, t = row - c * taps;
+    dy = t / gm.kw;
+    dx = t - dy * gm.kw;
+    c1 = chan1 ? chan1[c] : c;
+    c2 = chan2 ? chan2[c] : -1;
+    w1 = scale1 ? scale1[c] : 1.f;
+    w2 = scale2 ? scale2[c] : 0.f;
+  }
+  const uint32_t HoWo = (uint32_t)(gm.Ho * gm.Wo);
+  const int64_t plane = gm.H * gm.W;
+  const int kb_end = min(k_blocks, (int)(blockIdx.x + 1) * kKbPerBlock);
+  for (int kb = blockIdx.x * kKbPerBlock + warp; kb < kb_end; kb += 8) {
+    const uint32_t k = (uint32_t)kb * kPackK + jj * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < rows) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t ke = k + e;
+        if (ke >= K) continue;
+        if (is_ones) {
+          v[e] = 1.f;
+          continue;
+        }
+        const uint32_t n = ke / HoWo, p = ke - n * HoWo;
+        const int ho = (int)(p / (uint32_t)gm.Wo), wo = (int)(p - (uint32_t)ho * (uint32_t)gm.Wo);
+        const int h = ho * gm.sh - gm.ph + dy * gm.dh, wq = wo * gm.sw - gm.pw + dx * gm.dw;
+        if (h < 0 || h >= gm.H || wq < 0 || wq >= gm.W) continue;
+        const int64_t sp = (int64_t)h * gm.W + wq;
+        float a = 0.f, b = 0.f;
+        if (c1 >= 0) a = __ldg(x1 + ((int64_t)n * gm.cin_src + c1) * plane + sp);
+        if (c2 >= 0) b = __ldg(x2 + ((int64_t)n * gm.cin_src + c2) * plane + sp);
+        // (a + b) / 2 for merged channels: exact products, one rounding of the sum
+        v[e] = fmaf(w1, a, w2 * b);
+      }
+    }
+    split_store(v, hi, lo, panel_offset(kb_offset + kb, g, row_groups) + (jj * 8 + r) * 4);
+  }
+}
+
+}  // namespace plb
+
+extern "C" int plb_pack_split(const float *x, int64_t outer, int64_t src_rows, int64_t inner,
+                              const int64_t *row_index, int64_t rows, float *hi, float *lo, int32_t row_groups,
+                              int32_t kb_offset, double *row_sumsq, double *row_sum, void *stream) {
+  using namespace plb;
+  PLB_REQUIRE(x && hi && lo, PLB_EINVAL, "plb_pack_split: null pointer");
+  PLB_REQUIRE(outer > 0 && src_rows > 0 && inner > 0 && rows > 0, PLB_EINVAL, "plb_pack_split: empty operand");
+  PLB_REQUIRE(row_index != nullptr || rows <= src_rows, PLB_EINVAL, "plb_pack_split: rows > src_rows without index");
+  const int64_t K = outer * inner;
+  PLB_REQUIRE(K < (int64_t)1 << 31 && inner < (int64_t)1 << 31, PLB_ESIZE, "plb_pack_split: K too large");
+  PLB_REQUIRE(row_groups % 16 == 0 && (int64_t)row_groups * 8 >= rows, PLB_EINVAL,
+              "plb_pack_split: row_groups must be a multiple of 16 covering rows");
+  PLB_REQUIRE(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0, PLB_EALIGN, "plb_pack_split: planes unaligned");
+  const int k_blocks = (int)ceil_div(K, kPackK);
+  dim3 grid((unsigned)ceil_div(k_blocks, kKbPerBlock), (unsigned)ceil_div(rows, 8));
+  PLB_REQUIRE(grid.y <= 65535, PLB_ESIZE, "plb_pack_split: too many rows");
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool vec4 = (inner % 4 == 0) && (((uintptr_t)x & 15) == 0);
+  if (vec4)
+    pack_split_kernel<true><<<grid, 256, 0, s>>>(x, src_rows, (uint32_t)inner, (uint32_t)K, row_index, (int)rows, hi,
+                                                 lo, row_groups, kb_offset, k_blocks, row_sumsq, row_sum);
+  else
+    pack_split_kernel<false><<<grid, 256, 0, s>>>(x, src_rows, (uint32_t)inner, (uint32_t)K, row_index, (int)rows, hi,
+                                                  lo, row_groups, kb_offset, k_blocks, row_sumsq, row_sum);
+  return launch_status("pack_split_kernel");
+}
+
+extern "C" int plb_pack_im2col(const float *x1, const float *x2, int64_t N, int64_t cin_src, int64_t H, int64_t W,
+                               const int32_t *chan1, const int32_t *chan2, const float *scale1, const float *scale2,
+                               int64_t cmerged, int32_t kh, int32_t kw, int32_t stride_h, int32_t stride_w,
+                               int32_t pad_h, int32_t pad_w, int32_t dil_h, int32_t dil_w, int64_t Ho, int64_t Wo,
+                               int32_t ones_row, float *hi, float *lo, int32_t row_groups, int32_t kb_offset,
+                               void *stream) {
+  using namespace plb;
+  PLB_REQUIRE(x1 && hi && lo, PLB_EINVAL, "plb_pack_im2col: null pointer");
+  PLB_REQUIRE(N > 0 && cin_src > 0 && H > 0 && W > 0 && Ho > 0 && Wo > 0 && cmerged > 0 && kh > 0 && kw > 0,
+              PLB_EINVAL, "plb_pack_im2col: empty geometry");
+  PLB_REQUIRE(x2 != nullptr || chan2 == nullptr, PLB_EINVAL, "plb_pack_im2col: chan2 given without x2");
+  const int64_t rows = cmerged * kh * kw + (ones_row ? 1 : 0);
+  const int64_t K = N * Ho * Wo;
+  PLB_REQUIRE(K < (int64_t)1 << 31, PLB_ESIZE, "plb_pack_im2col: K too large");
+  PLB_REQUIRE(row_groups % 16 == 0 && (int64_t)row_groups * 8 >= rows, PLB_EINVAL,
+              "plb_pack_im2col: row_groups must be a multiple of 16 covering rows");
+  Im2colGeom gm{N, cin_src, H, W, Ho, Wo, cmerged, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, ones_row};
+  const int k_blocks = (int)ceil_div(K, kPackK);
+  dim3 grid((unsigned)ceil_div(k_blocks, kKbPerBlock), (unsigned)ceil_div(rows, 8));
+  PLB_REQUIRE(grid.y <= 65535, PLB_ESIZE, "plb_pack_im2col: too many rows");
+  pack_im2col_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x1, x2, chan1, chan2, scale1, scale2, gm, (int)rows,
+                                                            (uint32_t)K, hi, lo, row_groups, kb_offset, k_blocks);
+  return launch_status("pack_im2col_kernel");
+}

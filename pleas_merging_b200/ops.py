@@ -1,0 +1,305 @@
+"""Tensor-level wrappers over the C ABI (include/pleas_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every arithmetic
+step is one of the library's sm_100a kernels.  Nothing in this module falls back to a CPU or
+torch implementation.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import _native as N
+
+MODE_INNER, MODE_NEG_CDIST = 0, 1
+NUM_SMS = 148
+# PLB_GEMM_IMPL=simt selects the SIMT fp32 cross-check kernel (debugging only; still CUDA)
+_GEMM_IMPL = {"tcgen05": 0, "simt": 1}[os.environ.get("PLB_GEMM_IMPL", "tcgen05")]
+
+
+def set_gemm_impl(name):
+    global _GEMM_IMPL
+    _GEMM_IMPL = {"tcgen05": 0, "simt": 1}[name]
+
+
+def _require_cuda_f32(t, what):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32):
+        raise TypeError(f"{what}: expected a float32 CUDA tensor, got "
+                        f"{type(t).__name__} {getattr(t, 'dtype', None)} on {getattr(t, 'device', None)}")
+
+
+def plane_geometry(rows, K):
+    """(row_groups, k_blocks, floats per plane) of the packed layout."""
+    rg = 16 * ((rows + 127) // 128)
+    kb = (K + 15) // 16
+    return rg, kb, rg * kb * 128
+
+
+class Planes:
+    """hi/lo packed planes of one [rows, K] operand (or several K-concatenated ones)."""
+
+    def __init__(self, rows, k_blocks, device):
+        self.rows = rows
+        self.row_groups = 16 * ((rows + 127) // 128)
+        self.k_blocks = k_blocks
+        n = self.row_groups * k_blocks * 128
+        # no zero-fill needed: pad row groups only feed output rows/cols nobody reads, and the
+        # pack kernel writes zeros for k >= K and for rows >= rows inside real groups
+        self.hi = torch.empty(n, dtype=torch.float32, device=device)
+        self.lo = torch.empty(n, dtype=torch.float32, device=device)
+
+
+def as_rows_view(x, axis):
+    """[outer, rows, inner] view of a contiguous tensor for axis `axis` (the reference's
+    movedim+reshape, activation_matching.py:26-27, without the copy)."""
+    axis = axis % x.dim()
+    outer = 1
+    for s in x.shape[:axis]:
+        outer *= s
+    inner = 1
+    for s in x.shape[axis + 1:]:
+        inner *= s
+    return outer, x.shape[axis], inner
+
+
+def pack_split(x, axis, planes, kb_offset=0, row_index=None, rows=None, sumsq=None, rowsum=None):
+    """Packs the [rows, K] operand view of x along `axis` into planes at k-block kb_offset.
+    Returns the number of k-blocks written."""
+    _require_cuda_f32(x, "pack_split")
+    if not x.is_contiguous():
+        x = x.contiguous()
+    outer, src_rows, inner = as_rows_view(x, axis)
+    rows = src_rows if rows is None else rows
+    K = outer * inner
+    kb = (K + 15) // 16
+    if kb_offset + kb > planes.k_blocks or rows > planes.row_groups * 8:
+        raise ValueError("pack_split: operand does not fit the planes")
+    N.check(N.lib().plb_pack_split(x.data_ptr(), outer, src_rows, inner, N.ptr(row_index), rows,
+                                   planes.hi.data_ptr(), planes.lo.data_ptr(), planes.row_groups, kb_offset,
+                                   N.ptr(sumsq), N.ptr(rowsum), N.stream_ptr()), "plb_pack_split")
+    return kb
+
+
+def choose_bn(n_rows):
+    return 64 if n_rows <= 64 else (128 if n_rows <= 128 else 256)
+
+
+# The tensor core's fp32 accumulator rounds toward zero: measured bias is -1e-7 (relative) per
+# 16-wide k-block chained into one accumulator (profiles/experiments/exp_chain_length.py), so a
+# chain is capped and the K splits are summed in fp64 by the finalize kernel.
+MAX_CHAIN_KB = int(os.environ.get("PLB_MAX_CHAIN_KB", "16"))
+
+
+def choose_splits(tiles, k_blocks, target_ctas=NUM_SMS * 4, min_kb=4):
+    """K splits: enough to bound the accumulation chain, and enough that one problem alone
+    fills the GPU (small-C taps have a single output tile and K up to 401 408)."""
+    fill = min(target_ctas // max(tiles, 1), k_blocks // min_kb)
+    chain = -(-k_blocks // MAX_CHAIN_KB)
+    return max(1, min(max(fill, chain), k_blocks))
+
+
+class GemmPlan:
+    """One 3xTF32 GEMM over packed planes: partial tiles + problem-table entry on device."""
+
+    def __init__(self, a, b, M, Nn, k_blocks, splits=None, symmetric=False):
+        self.M, self.N = M, Nn
+        self.bn = choose_bn(Nn)
+        self.m_tiles = (M + 127) // 128
+        self.n_tiles = (Nn + self.bn - 1) // self.bn
+        tiles = self.m_tiles * self.n_tiles
+        self.splits = choose_splits(tiles, k_blocks) if splits is None else splits
+        self.ld_m, self.ld_n = self.m_tiles * 128, self.n_tiles * self.bn
+        dev = a.hi.device
+        self.partial = torch.empty(self.splits * self.ld_m * self.ld_n, dtype=torch.float32, device=dev)
+        self.total_ctas = tiles * self.splits
+        p = N.GemmProblem(a.hi.data_ptr(), a.lo.data_ptr(), b.hi.data_ptr(), b.lo.data_ptr(),
+                          self.partial.data_ptr(), a.row_groups, b.row_groups, k_blocks, self.m_tiles,
+                          self.n_tiles, self.splits, 0, int(symmetric))
+        raw = bytes(p)
+        self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self._keep = (a, b)
+
+    def run(self, impl=None):
+        N.check(N.lib().plb_gemm_grouped(self.table.data_ptr(), 1, self.total_ctas, self.bn,
+                                         _GEMM_IMPL if impl is None else impl, N.stream_ptr()),
+                "plb_gemm_grouped")
+
+    def finalize(self, out, mode=MODE_INNER, qa=None, qb=None, accumulate=False):
+        """out[i, j] (+)= f(sum_s partial_s[i, j]); out fp32 or fp64 [M, N] (row stride = ldc)."""
+        if out.dtype == torch.float64:
+            c32, c64 = None, out.data_ptr()
+        else:
+            c32, c64 = out.data_ptr(), None
+        N.check(N.lib().plb_cross_finalize(self.partial.data_ptr(), self.splits, self.ld_m, self.ld_n, self.M,
+                                           self.N, N.ptr(qa), N.ptr(qb), mode, c32, c64, out.stride(0),
+                                           int(accumulate), N.stream_ptr()), "plb_cross_finalize")
+
+
+def cross_statistic(x, y, axis, mode):
+    """One tap: [x.shape[axis], y.shape[axis]] cross-statistic matrix of two activations
+    (cross_features_inner_product / cross_features_cdist, activation_matching.py:14-46)."""
+    _require_cuda_f32(x, "cross_statistic")
+    _require_cuda_f32(y, "cross_statistic")
+    oa, ra, ia = as_rows_view(x, axis)
+    ob, rb, ib = as_rows_view(y, axis)
+    if oa * ia != ob * ib:
+        raise ValueError(f"cross_statistic: contraction sizes differ ({oa * ia} vs {ob * ib})")
+    kb = (oa * ia + 15) // 16
+    dev = x.device
+    pa, pb = Planes(ra, kb, dev), Planes(rb, kb, dev)
+    need_q = mode == MODE_NEG_CDIST
+    q = torch.zeros(ra + rb, dtype=torch.float64, device=dev) if need_q else None
+    qa, qb = (q[:ra], q[ra:]) if need_q else (None, None)
+    pack_split(x, axis, pa, sumsq=qa)
+    pack_split(y, axis, pb, sumsq=qb)
+    plan = GemmPlan(pa, pb, ra, rb, kb)
+    plan.run()
+    out = torch.empty(ra, rb, dtype=torch.float32, device=dev)
+    plan.finalize(out, mode, qa, qb, accumulate=False)
+    return out
+
+
+# ------------------------------------------------------------------------------------ LAP
+
+def lap_solve_batched(costs, maximize=True):
+    """Solves all square problems in one launch.  Returns (list of int64 CUDA tensors,
+    objective fp64 CUDA tensor, status int32 CUDA tensor)."""
+    if not costs:
+        return [], None, None
+    dev = costs[0].device
+    mats = []
+    for c in costs:
+        _require_cuda_f32(c, "lap_solve_batched")
+        if c.dim() != 2 or c.shape[0] != c.shape[1]:
+            raise ValueError(f"lap_solve_batched: square cost matrices only, got {tuple(c.shape)}")
+        mats.append(c if c.stride(1) == 1 else c.contiguous())
+    ns = [m.shape[0] for m in mats]
+    outs = [torch.empty(n, dtype=torch.int64, device=dev) for n in ns]
+    table = torch.tensor([[m.data_ptr() for m in mats], [o.data_ptr() for o in outs]], dtype=torch.int64).to(dev)
+    meta = torch.tensor([ns, [m.stride(0) for m in mats]], dtype=torch.int32).to(dev)
+    obj = torch.empty(len(mats), dtype=torch.float64, device=dev)
+    status = torch.empty(len(mats), dtype=torch.int32, device=dev)
+    N.check(N.lib().plb_lap_solve_batched(table[0].data_ptr(), meta[0].data_ptr(), meta[1].data_ptr(),
+                                          table[1].data_ptr(), obj.data_ptr(), status.data_ptr(), len(mats),
+                                          max(ns), int(bool(maximize)), N.stream_ptr()), "plb_lap_solve_batched")
+    return outs, obj, status
+
+
+def raise_on_lap_status(status):
+    st = status.cpu()
+    if (st == 2).any():
+        raise ValueError("matrix contains invalid numeric entries")  # SciPy's message
+    if (st == 1).any():
+        raise ValueError("cost matrix is infeasible")
+
+
+# ------------------------------------------------------------------------------------ blocks
+
+def get_blocks_group(cost, perm, ratio, identity):
+    """(Q[mask], P[mask], Q[~mask], P[~mask]) for one group (partial_matching.py:76-86)."""
+    _require_cuda_f32(cost, "get_blocks_group")
+    n = cost.shape[0]
+    dev = cost.device
+    buf = torch.empty(4, n, dtype=torch.int64, device=dev)
+    counts = torch.zeros(1, dtype=torch.int32, device=dev)
+    perm = perm.to(device=dev, dtype=torch.int64).contiguous()
+    N.check(N.lib().plb_get_blocks(cost.data_ptr(), cost.stride(0), perm.data_ptr(), n, float(ratio), int(identity),
+                                   buf[0].data_ptr(), buf[1].data_ptr(), buf[2].data_ptr(), buf[3].data_ptr(),
+                                   counts.data_ptr(), N.stream_ptr()), "plb_get_blocks")
+    m = int(counts.item())
+    return buf[0, :m], buf[1, :m], buf[2, :n - m], buf[3, :n - m]
+
+
+def _prod(xs):
+    r = 1
+    for v in xs:
+        r *= v
+    return r
+
+
+def block_merge(w1, w2, blocks_by_axis):
+    """Assembles one merged tensor (partial_matching.py:112-176).  blocks_by_axis maps the
+    tensor's blocked axes ({0}, {1}, {k} or {0, 1}) to (b1, b2, b1c, b2c) int64 CUDA index
+    tensors."""
+    _require_cuda_f32(w1, "block_merge")
+    _require_cuda_f32(w2, "block_merge")
+    w1, w2 = w1.contiguous(), w2.contiguous()
+    shape = list(w1.shape)
+    axes = sorted(blocks_by_axis)
+    if axes == [0, 1]:
+        bo, bi, in_only = blocks_by_axis[0], blocks_by_axis[1], 0
+        O, I, R = shape[0], shape[1], _prod(shape[2:])
+    elif axes == [0]:
+        bo, bi, in_only = blocks_by_axis[0], None, 0
+        O, I, R = shape[0], 1, _prod(shape[1:])
+    elif len(axes) == 1:  # concatenation along a non-leading axis (partial_matching.py:122-129)
+        ax = axes[0]
+        bo, bi, in_only = None, blocks_by_axis[ax], 1
+        O, I, R = _prod(shape[:ax]), shape[ax], _prod(shape[ax + 1:])
+    else:
+        raise ValueError(f"block_merge: unsupported blocked axes {axes}")
+
+    keep = []
+
+    def unpack(b):
+        if b is None:
+            return [None, None, None, None], 0, 0
+        b = [t.to(device=w1.device, dtype=torch.int64).contiguous() for t in b]
+        keep.append(b)
+        return [t.data_ptr() if t.numel() else None for t in b], b[0].numel(), b[2].numel()
+
+    po, no, mo = unpack(bo)
+    pi, ni, mi = unpack(bi)
+    if bo is not None and no == 0 or bi is not None and ni == 0:
+        raise ValueError("block_merge: a blocked axis needs at least one merged unit")
+    Oout = no + 2 * mo if bo is not None else O
+    Iout = ni + 2 * mi if bi is not None else I
+    out = torch.empty(Oout * Iout * R, dtype=torch.float32, device=w1.device)
+    N.check(N.lib().plb_block_merge(w1.data_ptr(), w2.data_ptr(), O, I, R, po[0], po[1], po[2], po[3], no, mo,
+                                    pi[0], pi[1], pi[2], pi[3], ni, mi, in_only, out.data_ptr(), N.stream_ptr()),
+            "plb_block_merge")
+    if axes == [0, 1]:
+        return out.view([Oout, Iout] + shape[2:])
+    if axes == [0]:
+        return out.view([Oout] + shape[1:])
+    return out.view(shape[:axes[0]] + [Iout] + shape[axes[0] + 1:])
+
+
+def gather_axis(x, axis, P):
+    """index_select(x, axis, P) (apply_perm, pleas/core/utils.py:244)."""
+    _require_cuda_f32(x, "gather_axis")
+    x = x.contiguous()
+    outer, n, inner = as_rows_view(x, axis)
+    P = P.to(device=x.device, dtype=torch.int64).contiguous()
+    out_shape = list(x.shape)
+    out_shape[axis % x.dim()] = P.numel()
+    if P.numel() != n:
+        raise ValueError("gather_axis: permutation length mismatch")
+    out = torch.empty(out_shape, dtype=torch.float32, device=x.device)
+    N.check(N.lib().plb_gather_axis(x.data_ptr(), out.data_ptr(), outer, n, inner, P.data_ptr(), N.stream_ptr()),
+            "plb_gather_axis")
+    return out
+
+
+def compose_perm(a, b):
+    out = torch.empty_like(a)
+    N.check(N.lib().plb_compose_perm(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), N.stream_ptr()),
+            "plb_compose_perm")
+    return out
+
+
+def wm_progress(A, P, flag, gain=None):
+    N.check(N.lib().plb_wm_progress(A.data_ptr(), A.stride(0), P.data_ptr(), A.shape[0], flag.data_ptr(),
+                                    N.ptr(gain), N.stream_ptr()), "plb_wm_progress")
+
+
+# ------------------------------------------------------------------------------------ solve
+
+def chol_solve_(G, B, ridge):
+    """In place: G <- chol(G + ridge I) (lower), B <- (G + ridge I)^-1 B.  fp64 CUDA, row-major."""
+    assert G.dtype == torch.float64 and B.dtype == torch.float64 and G.is_cuda and B.is_cuda
+    assert G.is_contiguous() and B.is_contiguous() and G.shape[0] == G.shape[1] == B.shape[0]
+    info = torch.zeros(1, dtype=torch.int32, device=G.device)
+    N.check(N.lib().plb_chol_solve(G.data_ptr(), G.shape[0], B.data_ptr(), B.shape[1], float(ridge),
+                                   info.data_ptr(), N.stream_ptr()), "plb_chol_solve")
+    return info

@@ -1,0 +1,266 @@
+"""Kernel-level parity tests: every CUDA kernel, called through the C ABI, against the CPU
+oracle / numpy on seeded inputs.  Bit-exact for integer and index work, stated tolerances for
+floating point."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import key_str, load_spec_json
+from oracle import ref_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from pleas_merging_b200 import ops
+
+    return ops
+
+
+def unpack_planes(plane, rows, K, row_groups, kb_offset=0):
+    """numpy view of one packed plane back to [rows, K] (include/pleas_b200.h layout)."""
+    p = plane.cpu().numpy()
+    r = np.arange(rows)[:, None]
+    k = np.arange(K)[None, :]
+    kb, j, e = k // 16 + kb_offset, (k % 16) // 4, k % 4
+    off = ((kb * row_groups + r // 8) * 4 + j) * 32 + (r % 8) * 4 + e
+    return p[off]
+
+
+@pytest.mark.parametrize("shape,axis", [((3, 20, 5, 4), 1), ((2, 12, 7, 7), 1), ((5, 24), 1), ((24, 12, 3, 3), 0),
+                                        ((24, 12, 3, 3), 1), ((2, 130, 4, 4), 1)])
+def test_pack_split_layout_and_stats(shape, axis):
+    ops = _ops()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(*shape, generator=g)
+    xd = x.cuda()
+    outer, rows, inner = ops.as_rows_view(xd, axis)
+    K = outer * inner
+    planes = ops.Planes(rows, (K + 15) // 16, xd.device)
+    planes.hi.fill_(float("nan"))
+    planes.lo.fill_(float("nan"))
+    q = torch.zeros(2, rows, dtype=torch.float64, device=xd.device)
+    ops.pack_split(xd, axis, planes, sumsq=q[0], rowsum=q[1])
+    ref = O._rows(x.numpy(), axis)
+    hi = unpack_planes(planes.hi, rows, K, planes.row_groups)
+    lo = unpack_planes(planes.lo, rows, K, planes.row_groups)
+    assert (hi.view(np.uint32) & 0x1FFF == 0).all() and (lo.view(np.uint32) & 0x1FFF == 0).all()
+    assert np.abs(hi - ref).max() <= 2.0 ** -11 * np.abs(ref).max()
+    assert np.abs((hi.astype(np.float64) + lo) - ref).max() <= 2.0 ** -21 * np.abs(ref).max()
+    # zero padding in k for real rows
+    kpad = planes.k_blocks * 16
+    if kpad > K:
+        full = unpack_planes(planes.hi, rows, kpad, planes.row_groups)
+        assert (full[:, K:] == 0).all()
+    np.testing.assert_allclose(q[0].cpu().numpy(), (ref.astype(np.float64) ** 2).sum(1), rtol=1e-6)
+    np.testing.assert_allclose(q[1].cpu().numpy(), ref.astype(np.float64).sum(1), rtol=1e-5, atol=1e-5)
+
+
+def test_pack_split_row_gather():
+    ops = _ops()
+    x = torch.randn(4, 10, 6, generator=torch.Generator().manual_seed(1))
+    P = torch.randperm(10, generator=torch.Generator().manual_seed(2))
+    xd = x.cuda()
+    planes = ops.Planes(10, 2, xd.device)
+    ops.pack_split(xd, 1, planes, row_index=P.cuda())
+    hi = unpack_planes(planes.hi, 10, 24, planes.row_groups)
+    lo = unpack_planes(planes.lo, 10, 24, planes.row_groups)
+    ref = O._rows(x.numpy(), 1)[P.numpy()]
+    assert np.abs(hi.astype(np.float64) + lo - ref).max() <= 2.0 ** -21 * np.abs(ref).max()
+
+
+GEMM_CASES = [((2, 12, 5, 5), 1), ((4, 64, 16, 16), 1), ((3, 200, 9, 10), 1), ((2, 300, 7, 7), 1),
+              ((32, 24), 1), ((1, 128, 64, 64), 1), ((2, 520, 4, 4), 1)]
+
+
+@pytest.mark.parametrize("impl", ["simt", "tcgen05"])
+@pytest.mark.parametrize("shape,axis", GEMM_CASES)
+def test_cross_statistic_inner_and_cdist(shape, axis, impl):
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    x = torch.relu(torch.randn(*shape, generator=g)) + 0.1 * torch.randn(*shape, generator=g)
+    y = torch.relu(torch.randn(*shape, generator=g))
+    ops.set_gemm_impl(impl)
+    try:
+        G = ops.cross_statistic(x.cuda(), y.cuda(), axis, ops.MODE_INNER).cpu().numpy()
+        D = ops.cross_statistic(x.cuda(), y.cuda(), axis, ops.MODE_NEG_CDIST).cpu().numpy()
+    finally:
+        ops.set_gemm_impl("tcgen05")
+    X, Y = O._rows(x.numpy(), axis).astype(np.float64), O._rows(y.numpy(), axis).astype(np.float64)
+    Gref = X @ Y.T
+    # north-star bar is rel-err <= 1e-4; 3xTF32 holds ~1e-6
+    assert np.abs(G - Gref).max() <= 2e-6 * np.abs(Gref).max()
+    d2 = (X * X).sum(1)[:, None] + (Y * Y).sum(1)[None] - 2 * Gref
+    Dref = -np.sqrt(np.maximum(d2, 0))
+    assert np.abs(D - Dref).max() <= 1e-4 * np.abs(Dref).max()
+    # and against the fp32 oracle restatement of the reference operator
+    assert np.abs(D - O.cross_neg_cdist(x.numpy(), y.numpy(), axis)).max() <= 1e-4 * np.abs(Dref).max()
+
+
+def test_gemm_split_k_chain_bound():
+    """Results agree across K splits; the default split bounds the tensor-core accumulation
+    chain (RZ accumulate: -1e-7 relative per chained k-block) so parity holds at 2e-6."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    x, y = torch.randn(8, 96, 32, 32, generator=g).cuda(), torch.randn(8, 96, 32, 32, generator=g).cuda()
+    kb = 8 * 1024 // 16
+    pa, pb = ops.Planes(96, kb, x.device), ops.Planes(96, kb, x.device)
+    ops.pack_split(x, 1, pa)
+    ops.pack_split(y, 1, pb)
+    X = O._rows(x.cpu().numpy(), 1).astype(np.float64)
+    Y = O._rows(y.cpu().numpy(), 1).astype(np.float64)
+    ref = X @ Y.T
+    errs = {}
+    for splits in (None, 32, 64, 512, 1):
+        plan = ops.GemmPlan(pa, pb, 96, 96, kb, splits=splits)
+        assert splits is not None or -(-kb // plan.splits) <= ops.MAX_CHAIN_KB
+        plan.run()
+        out = torch.empty(96, 96, device=x.device)
+        plan.finalize(out)
+        errs[splits] = np.abs(out.cpu().numpy() - ref).max() / np.abs(ref).max()
+    for splits in (None, 32, 64, 512):
+        assert errs[splits] <= 2e-6, errs
+    assert errs[1] <= 1e-4, errs  # one 512-block chain: still inside the matrix bar, not the perm bar
+
+
+def test_finalize_accumulates_fp32_and_fp64():
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    x, y = torch.randn(2, 40, 6, 6, generator=g).cuda(), torch.randn(2, 40, 6, 6, generator=g).cuda()
+    kb = (72 + 15) // 16
+    pa, pb = ops.Planes(40, kb, x.device), ops.Planes(40, kb, x.device)
+    ops.pack_split(x, 1, pa)
+    ops.pack_split(y, 1, pb)
+    plan = ops.GemmPlan(pa, pb, 40, 40, kb)
+    plan.run()
+    acc32 = torch.ones(40, 40, device=x.device)
+    acc64 = torch.ones(40, 40, device=x.device, dtype=torch.float64)
+    plan.finalize(acc32, accumulate=True)
+    plan.finalize(acc64, accumulate=True)
+    ref = 1.0 + O.cross_inner(x.cpu().numpy(), y.cpu().numpy(), 1)
+    np.testing.assert_allclose(acc32.cpu().numpy(), ref, rtol=0, atol=2e-5 * np.abs(ref).max())
+    np.testing.assert_allclose(acc64.cpu().numpy(), ref, rtol=0, atol=2e-5 * np.abs(ref).max())
+
+
+def test_lap_golden_instances(lap_golden):
+    ops = _ops()
+    for maximize in (True, False):
+        names = [n for n, g in lap_golden.items() if bool(g["maximize"]) == maximize]
+        costs = [torch.from_numpy(lap_golden[n]["A"]).cuda() for n in names]
+        outs, obj, status = ops.lap_solve_batched(costs, maximize)
+        assert (status.cpu() == 0).all()
+        for n, o, ob in zip(names, outs, obj.cpu().tolist()):
+            assert (o.cpu().numpy() == lap_golden[n]["col"]).all(), n  # identical to SciPy, ties included
+            assert ob == pytest.approx(float(lap_golden[n]["obj"]), rel=1e-12, abs=1e-12), n
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 257, 1000, 2048])
+def test_lap_random_vs_oracle(n):
+    ops = _ops()
+    rng = np.random.default_rng(n)
+    mats = [rng.standard_normal((n, n)).astype(np.float32), rng.integers(0, 5, (n, n)).astype(np.float32)]
+    if n >= 31:
+        X = rng.standard_normal((n, 64)).astype(np.float32)
+        Y = X[rng.permutation(n)] + 0.3 * rng.standard_normal((n, 64)).astype(np.float32)
+        mats.append(O.cross_neg_cdist(X, Y, 0))
+    outs, obj, status = ops.lap_solve_batched([torch.from_numpy(m).cuda() for m in mats], True)
+    assert (status.cpu() == 0).all()
+    for m, o in zip(mats, outs):
+        col, _ = O.solve_lsa(m, True)
+        assert (o.cpu().numpy() == col).all()
+
+
+def test_lap_strided_and_invalid():
+    ops = _ops()
+    big = torch.randn(40, 64, generator=torch.Generator().manual_seed(6)).cuda()
+    view = big[:40, :40]  # leading dimension 64
+    outs, _, status = ops.lap_solve_batched([view], True)
+    assert (outs[0].cpu().numpy() == O.solve_lsa(view.cpu().numpy(), True)[0]).all()
+    bad = torch.ones(4, 4).cuda()
+    bad[1, 2] = float("nan")
+    _, _, status = ops.lap_solve_batched([bad], True)
+    assert status.cpu().tolist() == [2]
+    with pytest.raises(ValueError):
+        ops.raise_on_lap_status(status)
+
+
+@pytest.mark.parametrize("n,ratio", [(12, 0.0), (12, 0.5), (24, 0.3), (24, 1.0), (100, 0.7), (1000, 0.25), (4096, 0.5)])
+def test_get_blocks_vs_oracle(n, ratio):
+    ops = _ops()
+    rng = np.random.default_rng(n)
+    C = rng.standard_normal((n, n)).astype(np.float32)
+    C[3 % n] = C[5 % n]  # duplicate row
+    P = rng.permutation(n)
+    spec = [{"key": ("w", 0), "size": n, "state": [("w", 0)], "node": []}]
+    ref = O.get_blocks(spec, {("w", 0): P}, {("w", 0): C}, ratio)[("w", 0)]
+    identity = abs(ratio - 1.0) < 1e-3
+    got = ops.get_blocks_group(torch.from_numpy(C).cuda(), torch.from_numpy(P).cuda(), ratio, identity)
+    for a, b in zip(got, ref):
+        assert (a.cpu().numpy() == b).all()
+
+
+@pytest.mark.parametrize("name", ["r0", "r05", "r1", "mixed"])
+def test_block_merge_vs_reference_state(tiny_golden, name):
+    """Merged tensors equal the reference's partial_merge state dict bit for bit."""
+    from oracle import tinynet
+
+    ops = _ops()
+    spec = load_spec_json("tiny")
+    m1, m2 = tinynet.make_pair(12, 10)
+    blocks = {g["key"]: [t.cuda() for t in tiny_golden[f"pm/{name}/blocks"][key_str(g["key"])]] for g in spec}
+    per_axis = O.blocks_by_state_axis(spec, blocks)
+    by_tensor = {}
+    for (tname, ax), b in per_axis.items():
+        by_tensor.setdefault(tname, {})[ax] = b
+    sd1, sd2 = m1.state_dict(), m2.state_dict()
+    gold = tiny_golden[f"pm/{name}/state"]
+    for tname, bl in by_tensor.items():
+        out = ops.block_merge(sd1[tname].cuda(), sd2[tname].cuda(), bl)
+        assert tuple(out.shape) == tuple(gold[tname].shape), tname
+        assert torch.equal(out.cpu(), gold[tname]), tname
+
+
+def test_gather_compose_progress():
+    ops = _ops()
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(5, 9, 3, 3, generator=g)
+    P = torch.randperm(9, generator=g)
+    for axis in (0, 1):
+        xx = x if axis == 1 else x.transpose(0, 1).contiguous()
+        assert torch.equal(ops.gather_axis(xx.cuda(), axis, P.cuda()).cpu(), torch.index_select(xx, axis, P))
+    a, b = torch.randperm(50, generator=g), torch.randperm(50, generator=g)
+    assert torch.equal(ops.compose_perm(a.cuda(), b.cuda()).cpu(), a[b])
+    A = torch.randn(50, 50, generator=g)
+    flag = torch.zeros(1, dtype=torch.int32).cuda()
+    gain = torch.zeros(1, dtype=torch.float64).cuda()
+    ops.wm_progress(A.cuda(), torch.arange(50).cuda(), flag, gain)
+    assert flag.item() == 0 and gain.item() == 0.0
+    col, _ = O.solve_lsa(A.numpy(), True)
+    ops.wm_progress(A.cuda(), torch.from_numpy(col).cuda(), flag, gain)
+    assert flag.item() == 1
+    assert gain.item() == pytest.approx(float(A.double()[torch.arange(50), col].sum() - A.double().diag().sum()))
+
+
+@pytest.mark.parametrize("n,nrhs", [(1, 1), (5, 3), (33, 7), (100, 130), (300, 64), (1000, 257)])
+def test_chol_solve_vs_numpy(n, nrhs):
+    ops = _ops()
+    rng = np.random.default_rng(n)
+    U = rng.standard_normal((2 * n + 3, n))
+    G = U.T @ U
+    B = rng.standard_normal((n, nrhs))
+    ridge = 1e-3
+    Gd, Bd = torch.from_numpy(G).cuda(), torch.from_numpy(B.copy()).cuda()
+    info = ops.chol_solve_(Gd, Bd, ridge)
+    assert info.item() == 0
+    ref = np.linalg.solve(G + ridge * np.eye(n), B)
+    np.testing.assert_allclose(Bd.cpu().numpy(), ref, rtol=1e-8, atol=1e-10 * np.abs(ref).max())
+    L = np.tril(Gd.cpu().numpy())
+    np.testing.assert_allclose(L @ L.T, G + ridge * np.eye(n), rtol=1e-10, atol=1e-10 * np.abs(G).max())
+
+
+def test_chol_reports_non_spd():
+    ops = _ops()
+    G = torch.eye(40, dtype=torch.float64)
+    G[17, 17] = -1.0
+    info = ops.chol_solve_(G.cuda(), torch.ones(40, 2, dtype=torch.float64).cuda(), 0.0)
+    assert info.item() == 18
