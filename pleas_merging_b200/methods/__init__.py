@@ -1,0 +1,10 @@
+"""Merge methods — same public names as pleas/methods/__init__.py:12-35 (hot-path subset)."""
+from .activation_matching import (activation_matching, build_cross_module, compute_matching_costs,
+                                  cross_features_cdist, cross_features_inner_product)
+from .partial_matching import build_partial_merge_model, expand_ratios, get_blocks, partial_merge
+from .pleas_merging import train
+from .weight_matching import weight_matching
+
+__all__ = ["activation_matching", "build_cross_module", "compute_matching_costs", "cross_features_cdist",
+           "cross_features_inner_product", "weight_matching", "partial_merge", "get_blocks", "expand_ratios",
+           "build_partial_merge_model", "train"]

@@ -1,0 +1,315 @@
+"""Activation matching on B200 (drop-in for pleas/methods/activation_matching.py).
+
+Same public surface as the reference — ``cross_features_inner_product``,
+``cross_features_cdist``, ``build_cross_module``, ``compute_matching_costs``,
+``activation_matching`` — with the arithmetic moved into the library's kernels:
+
+* every tap is one pass over the two activations (pack.cu: hi/lo split into tcgen05 operand
+  order + row norms, no transposed copy), one 3xTF32 tcgen05 GEMM (gemm.cu) and one fused
+  epilogue (finalize.cu) that applies ``-cdist``/inner product and adds straight into the tap's
+  permutation-group cost matrix;
+* all groups' assignment problems are solved in ONE launch of the GPU LAP kernel (lap.cu),
+  bit-identical to SciPy's answer, with a single D2H copy of the permutations at the end.
+
+``accumulate`` selects the batch semantics (SURVEY.md finding F1): ``"reference"`` (default)
+reproduces the reference exactly — its membership test at activation_matching.py:124 compares
+a tuple with ``Axis`` keys, so every batch overwrites and only the last processed batch
+counts; ``"sum"`` is the paper-intended sum over batches.
+"""
+import itertools
+from collections.abc import Collection
+
+import torch
+import torch.fx
+from torch.nn import Module
+
+from .. import ops
+from ..core.solvers import b200_solve_lsa, solve_lsa_batched
+from ..core.utils import Axis, Permutation, PermutationSpec
+
+
+# ------------------------------------------------------------------ plug-compatible operators
+
+def cross_features_inner_product(x, y, a: int):
+    """[x.shape[a], y.shape[a]] Gram matrix over all other axes (reference :14-28)."""
+    return ops.cross_statistic(x, y, a, ops.MODE_INNER)
+
+
+def cross_features_cdist(x, y, a: int):
+    """Negative Euclidean distance between the axis-``a`` slices (reference :31-46)."""
+    return ops.cross_statistic(x, y, a, ops.MODE_NEG_CDIST)
+
+
+_FUSED_MODES = {cross_features_inner_product: ops.MODE_INNER, cross_features_cdist: ops.MODE_NEG_CDIST}
+
+
+# ------------------------------------------------------------------ dual-model graph
+
+def _tap_axes(axes: Collection) -> dict:
+    taps = {}
+    for ax in axes:
+        taps.setdefault(ax.key, set()).add(ax.axis)
+    return {k: sorted(v) for k, v in taps.items()}
+
+
+def _dual_graph(model1: Module, model2: Module, axes: Collection, emit):
+    """Runs both models side by side in one fx graph (model2 must trace to model1's graph, as
+    in the reference, :68).  After every tapped node ``emit(graph, name, axis, node_a, node_b)``
+    inserts the tap consumer right behind its producers — torchvision's in-place ReLU
+    overwrites the preceding tap's storage, so consumers must not be deferred."""
+    traced = torch.fx.symbolic_trace(model1)
+    taps = _tap_axes(axes)
+    g = torch.fx.Graph()
+    env = ({}, {})
+    emitted = {}
+    out_a = out_b = None
+    for node in traced.graph.nodes:
+        if node.op == "placeholder":
+            ph = g.node_copy(node)
+            env[0][node] = env[1][node] = ph
+            continue
+        if node.op == "output":
+            out_a = torch.fx.node.map_arg(node.args[0], lambda n: env[0][n])
+            out_b = torch.fx.node.map_arg(node.args[0], lambda n: env[1][n])
+            continue
+        for side in (0, 1):
+            new = g.node_copy(node, lambda n, side=side: env[side][n])
+            if node.op in ("call_module", "get_attr"):
+                new.target = f"{side}.{node.target}"
+            env[side][node] = new
+        for a in taps.get(node.name, ()):
+            emitted[node.name, a] = emit(g, node.name, a, env[0][node], env[1][node])
+    g.output(([out_a, out_b], emitted))
+    gm = torch.fx.GraphModule(torch.nn.ModuleList([model1, model2]), g)
+    gm.graph.lint()
+    return gm
+
+
+def build_cross_module(model1: Module, model2: Module, axes: Collection, cross_features):
+    """GraphModule returning ``([out1, out2], {(node_name, axis): cross_features(a, b, axis)})``
+    (reference :49-100)."""
+    return _dual_graph(model1, model2, axes,
+                       lambda g, name, a, na, nb: g.call_function(cross_features, (na, nb, a)))
+
+
+# ------------------------------------------------------------------ fused accumulation
+
+_SINKS = {}
+_sink_ids = itertools.count()
+
+
+def _tap_dispatch(sink_id: int, tap_id: int, xa, xb):
+    """fx ``call_function`` target of the fused path (a plain def so codegen can name it)."""
+    _SINKS[sink_id].tap(tap_id, xa, xb)
+    return None
+
+
+class _Arena:
+    """Staging memory shared by all taps (they run back to back on one stream): packed hi/lo
+    planes of both operands and the K-split partial tiles."""
+
+    def __init__(self, device):
+        self.device = device
+        self.plane_floats = 0
+        self.partial_floats = 0
+        self.version = 0
+        self.buf = None
+        self.partial = None
+
+    def ensure(self, plane_floats, partial_floats):
+        if plane_floats > self.plane_floats:
+            self.plane_floats = int(plane_floats * 1.25)
+            self.buf = torch.empty(4, self.plane_floats, dtype=torch.float32, device=self.device)
+            self.version += 1
+        if partial_floats > self.partial_floats:
+            self.partial_floats = int(partial_floats * 1.25)
+            self.partial = torch.empty(self.partial_floats, dtype=torch.float32, device=self.device)
+            self.version += 1
+
+
+class _View:
+    """Planes-like view into the arena."""
+
+    def __init__(self, hi, lo, rows, row_groups, k_blocks):
+        self.hi, self.lo, self.rows, self.row_groups, self.k_blocks = hi, lo, rows, row_groups, k_blocks
+
+
+class _Tap:
+    __slots__ = ("name", "axis", "group", "shape", "ra", "rb", "kb", "q", "plan", "version", "pa", "pb")
+
+
+class CrossAccumulator:
+    """Receives (activation_a, activation_b) at every tap, in graph order, and accumulates the
+    chosen cross statistic into its permutation group's cost matrix."""
+
+    def __init__(self, spec: PermutationSpec, mode: int, device):
+        self.mode, self.device = mode, device
+        self.keys = list(spec.keys())
+        sizes = [spec[k].size for k in self.keys]
+        self.flat = torch.zeros(sum(n * n for n in sizes), dtype=torch.float32, device=device)
+        self.costs, off = [], 0
+        for n in sizes:
+            self.costs.append(self.flat[off:off + n * n].view(n, n))
+            off += n * n
+        self.group_of = {}
+        for gi, k in enumerate(self.keys):
+            for ax in spec[k].node:
+                self.group_of[ax.key, ax.axis] = gi
+        self.taps = []
+        self.seen = set()
+        self.arena = _Arena(device)
+        self.sink_id = next(_sink_ids)
+        _SINKS[self.sink_id] = self
+
+    def close(self):
+        _SINKS.pop(self.sink_id, None)
+
+    def emit(self, g, name, axis, na, nb):
+        t = _Tap()
+        t.name, t.axis, t.group, t.shape, t.version = name, axis, self.group_of[name, axis], None, -1
+        self.taps.append(t)
+        return g.call_function(_tap_dispatch, (self.sink_id, len(self.taps) - 1, na, nb))
+
+    def begin_batch(self, reset_costs):
+        if reset_costs:
+            self.flat.zero_()
+        qs = [t.q for t in self.taps if t.shape is not None and t.q is not None]
+        if qs:
+            torch._foreach_zero_(qs)
+
+    def _prepare(self, t, xa, xb):
+        oa, ra, ia = ops.as_rows_view(xa, t.axis)
+        ob, rb, ib = ops.as_rows_view(xb, t.axis)
+        if oa * ia != ob * ib:
+            raise ValueError(f"tap {t.name}: contraction sizes differ between the two models")
+        n = self.costs[t.group].shape[0]
+        if (ra, rb) != (n, n):
+            raise ValueError(f"tap {t.name}:{t.axis} has {ra}x{rb} units but its group has {n}")
+        t.shape, t.ra, t.rb, t.kb = (tuple(xa.shape), tuple(xb.shape)), ra, rb, (oa * ia + 15) // 16
+        t.q = torch.zeros(ra + rb, dtype=torch.float64, device=self.device) \
+            if self.mode == ops.MODE_NEG_CDIST else None
+        t.version = -1
+
+    def _bind(self, t):
+        """(Re)creates the tap's GEMM problem entry against the current arena."""
+        rga, rgb = 16 * ((t.ra + 127) // 128), 16 * ((t.rb + 127) // 128)
+        bn = ops.choose_bn(t.rb)
+        m_tiles, n_tiles = (t.ra + 127) // 128, (t.rb + bn - 1) // bn
+        splits = ops.choose_splits(m_tiles * n_tiles, t.kb)
+        self.arena.ensure(max(rga, rgb) * t.kb * 128, splits * m_tiles * 128 * n_tiles * bn)
+        b = self.arena.buf
+        t.pa = _View(b[0], b[1], t.ra, rga, t.kb)
+        t.pb = _View(b[2], b[3], t.rb, rgb, t.kb)
+        t.plan = ops.GemmPlan(t.pa, t.pb, t.ra, t.rb, t.kb, splits=splits, partial=self.arena.partial)
+        t.version = self.arena.version
+
+    def tap(self, idx, xa, xb):
+        t = self.taps[idx]
+        self.seen.add(idx)
+        if t.shape != (tuple(xa.shape), tuple(xb.shape)):
+            self._prepare(t, xa, xb)
+        if t.version != self.arena.version:
+            self._bind(t)
+            if t.version != self.arena.version:  # _bind grew the arena: bind against the new one
+                self._bind(t)
+        qa, qb = (t.q[:t.ra], t.q[t.ra:]) if t.q is not None else (None, None)
+        ops.pack_split(xa, t.axis, t.pa, sumsq=qa)
+        ops.pack_split(xb, t.axis, t.pb, sumsq=qb)
+        t.plan.run()
+        t.plan.finalize(self.costs[t.group], self.mode, qa, qb, accumulate=True)
+
+
+# ------------------------------------------------------------------ public API
+
+def _model_device(model):
+    p = next(iter(model.parameters()), None)
+    if p is None or not p.is_cuda:
+        raise RuntimeError("pleas_merging_b200 runs on a CUDA device: move both models to cuda first "
+                           "(there is no CPU fallback)")
+    return p.device
+
+
+def compute_matching_costs(spec: PermutationSpec, gm_cross: Module, dataloader, num_batches,
+                           accumulate="reference"):
+    """Generic (un-fused) cost loop for a module built by ``build_cross_module`` with any
+    ``cross_features`` callable (reference :103-136)."""
+    if accumulate not in ("reference", "sum"):
+        raise ValueError("accumulate must be 'reference' or 'sum'")
+    device = _model_device(gm_cross)
+    cross_sum = {}
+    with torch.inference_mode():
+        for (x, _), _ in zip(dataloader, range(num_batches)):
+            _, cross = gm_cross(x.to(device, non_blocking=True))
+            for ka, v in cross.items():
+                k = Axis(*ka)
+                if accumulate == "sum" and k in cross_sum:
+                    cross_sum[k].add_(v)
+                else:
+                    cross_sum[k] = v
+    costs = {}
+    for key, pg in spec.items():
+        present = [cross_sum[n] for n in pg.node if n in cross_sum]
+        costs[key] = sum(present[1:], present[0].clone()) if present else 0
+    return costs
+
+
+def _fused_costs(spec, model1, model2, dataloader, num_batches, mode, accumulate):
+    device = _model_device(model1)
+    acc = CrossAccumulator(spec, mode, device)
+    try:
+        axes = [ax for pg in spec.values() for ax in pg.node]
+        gm = _dual_graph(model1, model2, axes, acc.emit)
+        with torch.inference_mode():
+            for (x, _), _ in zip(dataloader, range(num_batches)):
+                acc.begin_batch(reset_costs=(accumulate == "reference"))
+                gm(x.to(device, non_blocking=True))
+        return {k: c for k, c in zip(acc.keys, acc.costs)}
+    finally:
+        acc.close()
+
+
+def activation_matching(
+    spec: PermutationSpec,
+    model1: Module,
+    model2: Module,
+    dataloader,
+    num_batches=1000,
+    cross_features=cross_features_cdist,
+    lsa_solver=b200_solve_lsa,
+    output_costs=False,
+    *,
+    accumulate="reference",
+) -> Permutation:
+    """Permute model2's units to match model1's activations (reference :139-177).
+
+    Returns ``{group key: CPU int64[n]}`` in spec order, plus the device fp32 ``[n, n]`` cost
+    matrices when ``output_costs`` is set.  With the library's own ``cross_features`` /
+    ``lsa_solver`` (the defaults) the fused kernels run; any other callable is honoured through
+    the generic per-tap path."""
+    if accumulate not in ("reference", "sum"):
+        raise ValueError("accumulate must be 'reference' or 'sum'")
+    if cross_features in _FUSED_MODES:
+        costs = _fused_costs(spec, model1, model2, dataloader, num_batches, _FUSED_MODES[cross_features], accumulate)
+    else:
+        axes = [ax for pg in spec.values() for ax in pg.node]
+        gm = build_cross_module(model1, model2, axes, cross_features)
+        costs = compute_matching_costs(spec, gm, dataloader, num_batches, accumulate)
+    if lsa_solver is b200_solve_lsa:
+        perm = dict(zip(costs.keys(), solve_lsa_batched(costs.values())))
+    else:
+        perm = {k: lsa_solver(v) for k, v in costs.items()}
+    if output_costs:
+        return perm, costs
+    return perm
+
+
+def check_multi_axis(spec):
+    """True when some fx node contributes more than one axis to the spec (reference :180-194,
+    restated with the evident intent: the reference never adds to its ``counter``)."""
+    seen = set()
+    for pg in spec.values():
+        for ax in pg.node:
+            if ax.key in seen:
+                return True
+            seen.add(ax.key)
+    return False

@@ -1,0 +1,390 @@
+"""PLeaS per-layer least squares on B200 (drop-in for pleas/methods/pleas_merging.py:11-405).
+
+The reference fits every Conv2d/Linear of the merged model to the (permuted, averaged)
+activations of the two source models — ``min sum_l mean((layer_l(X-bar_l) - Y-bar_l)^2)`` —
+with 401 Adam steps (:357-375).  The layers are independent (inputs and targets come from the
+frozen source models), so the optimum is a linear least-squares problem per layer.  The
+default ``solver="lstsq"`` therefore streams the calibration batches ONCE and
+
+  * builds the normal equations ``G_l = U^T U``, ``R_l = U^T Y-bar`` (U = im2col of X-bar) with
+    the fused gather-average-im2col pack kernel and the 3xTF32 tcgen05 GEMM, accumulated in
+    fp64 on device;
+  * solves ``(G_l + ridge I) dW^T = R_l - G_l W0^T`` per layer with the library's blocked fp64
+    Cholesky (csrc/chol.cu), i.e. the minimum-ridge UPDATE of the partial_merge init ``W0``:
+    directions the data never excites keep their init value, exactly like a gradient method
+    started at ``W0``; entries whose gradient mask is zero stay at ``W0``.
+
+``solver="adam"`` replays the reference's Adam trajectory (same hooks, targets, masks,
+optimizer and schedule) for weight-level parity checks.  Gradient masks reproduce the
+reference's index order ``mask[si1, so2]``.
+"""
+from copy import copy, deepcopy
+
+import torch
+
+from .. import ops
+from ..core.utils import Axis, get_attr
+from .partial_matching import get_blocks
+
+
+# ------------------------------------------------------------------ reference helpers
+
+def get_gradient_mask(perm_blocks, model_weights):
+    """0/1 masks per trained parameter (reference :11-60, including its index order)."""
+    masks = []
+    for layer_name, params in model_weights.items():
+        bi = perm_blocks.get(Axis(f"{layer_name}.weight", 1), (torch.arange(3), torch.arange(3), [], []))
+        bo = perm_blocks.get(Axis(f"{layer_name}.weight", 0), (torch.arange(1000), torch.arange(1000), [], []))
+        ni, mi, no, mo = len(bi[0]), len(bi[2]), len(bo[0]), len(bo[2])
+        si1, si2 = slice(ni, ni + mi), slice(ni + mi, ni + 2 * mi)
+        so1, so2 = slice(no, no + mo), slice(no + mo, no + 2 * mo)
+        for v in params.parameters():
+            mask = torch.ones_like(v)
+            if v.dim() >= 2:
+                mask[si1, so2] = 0.0
+                mask[si2, so1] = 0.0
+            masks.append(mask)
+    return masks
+
+
+def get_model_dict_and_params(model3):
+    """Detached fp32 CUDA copies of every Conv2d/Linear of model3 (reference :152-177)."""
+    model3_dict = {}
+    for name, v in model3.named_modules():
+        if isinstance(v, (torch.nn.Conv2d, torch.nn.Linear)):
+            model3_dict[name] = deepcopy(v).float().cuda()
+            for p in model3_dict[name].parameters():
+                p.requires_grad = True
+    m3_params = [p for m in model3_dict.values() for p in m.parameters()]
+    return model3, model3_dict, m3_params
+
+
+def capture_inputs(model, act_dict):
+    """Forward hooks storing (input, output) of every Conv2d/Linear (reference :216-231 stores
+    the input and recomputes the output with a second forward of the layer, :113-114)."""
+    handles = []
+    for name, module in model.named_modules():
+        if isinstance(module, (torch.nn.Conv2d, torch.nn.Linear)):
+            def hook(mod, inp, out, name=name):
+                act_dict[name] = (inp[0] if isinstance(inp, tuple) else inp, out)
+            handles.append(module.register_forward_hook(hook))
+    return handles
+
+
+def _layer_blocks(perm_blocks, name, cin, num_classes, separate_classifier, model_type):
+    """Block lookup with the reference's fallbacks (:91-111)."""
+    e = torch.zeros(0, dtype=torch.int64)
+    bo = perm_blocks.get(Axis(f"{name}.weight", 0))
+    if bo is None:
+        if separate_classifier:
+            feat = {"rn50": 2048, "rn101": 2048, "rn20": 1024, "rn18": 512}.get(model_type)
+            if feat is None:
+                raise ValueError(f"Unknown model type: {model_type}")
+            bo = (torch.arange(feat), torch.arange(feat), e, e)
+        else:
+            bo = (torch.arange(num_classes), torch.arange(num_classes), e, e)
+    bi = perm_blocks.get(Axis(f"{name}.weight", 1))
+    if bi is None:
+        bi = (torch.arange(cin), torch.arange(cin), e, e)
+    return bi, bo
+
+
+def get_model_orig_activations(acts1, acts2, bi, bo, merging="perm_gradmask"):
+    """(X-bar, Y-bar) of one layer with torch ops (reference :116-147) — used by the Adam
+    replay; the least-squares path fuses this into its pack kernel."""
+    (ip1, op1), (ip2, op2) = acts1, acts2
+    dev = ip1.device
+    sel = lambda t, idx: t.index_select(1, idx.to(dev).int())
+    i11, i22, i1c, i2c = sel(ip1, bi[0]), sel(ip2, bi[1]), sel(ip1, bi[2]), sel(ip2, bi[3])
+    o11, o22, o1c, o2c = sel(op1, bo[0]), sel(op2, bo[1]), sel(op1, bo[2]), sel(op2, bo[3])
+    if merging == "reg_mean":
+        return torch.cat([ip1, ip2], 0), torch.cat([op1, op2], 0)
+    if "perm_separatels" in merging:
+        X = torch.cat([torch.cat([i11, i1c, torch.zeros_like(i2c)], 1),
+                       torch.cat([i22, torch.zeros_like(i1c), i2c], 1)], 0)
+        Y = torch.cat([torch.cat([o11, o1c, torch.zeros_like(o2c)], 1),
+                       torch.cat([o22, torch.zeros_like(o1c), o2c], 1)], 0)
+        return X, Y
+    if "perm_mixedls" in merging:
+        X = torch.cat([torch.cat([(i11 + i22) / 2, i1c, torch.zeros_like(i2c)], 1),
+                       torch.cat([(i11 + i22) / 2, torch.zeros_like(i1c), i2c], 1)], 0)
+        Y = torch.cat([torch.cat([o11, o1c, torch.zeros_like(o2c)], 1),
+                       torch.cat([o22, torch.zeros_like(o1c), o2c], 1)], 0)
+        return X, Y
+    return torch.cat([(i11 + i22) / 2, i1c, i2c], 1), torch.cat([(o11 + o22) / 2, o1c, o2c], 1)
+
+
+# ------------------------------------------------------------------ least-squares path
+
+def _channel_map(b, device):
+    """Merged-channel -> (source channel in model 1, in model 2, weights) for
+    cat[(a[b1] + b[b2]) / 2, a[b1c], b[b2c]]."""
+    b1, b2, b1c, b2c = (t.to("cpu", torch.int64) for t in b)
+    nm, ms = len(b1), len(b1c)
+    neg = lambda n: torch.full((n,), -1, dtype=torch.int64)
+    c1 = torch.cat([b1, b1c, neg(ms)]).to(torch.int32)
+    c2 = torch.cat([b2, neg(ms), b2c]).to(torch.int32)
+    s1 = torch.cat([torch.full((nm,), 0.5), torch.ones(ms), torch.zeros(ms)])
+    s2 = torch.cat([torch.full((nm,), 0.5), torch.zeros(ms), torch.ones(ms)])
+    return tuple(t.to(device) for t in (c1, c2, s1, s2)), nm + 2 * ms
+
+
+class _Workspace:
+    """Growable staging shared by all layers (they run back to back on one stream)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.cap = {}
+        self.buf = {}
+
+    def get(self, name, floats):
+        if self.cap.get(name, 0) < floats:
+            self.cap[name] = int(floats * 1.2)
+            self.buf[name] = torch.empty(self.cap[name], dtype=torch.float32, device=self.device)
+        return self.buf[name]
+
+    def planes(self, name, rows, kb):
+        rg = 16 * ((rows + 127) // 128)
+        n = rg * kb * 128
+        from .activation_matching import _View
+
+        return _View(self.get(name + "_hi", n), self.get(name + "_lo", n), rows, rg, kb)
+
+
+class _LayerLS:
+    """Normal-equation accumulator of one trained layer."""
+
+    def __init__(self, name, layer, bi, bo, ip_shape, op_shape, device):
+        self.name = name
+        self.is_conv = isinstance(layer, torch.nn.Conv2d)
+        if self.is_conv:
+            if layer.groups != 1:
+                raise NotImplementedError(f"{name}: grouped convolutions are not supported by the closed form")
+            self.kernel, self.stride = tuple(layer.kernel_size), tuple(layer.stride)
+            self.padding, self.dilation = tuple(layer.padding), tuple(layer.dilation)
+            if isinstance(layer.padding, str):
+                raise NotImplementedError(f"{name}: string padding is not supported")
+        else:
+            if len(ip_shape) != 2:
+                raise NotImplementedError(f"{name}: Linear inputs must be [batch, features]")
+            self.kernel = self.stride = self.dilation = (1, 1)
+            self.padding = (0, 0)
+        self.has_bias = layer.bias is not None
+        self.imap, self.cin = _channel_map(bi, device)
+        self.omap, self.cout = _channel_map(bo, device)
+        self.K = self.cin * self.kernel[0] * self.kernel[1] + int(self.has_bias)
+        self.bi, self.bo = bi, bo
+        self.G = torch.zeros(self.K, self.K, dtype=torch.float64, device=device)
+        self.R = torch.zeros(self.K, self.cout, dtype=torch.float64, device=device)
+        self.count = 0
+
+    def accumulate(self, acts1, acts2, ws):
+        (ip1, op1), (ip2, op2) = acts1, acts2
+        if not self.is_conv:
+            ip1, ip2 = ip1[:, :, None, None], ip2[:, :, None, None]
+            op1, op2 = op1[:, :, None, None], op2[:, :, None, None]
+        B, _, Ho, Wo = op1.shape
+        L = B * Ho * Wo
+        kb = (L + 15) // 16
+        pu = ws.planes("u", self.K, kb)
+        py = ws.planes("y", self.cout, kb)
+        ops.pack_im2col(ip1.float(), ip2.float(), *self.imap, self.cin, self.kernel, self.stride, self.padding,
+                        self.dilation, (Ho, Wo), self.has_bias, pu)
+        ops.pack_im2col(op1.float(), op2.float(), *self.omap, self.cout, (1, 1), (1, 1), (0, 0), (1, 1), (Ho, Wo),
+                        False, py)
+        for b_planes, n_cols, out in ((pu, self.K, self.G), (py, self.cout, self.R)):
+            bn = ops.choose_bn(n_cols)
+            m_tiles, n_tiles = (self.K + 127) // 128, (n_cols + bn - 1) // bn
+            splits = ops.choose_splits(m_tiles * n_tiles, kb)
+            partial = ws.get("partial", splits * m_tiles * 128 * n_tiles * bn)
+            plan = ops.GemmPlan(pu, b_planes, self.K, n_cols, kb, splits=splits, partial=partial)
+            plan.run()
+            plan.finalize(out, ops.MODE_INNER, accumulate=True)
+        self.count += L
+
+    def mask2d(self, wshape):
+        """Gradient mask over the flattened [Co, K] weight (+ bias column)."""
+        ni, mi, no, mo = len(self.bi[0]), len(self.bi[2]), len(self.bo[0]), len(self.bo[2])
+        mask = torch.ones(wshape)
+        if len(wshape) >= 2:
+            mask[slice(ni, ni + mi), slice(no + mo, no + 2 * mo)] = 0.0
+            mask[slice(ni + mi, ni + 2 * mi), slice(no, no + mo)] = 0.0
+        mask = mask.reshape(wshape[0], -1)
+        if self.has_bias:
+            mask = torch.cat([mask, torch.ones(wshape[0], 1)], 1)
+        return mask > 0
+
+    def solve(self, layer, ridge_rel):
+        """Returns the fitted flattened weight [Co, K] (fp64, CUDA) and per-layer losses."""
+        dev = self.G.device
+        W0 = layer.weight.detach().to(dev, torch.float64).reshape(self.cout, -1)
+        if self.has_bias:
+            W0 = torch.cat([W0, layer.bias.detach().to(dev, torch.float64)[:, None]], 1)
+        assert W0.shape == (self.cout, self.K), f"{self.name}: merged layer shape {tuple(W0.shape)} != {(self.cout, self.K)}"
+        grad = self.R - self.G @ W0.T  # [K, Co] residual of the normal equations at the init
+        ridge = ridge_rel * float(self.G.diagonal().mean())
+        mask = self.mask2d(tuple(layer.weight.shape))
+        W = W0.clone()
+        patterns, inverse = torch.unique(mask, dim=0, return_inverse=True)
+        for pi in range(patterns.shape[0]):
+            free = patterns[pi].to(dev)
+            rows = (inverse == pi).nonzero().flatten().to(dev)
+            if not bool(free.any()):
+                continue
+            if bool(free.all()):
+                Gf, rhs = self.G.clone(), grad[:, rows].contiguous()
+            else:
+                idx = free.nonzero().flatten()
+                Gf, rhs = self.G[idx][:, idx].contiguous(), grad[idx][:, rows].contiguous()
+            info = ops.chol_solve_(Gf, rhs, ridge)
+            if int(info.item()) != 0:
+                raise RuntimeError(f"{self.name}: normal equations not positive definite at pivot "
+                                   f"{int(info.item()) - 1} (ridge {ridge:.3e}); raise `ridge`")
+            if bool(free.all()):
+                W[rows] = W0[rows] + rhs.T
+            else:
+                upd = torch.zeros(len(rows), self.K, dtype=torch.float64, device=dev)
+                upd[:, free.nonzero().flatten()] = rhs.T
+                W[rows] = W0[rows] + upd
+        return W, W0
+
+
+def layer_objective(W, G, R, yy_plus=0.0):
+    """sum_o (w_o G w_o - 2 w_o r_o): the layer's squared error up to the constant ||Y||^2."""
+    return float(((W @ G) * W).sum() - 2 * (W * R.T).sum()) + yy_plus
+
+
+def _train_lstsq(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, separate_classifier, num_classes,
+                 model_type, ridge, verbose, stats):
+    device = next(iter(model1.parameters())).device
+    acts1, acts2 = {}, {}
+    hooks = capture_inputs(model1, acts1) + capture_inputs(model2, acts2)
+    model1.eval()
+    model2.eval()
+    layers3 = {n: m for n, m in model3.named_modules() if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear))}
+    accs, ws = {}, _Workspace(device)
+    try:
+        with torch.no_grad():
+            for idx, batch in enumerate(dataloader):
+                if idx > MAX_STEPS:
+                    break
+                x = batch[0].to(device, non_blocking=True)
+                acts1.clear()
+                acts2.clear()
+                model1(x)
+                model2(x)
+                for name, layer in layers3.items():
+                    if name not in acts1 or name not in acts2:
+                        print(f"Key error on {name}")
+                        continue
+                    if name not in accs:
+                        bi, bo = _layer_blocks(perm_blocks, name, acts1[name][0].shape[1], num_classes,
+                                               separate_classifier, model_type)
+                        accs[name] = _LayerLS(name, layer, bi, bo, tuple(acts1[name][0].shape),
+                                              tuple(acts1[name][1].shape), device)
+                    accs[name].accumulate(acts1[name], acts2[name], ws)
+            for name, acc in accs.items():
+                layer = layers3[name]
+                W, W0 = acc.solve(layer, ridge)
+                if stats is not None:
+                    stats[name] = {"objective_init": layer_objective(W0, acc.G, acc.R),
+                                   "objective_fit": layer_objective(W, acc.G, acc.R),
+                                   "rows": acc.count, "cout": acc.cout}
+                if verbose:
+                    print(f"{name}: K={acc.K} Co={acc.cout} rows={acc.count}")
+                kw = acc.K - int(acc.has_bias)
+                layer.weight.data.copy_(W[:, :kw].reshape(layer.weight.shape).to(layer.weight.dtype))
+                if acc.has_bias:
+                    layer.bias.data.copy_(W[:, kw].to(layer.bias.dtype))
+    finally:
+        for h in hooks:
+            h.remove()
+    return model3
+
+
+def _train_adam(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, separate_classifier, merging,
+                num_classes, lr, verbose, model_type, WANDB, wandb_run):
+    """The reference's optimisation loop (:234-302, 357-397) on the same hooks/targets/masks."""
+    acts1, acts2 = {}, {}
+    hooks = capture_inputs(model1, acts1) + capture_inputs(model2, acts2)
+    model1.eval()
+    model2.eval()
+    model3, model3_dict, m3_params = get_model_dict_and_params(model3)
+    optimizer = torch.optim.Adam(m3_params, lr=lr)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, MAX_STEPS)
+    grad_masks = get_gradient_mask(perm_blocks, model3_dict)
+    assert len(grad_masks) == len(m3_params)
+    device = m3_params[0].device
+    all_layer_loss = {k: 0 for k in model3_dict}
+    tracking = 0.0
+    try:
+        for idx, batch in enumerate(dataloader):
+            if idx > MAX_STEPS:
+                break
+            with torch.no_grad():
+                x = batch[0].to(device)
+                acts1.clear()
+                acts2.clear()
+                model1(x)
+                model2(x)
+            optimizer.zero_grad()
+            total = 0.0
+            for name, layer in model3_dict.items():
+                if name not in acts1:
+                    print(f"Key error on {name}")
+                    continue
+                bi, bo = _layer_blocks(perm_blocks, name, acts1[name][0].shape[1], num_classes,
+                                       separate_classifier, model_type)
+                X, Y = get_model_orig_activations(acts1[name], acts2[name], bi, bo, merging)
+                loss = ((layer(X) - Y) ** 2).mean()
+                total = total + loss
+                all_layer_loss[name] += loss.detach()
+            total.backward()
+            for p, m in zip(m3_params, grad_masks):
+                p.grad *= m
+            optimizer.step()
+            sched.step()
+            tracking += float(total.detach())
+            if idx % 20 == 0 and idx:
+                print(f"Loss: {tracking / 20:.3f}")
+                if WANDB:
+                    metrics = {f"loss_{k}": v / 20 for k, v in all_layer_loss.items()}
+                    metrics.update(step=idx, loss=tracking / 20)
+                    wandb_run.log(metrics)
+                all_layer_loss = {k: 0 for k in model3_dict}
+                tracking = 0.0
+        sd = model3.state_dict()
+        for k, v in model3_dict.items():
+            for k2, t in v.state_dict().items():
+                sd[f"{k}.{k2}"] = t
+        model3.load_state_dict(sd)
+    finally:
+        for h in hooks:
+            h.remove()
+    return model3
+
+
+def train(dataloader, model1, model2, model3, spec, perm, costs, budget_ratios, WANDB, MAX_STEPS, wandb_run,
+          separate_classifier=False, merging="perm_gradmask", num_classes=1000, lr=5e-4, verbose=False,
+          model_type="rn50", *, solver="lstsq", ridge=1e-6, stats=None):
+    """Fit the merged model's layers to the source models' activations (reference :305-405).
+
+    Same positional signature as the reference.  ``solver="lstsq"`` (default) is the closed
+    form over the first ``MAX_STEPS + 1`` batches (the reference's loop consumes that many);
+    ``solver="adam"`` replays the reference optimiser.  ``ridge`` is relative to the mean
+    diagonal of each layer's Gram matrix.  ``stats`` (dict) receives per-layer objectives."""
+    blocks = get_blocks(spec, perm, costs, budget_ratios, False)
+    perm_blocks = copy(blocks)
+    for axis, pg in spec.items():
+        for ax in pg.state:
+            perm_blocks[ax] = perm_blocks[axis]
+    if solver == "adam":
+        return _train_adam(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, separate_classifier, merging,
+                           num_classes, lr, verbose, model_type, WANDB, wandb_run)
+    if solver != "lstsq":
+        raise ValueError("solver must be 'lstsq' or 'adam'")
+    if merging != "perm_gradmask":
+        raise NotImplementedError("the closed form implements the default 'perm_gradmask' targets; "
+                                  "use solver='adam' for the alternative targets")
+    return _train_lstsq(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, separate_classifier, num_classes,
+                        model_type, ridge, verbose, stats)

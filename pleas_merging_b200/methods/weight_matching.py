@@ -1,0 +1,154 @@
+"""Weight matching (Git Re-Basin coordinate ascent) on B200 — drop-in for
+pleas/methods/weight_matching.py:22-95.
+
+Per visited group the reference builds ``A = sum_ax W_a^(ax) W_b^(ax)^T`` with one
+transposed copy + SGEMM + add per state axis, syncs on ``A.norm()``, copies A to the host for
+SciPy, and rewrites every tensor of the group with ``index_select``.  Here a visit is: pack
+the group's model-B operands K-concatenated into one plane pair (the model-A planes are
+packed once per group), ONE 3xTF32 tcgen05 GEMM with a fused split-K reduction, the GPU LAP
+kernel on the device-resident cost matrix, a device-side progress test, and gather kernels
+for the permutation — the only host round trip is one 4-byte progress flag per sweep.  The
+visit order replays ``torch.randperm`` on a seeded CPU generator exactly like the reference.
+"""
+from collections.abc import Sequence
+from copy import copy, deepcopy
+from typing import Union
+
+import torch
+
+from .. import ops
+from ..core.solvers import b200_solve_lsa
+from ..core.utils import Permutation, PermutationSpec, StateDict, apply_perm, make_identity_perm
+from .activation_matching import cross_features_inner_product
+
+
+class _GroupPlan:
+    """Packed operands and GEMM plan of one permutation group."""
+
+    def __init__(self, pg, key, state_as, state_bs, skip_suffixes, skip_missing, device):
+        self.n = pg.size
+        self.operands = []  # (pair index, tensor name, axis, kb offset)
+        kb_total = 0
+        for ax in sorted(pg.state, key=lambda a: (a.key, a.axis)):
+            if ax.key.endswith(tuple(skip_suffixes)):
+                continue
+            for si, (sa, sb) in enumerate(zip(state_as, state_bs)):
+                if skip_missing and not (ax.key in sa and ax.key in sb):
+                    continue
+                outer, rows, inner = ops.as_rows_view(sa[ax.key], ax.axis)
+                assert rows == self.n
+                self.operands.append((si, ax.key, ax.axis, kb_total))
+                kb_total += (outer * inner + 15) // 16
+        assert kb_total > 0, f"group {key} has no weights to match"
+        self.kb = kb_total
+        self.pa = ops.Planes(self.n, kb_total, device)
+        self.pb = ops.Planes(self.n, kb_total, device)
+        for si, name, axis, off in self.operands:
+            ops.pack_split(state_as[si][name], axis, self.pa, kb_offset=off)
+        self.plan = ops.GemmPlan(self.pa, self.pb, self.n, self.n, kb_total)
+        self.cost = torch.empty(self.n, self.n, dtype=torch.float32, device=device)
+
+    def build_cost(self, state_bs):
+        for si, name, axis, off in self.operands:
+            ops.pack_split(state_bs[si][name], axis, self.pb, kb_offset=off)
+        self.plan.run()
+        self.plan.finalize(self.cost, ops.MODE_INNER, accumulate=False)
+        return self.cost
+
+
+def _to_device_state(state, keys, device):
+    for k in keys:
+        if k in state:
+            t = state[k]
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                state[k] = t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def weight_matching(
+    spec: PermutationSpec,
+    state_as: Union[StateDict, Sequence[StateDict]],
+    state_bs: Union[StateDict, Sequence[StateDict]],
+    max_iter=100,
+    init_perm=None,
+    inplace=False,
+    skip_suffixes=("running_mean", "running_var"),
+    skip_missing=True,
+    lsa_solver=b200_solve_lsa,
+    cross_weights=cross_features_inner_product,
+    verbose=True,
+    seed=0,
+    return_costs=False,
+) -> Permutation:
+    if isinstance(state_as, dict):
+        state_as = [state_as]
+    if isinstance(state_bs, dict):
+        state_bs = [state_bs]
+    assert len(state_as) == len(state_bs)
+    if not inplace:
+        state_bs = [copy(sb) for sb in state_bs]
+    first = next(iter(state_as[0].values()))
+    device = first.device if first.is_cuda else torch.device("cuda", torch.cuda.current_device())
+
+    group_keys = {ax.key for pg in spec.values() for ax in pg.state}
+    state_as = [copy(sa) for sa in state_as]
+    for sa, sb in zip(state_as, state_bs):
+        _to_device_state(sa, group_keys, device)
+        _to_device_state(sb, group_keys, device)
+
+    perm = make_identity_perm(spec) if init_perm is None else deepcopy(init_perm)
+    if init_perm is not None:
+        for sb in state_bs:
+            apply_perm(init_perm, spec, sb, inplace=True)
+    perm = {k: p.to(device=device, dtype=torch.int64).contiguous() for k, p in perm.items()}
+    perm_names = list(perm.keys())
+    all_costs = {}
+    rng = torch.Generator()
+    rng.manual_seed(seed)
+    fused = lsa_solver is b200_solve_lsa and cross_weights is cross_features_inner_product
+    plans = {}
+    flag = torch.zeros(1, dtype=torch.int32, device=device)
+    gain = torch.zeros(1, dtype=torch.float64, device=device)
+
+    with torch.no_grad():
+        for iteration in range(max_iter):
+            statuses = []
+            progress = False
+            for p_ix in torch.randperm(len(perm_names), generator=rng):
+                p = perm_names[p_ix]
+                pg = spec[p]
+                n = pg.size
+                if fused:
+                    if p not in plans:
+                        plans[p] = _GroupPlan(pg, p, state_as, state_bs, skip_suffixes, skip_missing, device)
+                    A = plans[p].build_cost(state_bs)
+                    (newP,), _, status = ops.lap_solve_batched([A], True)
+                    statuses.append(status)
+                else:
+                    A = torch.zeros(n, n, device=device)
+                    for ax in pg.state:
+                        if ax.key.endswith(tuple(skip_suffixes)):
+                            continue
+                        for sa, sb in zip(state_as, state_bs):
+                            if skip_missing and not (ax.key in sa and ax.key in sb):
+                                continue
+                            A.add_(cross_weights(sa[ax.key], sb[ax.key], ax.axis))
+                    assert A.norm() > 0
+                    newP = lsa_solver(A).to(device=device, dtype=torch.int64)
+                ops.wm_progress(A, newP, flag, gain)
+                if verbose:
+                    print(f"{iteration}/{p.key}:{p.axis}: {gain.item()}")
+                perm[p] = ops.compose_perm(perm[p], newP)
+                all_costs[p] = A
+                for sb in state_bs:
+                    apply_perm({p: newP}, spec, sb, inplace=True)
+            if statuses:
+                ops.raise_on_lap_status(torch.cat(statuses))
+            progress = bool(flag.item())
+            flag.zero_()
+            if not progress:
+                break
+        assert all(bool(c.any()) for c in all_costs.values()), "a group's weight cost matrix is all zero"
+        perm = {k: v.cpu() for k, v in perm.items()}
+        if return_costs:
+            return perm, all_costs
+        return perm

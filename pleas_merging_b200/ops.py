@@ -101,7 +101,7 @@ def choose_splits(tiles, k_blocks, target_ctas=NUM_SMS * 4, min_kb=4):
 class GemmPlan:
     """One 3xTF32 GEMM over packed planes: partial tiles + problem-table entry on device."""
 
-    def __init__(self, a, b, M, Nn, k_blocks, splits=None, symmetric=False):
+    def __init__(self, a, b, M, Nn, k_blocks, splits=None, symmetric=False, partial=None):
         self.M, self.N = M, Nn
         self.bn = choose_bn(Nn)
         self.m_tiles = (M + 127) // 128
@@ -110,7 +110,12 @@ class GemmPlan:
         self.splits = choose_splits(tiles, k_blocks) if splits is None else splits
         self.ld_m, self.ld_n = self.m_tiles * 128, self.n_tiles * self.bn
         dev = a.hi.device
-        self.partial = torch.empty(self.splits * self.ld_m * self.ld_n, dtype=torch.float32, device=dev)
+        need = self.splits * self.ld_m * self.ld_n
+        if partial is None:
+            partial = torch.empty(need, dtype=torch.float32, device=dev)
+        elif partial.numel() < need:
+            raise ValueError("GemmPlan: partial workspace too small")
+        self.partial = partial
         self.total_ctas = tiles * self.splits
         p = N.GemmProblem(a.hi.data_ptr(), a.lo.data_ptr(), b.hi.data_ptr(), b.lo.data_ptr(),
                           self.partial.data_ptr(), a.row_groups, b.row_groups, k_blocks, self.m_tiles,
@@ -303,3 +308,25 @@ def chol_solve_(G, B, ridge):
     N.check(N.lib().plb_chol_solve(G.data_ptr(), G.shape[0], B.data_ptr(), B.shape[1], float(ridge),
                                    info.data_ptr(), N.stream_ptr()), "plb_chol_solve")
     return info
+
+
+# ------------------------------------------------------------------------------------ im2col
+
+def pack_im2col(x1, x2, chan1, chan2, scale1, scale2, cmerged, kernel, stride, padding, dilation, out_hw,
+                ones_row, planes, kb_offset=0):
+    """Packs rows f=(c,dy,dx) x k=(n,ho,wo) of the merged layer input
+    s1[c]*x1[:, chan1[c]] + s2[c]*x2[:, chan2[c]] (pleas_merging.py:116-123, 146-147) into planes.
+    x1/x2: [N, C, H, W] float32 CUDA (x2 may be None)."""
+    _require_cuda_f32(x1, "pack_im2col")
+    x1 = x1.contiguous()
+    if x2 is not None:
+        _require_cuda_f32(x2, "pack_im2col")
+        x2 = x2.contiguous()
+        assert x2.shape == x1.shape
+    Nb, C, H, W = x1.shape
+    Ho, Wo = out_hw
+    N.check(N.lib().plb_pack_im2col(x1.data_ptr(), N.ptr(x2), Nb, C, H, W, N.ptr(chan1), N.ptr(chan2),
+                                    N.ptr(scale1), N.ptr(scale2), cmerged, kernel[0], kernel[1], stride[0],
+                                    stride[1], padding[0], padding[1], dilation[0], dilation[1], Ho, Wo,
+                                    int(bool(ones_row)), planes.hi.data_ptr(), planes.lo.data_ptr(),
+                                    planes.row_groups, kb_offset, N.stream_ptr()), "plb_pack_im2col")

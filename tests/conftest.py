@@ -36,7 +36,8 @@ def load_spec_json(name):
 
 
 def key_str(k):
-    return f"{k[0]}:{k[1]}"
+    key, axis = k  # tuple or Axis
+    return f"{key}:{axis}"
 
 
 @pytest.fixture(scope="session")
@@ -60,3 +61,17 @@ def lap_golden():
     z = np.load(os.path.join(GOLDEN, "lap_golden.npz"))
     names = sorted({k.split("/")[0] for k in z.files})
     return {n: {f: z[f"{n}/{f}"] for f in ("A", "maximize", "col", "obj")} for n in names}
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_library_math():
+    """cuDNN/cuBLAS TF32 is on by default for convolutions and would move activations by ~1e-3
+    relative to the CPU oracle (SURVEY.md §7 'Forward passes'); parity tests compare exact-fp32
+    forwards."""
+    import torch
+
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old

@@ -1,0 +1,241 @@
+"""Method-level parity: the drop-in API on the B200 against the golden outputs of the
+unmodified reference (tests/golden/) and the CPU oracle."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import key_str, load_spec_json
+from oracle import ref_oracle as O
+from oracle import tinynet
+
+pytestmark = pytest.mark.gpu
+
+
+def _pkg():
+    import pleas_merging_b200 as P
+
+    return P
+
+
+def _tiny(P):
+    m1, m2 = tinynet.make_pair(12, 10)
+    spec = P.get_permutation_spec(m1, ((1, 3, 16, 16),))
+    return m1.cuda(), m2.cuda(), spec
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def assert_perm_or_objective(perm, gold_perm, cost, name):
+    """Identical permutation, else an equal optimum (rel 1e-6) on the reference's cost matrix."""
+    perm, gold_perm = np.asarray(perm), np.asarray(gold_perm)
+    if (perm == gold_perm).all():
+        return
+    c = np.asarray(cost, dtype=np.float64)
+    idx = np.arange(len(perm))
+    a, b = c[idx, perm].sum(), c[idx, gold_perm].sum()
+    assert abs(a - b) <= 1e-6 * abs(b), f"{name}: objective {a} vs reference {b}"
+
+
+@pytest.mark.parametrize("cross", ["cdist", "inner"])
+@pytest.mark.parametrize("accumulate", ["reference", "sum"])
+def test_activation_matching_tiny_vs_reference(tiny_golden, cross, accumulate):
+    P = _pkg()
+    m1, m2, spec = _tiny(P)
+    loader = tinynet.make_loader(*tiny_golden["loader"])
+    cf = P.cross_features_cdist if cross == "cdist" else P.cross_features_inner_product
+    perm, costs = P.activation_matching(spec, m1, m2, loader, len(loader), cross_features=cf, output_costs=True,
+                                        accumulate=accumulate)
+    gp, gc = tiny_golden[f"am/{cross}/{accumulate}/perm"], tiny_golden[f"am/{cross}/{accumulate}/costs"]
+    assert list(perm.keys()) == list(spec.keys())
+    for k in spec:
+        assert perm[k].dtype == torch.int64 and not perm[k].is_cuda and costs[k].is_cuda
+        assert relerr(costs[k].cpu().numpy(), gc[key_str(k)].numpy()) <= 1e-4, k  # north-star matrix bar
+        assert_perm_or_objective(perm[k].numpy(), gp[key_str(k)].numpy(), gc[key_str(k)].numpy(), k)
+        assert (perm[k].numpy() == gp[key_str(k)].numpy()).all(), k  # no ties in this fixture
+
+
+def test_plugin_operators_in_generic_path(tiny_golden):
+    """The library's operators satisfy the reference's plug-in signatures: used through the
+    generic (un-fused) path with a user wrapper they reproduce the fused result."""
+    P = _pkg()
+    import importlib
+
+    AM = importlib.import_module("pleas_merging_b200.methods.activation_matching")
+
+    m1, m2, spec = _tiny(P)
+    loader = tinynet.make_loader(*tiny_golden["loader"])
+
+    def my_cross(x, y, a):
+        return P.cross_features_cdist(x, y, a)
+
+    def my_solver(A, maximize=True):
+        return P.b200_solve_lsa(A, maximize)
+
+    perm, costs = P.activation_matching(spec, m1, m2, loader, len(loader), cross_features=my_cross,
+                                        lsa_solver=my_solver, output_costs=True, accumulate="sum")
+    for k in spec:
+        assert relerr(costs[k].cpu().numpy(), tiny_golden["am/cdist/sum/costs"][key_str(k)].numpy()) <= 1e-4
+        assert (perm[k].numpy() == tiny_golden["am/cdist/sum/perm"][key_str(k)].numpy()).all()
+    # build_cross_module returns the reference's structure
+    axes = [ax for pg in spec.values() for ax in pg.node]
+    gm = AM.build_cross_module(m1, m2, axes, my_cross)
+    with torch.inference_mode():
+        (o1, o2), cross = gm(loader[-1][0].cuda())
+    assert o1.shape == o2.shape == (4, 10) and len(cross) == 22
+    gold = tiny_golden["am/cdist/taps_last"]
+    for (name, axis), v in cross.items():
+        assert relerr(v.cpu().numpy(), gold[f"{name}:{axis}"].numpy()) <= 1e-4
+
+
+def test_weight_matching_tiny_vs_reference(tiny_golden):
+    P = _pkg()
+    m1, m2, spec = _tiny(P)
+    sd2 = m2.state_dict()
+    before = {k: v.clone() for k, v in sd2.items()}
+    perm, costs = P.weight_matching(spec, m1.state_dict(), sd2, max_iter=100, seed=0, verbose=False,
+                                    return_costs=True)
+    for k in spec:
+        assert (perm[k].numpy() == tiny_golden["wm/perm"][key_str(k)].numpy()).all(), k
+        assert relerr(costs[k].cpu().numpy(), tiny_golden["wm/costs"][key_str(k)].numpy()) <= 1e-5, k
+    assert all(torch.equal(sd2[k], before[k]) for k in before)  # inplace=False leaves B untouched
+
+
+@pytest.mark.parametrize("name", ["r0", "r05", "r1", "mixed"])
+def test_partial_merge_tiny_vs_reference(tiny_golden, name):
+    P = _pkg()
+    m1, m2, spec = _tiny(P)
+    perm = {k: tiny_golden["am/cdist/sum/perm"][key_str(k)] for k in spec}
+    costs = {k: tiny_golden["am/cdist/sum/costs"][key_str(k)].cuda() for k in spec}
+    r = tiny_golden[f"pm/{name}/ratios"]
+    ratios = {k: r[key_str(k)] for k in spec} if isinstance(r, dict) else r
+    model3, blocks = P.partial_merge(spec, m1, m2, perm, costs, ratios, return_blocks=True)
+    for k in spec:
+        for mine, gold in zip(blocks[k], tiny_golden[f"pm/{name}/blocks"][key_str(k)]):
+            assert mine.dtype == torch.int64 and torch.equal(mine.cpu(), gold)
+    gold_state = tiny_golden[f"pm/{name}/state"]
+    sd3 = model3.state_dict()
+    assert set(sd3.keys()) == set(gold_state.keys())
+    for k, v in gold_state.items():
+        assert torch.equal(sd3[k].cpu(), v), k  # gathers and (a+b)/2: bit exact
+    assert not model3.training
+    assert all(not dict(model3.named_parameters())[k].requires_grad for k in gold_state if k in dict(model3.named_parameters()) and k != 'fc.bias')
+    with torch.no_grad():  # the merged module is runnable
+        assert model3(torch.randn(2, 3, 16, 16).cuda()).shape == (2, 10)
+
+
+def _merged_init(P, tiny_golden, name, m1, m2, spec):
+    perm = {k: tiny_golden["am/cdist/sum/perm"][key_str(k)] for k in spec}
+    costs = {k: tiny_golden["am/cdist/sum/costs"][key_str(k)].cuda() for k in spec}
+    ratios = tiny_golden[f"pm/{name}/ratios"]
+    return perm, costs, ratios, P.partial_merge(spec, m1, m2, perm, costs, ratios)
+
+
+@pytest.mark.parametrize("name", ["r0", "r05"])
+def test_train_closed_form_vs_reference(tiny_golden, name):
+    """Per-layer objective of the closed form: matches the fp64 optimum computed from the
+    reference's own (X-bar, Y-bar) pairs and is never worse than the reference's Adam result."""
+    P = _pkg()
+    m1, m2, spec = _tiny(P)
+    perm, costs, ratios, model3 = _merged_init(P, tiny_golden, name, m1, m2, spec)
+    loader = tinynet.make_loader(*tiny_golden["train/loader"])
+    steps = tiny_golden["train/max_steps"]
+    stats = {}
+    out = P.train(loader, m1, m2, model3, spec, perm, costs, ratios, False, steps, None, num_classes=10,
+                  model_type="rn18", stats=stats)
+    assert out is model3
+    # evaluate the fitted weights with the CPU oracle's fp64 normal equations
+    jspec = load_spec_json("tiny")
+    c1, c2 = tinynet.make_pair(12, 10)
+    ob = O.get_blocks(jspec, {g["key"]: perm[P.Axis(*g["key"])].numpy() for g in jspec},
+                      {g["key"]: costs[P.Axis(*g["key"])].cpu().numpy() for g in jspec},
+                      {g["key"]: ratios for g in jspec} if not isinstance(ratios, dict) else ratios)
+    acc = O.pleas_normal_equations(jspec, c1, c2, ob, loader, steps, num_classes=10)
+    sd3 = {k: v.detach().cpu().numpy() for k, v in model3.state_dict().items()}
+    gold = tiny_golden[f"train/{name}/layer_stats"]
+    for n, d in acc.items():
+        mine = O.layer_loss(O.flat_weight(sd3, n, f"{n}.bias" in sd3), d)
+        assert mine <= gold[n]["loss_adam"] * (1 + 1e-4) + 1e-9, (n, mine, gold[n])
+        assert mine <= gold[n]["loss_lstsq"] * (1 + 2e-2) + 1e-7, (n, mine, gold[n])
+        assert stats[n]["objective_fit"] <= stats[n]["objective_init"] + 1e-9
+
+
+def _oracle_layer_losses(P, tiny_golden, perm, costs, ratios, model3):
+    jspec = load_spec_json("tiny")
+    c1, c2 = tinynet.make_pair(12, 10)
+    loader = tinynet.make_loader(*tiny_golden["train/loader"])
+    ob = O.get_blocks(jspec, {g["key"]: perm[P.Axis(*g["key"])].numpy() for g in jspec},
+                      {g["key"]: costs[P.Axis(*g["key"])].cpu().numpy() for g in jspec}, ratios)
+    acc = O.pleas_normal_equations(jspec, c1, c2, ob, loader, tiny_golden["train/max_steps"], num_classes=10)
+    sd3 = {k: v.detach().cpu().numpy() for k, v in model3.state_dict().items()}
+    return {n: O.layer_loss(O.flat_weight(sd3, n, f"{n}.bias" in sd3), d) for n, d in acc.items()}
+
+
+def test_train_adam_replays_reference(tiny_golden):
+    """solver="adam" follows the reference trajectory: same per-layer losses, and the same
+    weights wherever the gradient is not rounding noise (conv1 is solved exactly by the init, so
+    Adam's sign-like steps there are noise-driven on any platform)."""
+    P = _pkg()
+    m1, m2, spec = _tiny(P)
+    perm, costs, ratios, model3 = _merged_init(P, tiny_golden, "r05", m1, m2, spec)
+    loader = tinynet.make_loader(*tiny_golden["train/loader"])
+    P.train(loader, m1, m2, model3, spec, perm, costs, ratios, False, tiny_golden["train/max_steps"], None,
+            num_classes=10, model_type="rn18", solver="adam")
+    gold_state = tiny_golden["train/r05/adam_state"]
+    gold = tiny_golden["train/r05/layer_stats"]
+    for n, mine in _oracle_layer_losses(P, tiny_golden, perm, costs, ratios, model3).items():
+        assert mine == pytest.approx(gold[n]["loss_adam"], rel=2e-2, abs=1e-6), n
+    for k, v in model3.state_dict().items():
+        if not k.startswith("conv1."):
+            assert torch.allclose(v.cpu(), gold_state[k], rtol=1e-2, atol=2e-4), k
+
+
+def test_activation_matching_rn18_vs_reference(rn18_golden):
+    import torchvision
+
+    P = _pkg()
+    torch.manual_seed(0)
+    m1 = torchvision.models.resnet18().eval()
+    torch.manual_seed(1)
+    m2 = torchvision.models.resnet18().eval()
+    spec = P.get_permutation_spec(m1, ((1, 3, 64, 64),))
+    nb, b, hw, seed = rn18_golden["loader"]
+    g = torch.Generator().manual_seed(seed)
+    loader = [(torch.randn(b, 3, hw, hw, generator=g), 0) for _ in range(nb)]
+    # oracle costs on the same inputs (CPU forward) to judge near-ties
+    ocosts = O.matching_costs(load_spec_json("resnet18"), m1, m2, loader, nb, "cdist", "sum")
+    perm, costs = P.activation_matching(spec, m1.cuda(), m2.cuda(), loader, nb, output_costs=True, accumulate="sum")
+    for k in spec:
+        ks = key_str(k)
+        assert relerr(costs[k].cpu().numpy(), ocosts[(k.key, k.axis)]) <= 1e-4, k
+        assert_perm_or_objective(perm[k].numpy(), rn18_golden["am/cdist/sum/perm"][ks].numpy().astype(np.int64),
+                                 ocosts[(k.key, k.axis)], ks)
+
+
+def test_planted_permutation_is_recovered():
+    """Merging a model with a permuted copy of itself: both matchers recover the planted
+    permutation and the ratio-0 merge reproduces the original function."""
+    P = _pkg()
+    m1, _ = tinynet.make_pair(12, 10)
+    spec = P.get_permutation_spec(m1, ((1, 3, 16, 16),))
+    planted = P.make_random_perm(spec, generator=torch.Generator().manual_seed(9))
+    m2 = copy.deepcopy(m1)
+    P.apply_perm(planted, spec, m2, inplace=True)
+    m1, m2 = m1.cuda(), m2.cuda()
+    x = torch.randn(4, 3, 16, 16, generator=torch.Generator().manual_seed(10))
+    with torch.no_grad():
+        assert torch.allclose(m1(x.cuda()), m2(x.cuda()), rtol=1e-4, atol=1e-5)
+    loader = [(x, 0)]
+    inv = P.invert_perm(planted)
+    perm_am, costs = P.activation_matching(spec, m1, m2, loader, 1, output_costs=True)
+    perm_wm = P.weight_matching(spec, m1.state_dict(), m2.state_dict(), verbose=False)
+    for k in spec:
+        assert torch.equal(perm_am[k], inv[k]), k
+        assert torch.equal(perm_wm[k], inv[k]), k
+    merged = P.partial_merge(spec, m1, m2, perm_am, costs, 0.0)
+    with torch.no_grad():
+        assert torch.allclose(merged(x.cuda()), m1(x.cuda()), rtol=1e-4, atol=1e-5)
