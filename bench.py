@@ -1,0 +1,323 @@
+"""Benchmark of the merge hot path on BASELINE.json's config 2: ResNet-50 pair, activation
+matching over synthetic 224x224 batches of 32 (+ the rest of the merge: LAP, partial_merge,
+PLeaS closed form over MAX_STEPS+1 batches).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A *step* is one calibration batch through activation matching's accumulation loop (two model
+forwards + one fused pack/GEMM/epilogue per tap — 174 taps for ResNet-50).  ``value`` is
+calibration samples/s with the batches already resident in HBM; ``e2e`` is the same metric
+through the public ``activation_matching`` call with pinned HOST batches (H2D copy of every
+batch and the D2H read of the permutations inside the timed region).  The whole merge
+(activation matching -> LAP -> partial_merge -> PLeaS) is timed once as ``merge_wall_s``.
+
+``--impl reference`` times the reference's CPU path (the oracle restatement, torch CPU + numpy
++ the C LAP port, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 32
+HW = 224
+METRIC = "rn50_pair_merge_calib_samples_per_s"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="resnet50")
+    ap.add_argument("--pleas-steps", type=int, default=None, help="MAX_STEPS of the PLeaS pass (default 400, "
+                    "or 4*steps when steps < 100)")
+    ap.add_argument("--no-merge", action="store_true", help="skip the one-off whole-merge timing")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="samples per CPU-baseline batch")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 7:
+                reasons |= {n for n, v in zip(names, r[3:7]) if v.lower().startswith("active")}
+        mx = max((float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def make_models(name, device=None):
+    import torch
+    import torchvision
+
+    torch.manual_seed(0)
+    m1 = getattr(torchvision.models, name)().eval()
+    torch.manual_seed(1)
+    m2 = getattr(torchvision.models, name)().eval()
+    if device is not None:
+        m1, m2 = m1.to(device), m2.to(device)
+    return m1, m2
+
+
+# ------------------------------------------------------------------------------ reference arm
+
+def run_reference(args):
+    """The reference's CPU path (oracle port) on a bounded sample: K steps of `cpu_sample`
+    samples each through matching_costs (two forwards + 174 -cdist taps), all host threads."""
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import ref_oracle as O
+
+    torch.set_num_threads(os.cpu_count())
+    m1, m2 = make_models(args.model)
+    import pleas_merging_b200 as P
+
+    spec = P.get_permutation_spec(m1, ((1, 3, 64, 64),))
+    jspec = [{"key": (k.key, k.axis), "size": pg.size, "state": sorted((a.key, a.axis) for a in pg.state),
+              "node": sorted((a.key, a.axis) for a in pg.node)} for k, pg in spec.items()]
+    b = args.cpu_sample
+    g = torch.Generator().manual_seed(123)
+    steps = min(args.steps, 3)  # bounded: ~10 s of CPU work per step on 8 cores
+    warm = min(args.warmup, 1)
+    loader = [(torch.randn(b, 3, HW, HW, generator=g), 0) for _ in range(steps + warm)]
+    if warm:
+        O.matching_costs(jspec, m1, m2, loader[:warm], warm, "cdist", "sum")
+    t0 = time.perf_counter()
+    O.matching_costs(jspec, m1, m2, loader[warm:], steps, "cdist", "sum")
+    dt = time.perf_counter() - t0
+    v = steps * b / dt
+    sample = f"{steps} steps x {b} samples of {HW}x{HW} through the oracle port of activation_matching's cost loop"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} pair, activation_matching cost loop (-cdist), {b} samples/step "
+                               f"(bounded sample of the 32-sample batch), CPU reference path"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------ B200 arm
+
+def cpu_baseline(args, spec):
+    import torch
+
+    from oracle import ref_oracle as O
+
+    torch.set_num_threads(os.cpu_count())
+    m1, m2 = make_models(args.model)
+    jspec = [{"key": (k.key, k.axis), "size": pg.size, "state": sorted((a.key, a.axis) for a in pg.state),
+              "node": sorted((a.key, a.axis) for a in pg.node)} for k, pg in spec.items()]
+    b = args.cpu_sample
+    g = torch.Generator().manual_seed(123)
+    loader = [(torch.randn(b, 3, HW, HW, generator=g), 0) for _ in range(3)]
+    O.matching_costs(jspec, m1, m2, loader[:1], 1, "cdist", "sum")  # warm-up
+    t0 = time.perf_counter()
+    O.matching_costs(jspec, m1, m2, loader[1:], 2, "cdist", "sum")
+    dt = time.perf_counter() - t0
+    return {"value": 2 * b / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"2 batches x {b} samples of {HW}x{HW} through the oracle port of the activation_matching "
+                      f"cost loop (2 forwards + all -cdist taps), after 1 warm-up batch"}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    import pleas_merging_b200 as P
+    from pleas_merging_b200 import _native, ops
+    import importlib
+
+    AM = importlib.import_module("pleas_merging_b200.methods.activation_matching")
+
+    # exact-fp32 library forwards: the permutations must reproduce the reference's
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+
+    K, W = args.steps, max(args.warmup, 0)
+    m1, m2 = make_models(args.model, device)
+    spec = P.get_permutation_spec(m1, ((1, 3, HW, HW),))
+    taps = sum(len(pg.node) for pg in spec.values())
+
+    # synthetic calibration batches, resident in HBM (weak scaling: K batches per GPU)
+    gen = torch.Generator(device=device).manual_seed(123 + rank)
+    n_dev = min(K + W, 16)  # distinct batches; each step's activations (~10 GB) dwarf the 126 MB L2
+    dev_batches = [torch.randn(BATCH, 3, HW, HW, generator=gen, device=device) for _ in range(n_dev)]
+
+    acc = AM.CrossAccumulator(spec, ops.MODE_NEG_CDIST, device)
+    axes = [ax for pg in spec.values() for ax in pg.node]
+    gm = AM._dual_graph(m1, m2, axes, acc.emit)
+
+    def step(i):
+        acc.begin_batch(reset_costs=False)
+        gm(dev_batches[i % n_dev])
+
+    with torch.inference_mode():
+        for i in range(W):
+            step(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        ops.GEMM_TIMER = []
+        _native.LAUNCH_COUNTS.clear()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(K):
+            step(W + i)
+        if world > 1:  # the path's one exchange: all-reduce of the cost accumulators over NVLink
+            dist.all_reduce(acc.flat)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        timer, ops.GEMM_TIMER = ops.GEMM_TIMER, None
+        launches = sum(_native.LAUNCH_COUNTS.values())
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in timer)
+    gemm_flops = sum(f for _, _, f, _ in timer)
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * K * BATCH / (ms_max / 1e3)
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+           "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{args.model} pair (random init, eval), activation_matching accumulation over "
+                                  f"{K} batches of {BATCH}x3x{HW}x{HW} per GPU, -cdist statistic on {taps} taps, "
+                                  f"accumulate=sum, 3xTF32 tcgen05 GEMM, exact-fp32 cuDNN forwards",
+                      "parallelism": f"batch-sharded x{world}, one NCCL all-reduce of the cost matrices",
+                      "l2": "inputs larger than L2: every step streams ~10 GB of activations"},
+           "gpu_launches": launches}
+    pk = peaks()
+    tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+    achieved = 3.0 * gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    out["roofline"] = {
+        "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+        "traffic": None, "kernel": "gemm3xtf32_kernel",
+        "note": f"achieved = 3 x algorithmic FLOPs (3xTF32 issues three tensor-pipe passes; algorithmic = "
+                f"2*C^2*K per tap, {gemm_flops / K / 1e12:.3f} TFLOP per step) / summed CUDA-event time of the "
+                f"{len(timer)} GEMM launches in the timed region; peak = {pk['source']} sustained bf16 "
+                f"{pk['bf16_tflops_sustained']} TFLOP/s / 2 (TF32 dense rate)",
+        "algorithmic_tflops": gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0,
+        "kernel_share_of_step": gemm_ms / ms}
+    out["clocks"] = clocks
+
+    # ---- e2e through the public API with pinned host batches (H2D + LAP + D2H of the perms inside)
+    with torch.inference_mode():
+        host = [(b.cpu().pin_memory(), 0) for b in dev_batches]
+    Ke = K
+    loader = [host[i % n_dev] for i in range(Ke)]
+    P.activation_matching(spec, m1, m2, loader[:2], 2, accumulate="sum")  # warm the public path
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    perm, costs = P.activation_matching(spec, m1, m2, loader, Ke, output_costs=True, accumulate="sum",
+                                        distributed=world > 1)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    d2h = sum(p.numel() * 8 for p in perm.values())
+    out["e2e"] = {"value": Ke * BATCH / dt, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * HW * HW * 4,
+                  "d2h_bytes_per_step": d2h / Ke, "wall_s": dt,
+                  "note": "activation_matching(spec, m1, m2, pinned host loader, K, accumulate='sum'): H2D of "
+                          "every batch, all taps, batched GPU LAP, D2H of the permutations"}
+
+    if rank != 0:  # the remaining legs are single-GPU; rank 0 reports
+        dist.destroy_process_group()
+        return
+
+    # ---- the whole merge once: activation matching -> partial_merge -> PLeaS closed form
+    if not args.no_merge and world == 1:
+        ps = args.pleas_steps if args.pleas_steps is not None else (400 if K >= 100 else 4 * K)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model3 = P.partial_merge(spec, m1, m2, perm, costs, 0.0)
+        torch.cuda.synchronize()
+        t_merge = time.perf_counter() - t0
+        ploader = [host[i % n_dev] for i in range(ps + 1)]
+        t0 = time.perf_counter()
+        P.train(ploader, m1, m2, model3, spec, perm, costs, 0.0, False, ps, None, num_classes=1000,
+                model_type="rn50")
+        torch.cuda.synchronize()
+        t_train = time.perf_counter() - t0
+        out["merge"] = {"activation_matching_s": dt, "am_batches": Ke, "partial_merge_s": t_merge,
+                        "pleas_train_s": t_train, "pleas_batches": ps + 1,
+                        "merge_wall_s": dt + t_merge + t_train,
+                        "pleas_samples_per_s": (ps + 1) * BATCH / t_train}
+
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, spec)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

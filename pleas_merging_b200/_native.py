@@ -65,7 +65,13 @@ def lib():
     return _lib
 
 
+import collections
+
+LAUNCH_COUNTS = collections.Counter()  # C-ABI calls by entry point (each launches >= 1 kernel)
+
+
 def check(rc, what):
+    LAUNCH_COUNTS[what] += 1
     if rc != 0:
         msg = lib().plb_last_error_string().decode(errors="replace")
         raise RuntimeError(f"pleas_merging_b200: {what} failed with status {rc}: {msg}")

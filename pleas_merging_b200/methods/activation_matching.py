@@ -26,6 +26,7 @@ from torch.nn import Module
 from .. import ops
 from ..core.solvers import b200_solve_lsa, solve_lsa_batched
 from ..core.utils import Axis, Permutation, PermutationSpec
+from ..parallel import BatchSharder, combine_costs_
 
 
 # ------------------------------------------------------------------ plug-compatible operators
@@ -135,7 +136,7 @@ class _View:
 
 
 class _Tap:
-    __slots__ = ("name", "axis", "group", "shape", "ra", "rb", "kb", "q", "plan", "version", "pa", "pb")
+    __slots__ = ("name", "axis", "group", "shape", "ra", "rb", "kb", "K", "q", "plan", "version", "pa", "pb")
 
 
 class CrossAccumulator:
@@ -186,6 +187,7 @@ class CrossAccumulator:
         if (ra, rb) != (n, n):
             raise ValueError(f"tap {t.name}:{t.axis} has {ra}x{rb} units but its group has {n}")
         t.shape, t.ra, t.rb, t.kb = (tuple(xa.shape), tuple(xb.shape)), ra, rb, (oa * ia + 15) // 16
+        t.K = oa * ia
         t.q = torch.zeros(ra + rb, dtype=torch.float64, device=self.device) \
             if self.mode == ops.MODE_NEG_CDIST else None
         t.version = -1
@@ -201,6 +203,7 @@ class CrossAccumulator:
         t.pa = _View(b[0], b[1], t.ra, rga, t.kb)
         t.pb = _View(b[2], b[3], t.rb, rgb, t.kb)
         t.plan = ops.GemmPlan(t.pa, t.pb, t.ra, t.rb, t.kb, splits=splits, partial=self.arena.partial)
+        t.plan.alg_flops = 2.0 * t.ra * t.rb * t.K
         t.version = self.arena.version
 
     def tap(self, idx, xa, xb):
@@ -253,16 +256,18 @@ def compute_matching_costs(spec: PermutationSpec, gm_cross: Module, dataloader, 
     return costs
 
 
-def _fused_costs(spec, model1, model2, dataloader, num_batches, mode, accumulate):
+def _fused_costs(spec, model1, model2, dataloader, num_batches, mode, accumulate, distributed=False):
     device = _model_device(model1)
     acc = CrossAccumulator(spec, mode, device)
     try:
         axes = [ax for pg in spec.values() for ax in pg.node]
         gm = _dual_graph(model1, model2, axes, acc.emit)
+        sharder = BatchSharder(dataloader, num_batches, *(() if distributed else (0, 1)))
         with torch.inference_mode():
-            for (x, _), _ in zip(dataloader, range(num_batches)):
+            for _, (x, _) in sharder:
                 acc.begin_batch(reset_costs=(accumulate == "reference"))
                 gm(x.to(device, non_blocking=True))
+        combine_costs_(acc.flat, sharder, accumulate)
         return {k: c for k, c in zip(acc.keys, acc.costs)}
     finally:
         acc.close()
@@ -279,18 +284,24 @@ def activation_matching(
     output_costs=False,
     *,
     accumulate="reference",
+    distributed=False,
 ) -> Permutation:
     """Permute model2's units to match model1's activations (reference :139-177).
 
     Returns ``{group key: CPU int64[n]}`` in spec order, plus the device fp32 ``[n, n]`` cost
     matrices when ``output_costs`` is set.  With the library's own ``cross_features`` /
     ``lsa_solver`` (the defaults) the fused kernels run; any other callable is honoured through
-    the generic per-tap path."""
+    the generic per-tap path.  ``distributed=True`` (inside an initialised torch.distributed
+    job, every rank passing the SAME loader) deals the batches round-robin over the ranks and
+    sums the cost matrices with one all-reduce; every rank returns the full result."""
     if accumulate not in ("reference", "sum"):
         raise ValueError("accumulate must be 'reference' or 'sum'")
     if cross_features in _FUSED_MODES:
-        costs = _fused_costs(spec, model1, model2, dataloader, num_batches, _FUSED_MODES[cross_features], accumulate)
+        costs = _fused_costs(spec, model1, model2, dataloader, num_batches, _FUSED_MODES[cross_features], accumulate,
+                             distributed)
     else:
+        if distributed:
+            raise NotImplementedError("distributed=True needs the library's own cross_features operators")
         axes = [ax for pg in spec.values() for ax in pg.node]
         gm = build_cross_module(model1, model2, axes, cross_features)
         costs = compute_matching_costs(spec, gm, dataloader, num_batches, accumulate)

@@ -231,20 +231,29 @@ class _LayerLS:
             rows = (inverse == pi).nonzero().flatten().to(dev)
             if not bool(free.any()):
                 continue
-            if bool(free.all()):
-                Gf, rhs = self.G.clone(), grad[:, rows].contiguous()
+            idx = None if bool(free.all()) else free.nonzero().flatten()
+            # The Gram matrix carries fp32-level noise (3xTF32, ~1e-6 of its entries); when the data
+            # do not span all features (few samples, dead channels) the ridge must dominate that
+            # noise, so a failed pivot escalates it tenfold instead of aborting.
+            r = ridge
+            for attempt in range(6):
+                if idx is None:
+                    Gf, rhs = self.G.clone(), grad[:, rows].contiguous()
+                else:
+                    Gf, rhs = self.G[idx][:, idx].contiguous(), grad[idx][:, rows].contiguous()
+                info = int(ops.chol_solve_(Gf, rhs, r).item())
+                if info == 0:
+                    break
+                r *= 10.0
             else:
-                idx = free.nonzero().flatten()
-                Gf, rhs = self.G[idx][:, idx].contiguous(), grad[idx][:, rows].contiguous()
-            info = ops.chol_solve_(Gf, rhs, ridge)
-            if int(info.item()) != 0:
-                raise RuntimeError(f"{self.name}: normal equations not positive definite at pivot "
-                                   f"{int(info.item()) - 1} (ridge {ridge:.3e}); raise `ridge`")
+                raise RuntimeError(f"{self.name}: normal equations not positive definite at pivot {info - 1} "
+                                   f"even with ridge {r:.3e}")
+            self.ridge_used = max(getattr(self, "ridge_used", 0.0), r)
             if bool(free.all()):
                 W[rows] = W0[rows] + rhs.T
             else:
                 upd = torch.zeros(len(rows), self.K, dtype=torch.float64, device=dev)
-                upd[:, free.nonzero().flatten()] = rhs.T
+                upd[:, idx] = rhs.T
                 W[rows] = W0[rows] + upd
         return W, W0
 
@@ -289,7 +298,8 @@ def _train_lstsq(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, sep
                 if stats is not None:
                     stats[name] = {"objective_init": layer_objective(W0, acc.G, acc.R),
                                    "objective_fit": layer_objective(W, acc.G, acc.R),
-                                   "rows": acc.count, "cout": acc.cout}
+                                   "rows": acc.count, "cout": acc.cout,
+                                   "ridge_rel": getattr(acc, "ridge_used", 0.0) / max(float(acc.G.diagonal().mean()), 1e-300)}
                 if verbose:
                     print(f"{name}: K={acc.K} Co={acc.cout} rows={acc.count}")
                 kw = acc.K - int(acc.has_bias)
@@ -366,13 +376,13 @@ def _train_adam(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, sepa
 
 def train(dataloader, model1, model2, model3, spec, perm, costs, budget_ratios, WANDB, MAX_STEPS, wandb_run,
           separate_classifier=False, merging="perm_gradmask", num_classes=1000, lr=5e-4, verbose=False,
-          model_type="rn50", *, solver="lstsq", ridge=1e-6, stats=None):
+          model_type="rn50", *, solver="lstsq", ridge=1e-5, stats=None):
     """Fit the merged model's layers to the source models' activations (reference :305-405).
 
     Same positional signature as the reference.  ``solver="lstsq"`` (default) is the closed
     form over the first ``MAX_STEPS + 1`` batches (the reference's loop consumes that many);
     ``solver="adam"`` replays the reference optimiser.  ``ridge`` is relative to the mean
-    diagonal of each layer's Gram matrix.  ``stats`` (dict) receives per-layer objectives."""
+    diagonal of each layer's Gram matrix and is escalated tenfold when a pivot fails.  ``stats`` (dict) receives per-layer objectives."""
     blocks = get_blocks(spec, perm, costs, budget_ratios, False)
     perm_blocks = copy(blocks)
     for axis, pg in spec.items():

@@ -17,6 +17,9 @@ NUM_SMS = 148
 _GEMM_IMPL = {"tcgen05": 0, "simt": 1}[os.environ.get("PLB_GEMM_IMPL", "tcgen05")]
 
 
+GEMM_TIMER = None  # set to a list by bench.py to collect (start, end, flops, bn) per GEMM launch
+
+
 def set_gemm_impl(name):
     global _GEMM_IMPL
     _GEMM_IMPL = {"tcgen05": 0, "simt": 1}[name]
@@ -123,8 +126,19 @@ class GemmPlan:
         raw = bytes(p)
         self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
         self._keep = (a, b)
+        self.alg_flops = 2.0 * M * Nn * k_blocks * 16  # callers that know the unpadded K overwrite
 
     def run(self, impl=None):
+        if GEMM_TIMER is not None:  # bench instrumentation: CUDA events around this launch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self._launch(impl)
+            e1.record()
+            GEMM_TIMER.append((e0, e1, self.alg_flops, self.bn))
+            return
+        self._launch(impl)
+
+    def _launch(self, impl=None):
         N.check(N.lib().plb_gemm_grouped(self.table.data_ptr(), 1, self.total_ctas, self.bn,
                                          _GEMM_IMPL if impl is None else impl, N.stream_ptr()),
                 "plb_gemm_grouped")

@@ -1,0 +1,64 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch on the
+B200 box, gloo in CPU tests).
+
+The merge path shards only where the work splits naturally: calibration
+batches are dealt round-robin at WHOLE-batch granularity (the -cdist statistic takes a sqrt per
+batch, so a batch is never split) and the additive accumulators — group cost matrices, PLeaS
+normal equations — are summed with ONE all-reduce at the end.  There is no collective inside
+the data path.
+"""
+import torch
+import torch.distributed as dist
+
+
+def world():
+    """(rank, world_size); (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_batches(loader, num_batches, rank, world_size):
+    """Yields (global_index, batch) for this rank's share of the first num_batches batches.
+    Returns the total number of batches seen through ``.total`` of the generator's holder."""
+    for idx, (batch, _) in enumerate(zip(loader, range(num_batches))):
+        if idx % world_size == rank:
+            yield idx, batch
+
+
+class BatchSharder:
+    """Iterates this rank's batches and remembers how many batches existed in total."""
+
+    def __init__(self, loader, num_batches, rank=None, world_size=None):
+        r, w = world()
+        self.rank = r if rank is None else rank
+        self.world = w if world_size is None else world_size
+        self.loader, self.num_batches, self.total = loader, num_batches, 0
+
+    def __iter__(self):
+        self.total = 0
+        for idx, (batch, _) in enumerate(zip(self.loader, range(self.num_batches))):
+            self.total = idx + 1
+            if idx % self.world == self.rank:
+                yield idx, batch
+
+    def owns_last(self):
+        """True on the rank that processed the globally last batch (reference accumulate mode)."""
+        return self.total > 0 and (self.total - 1) % self.world == self.rank
+
+
+def allreduce_sum_(tensor):
+    """In-place sum over ranks (no-op for a single process)."""
+    if world()[1] > 1:
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
+    return tensor
+
+
+def combine_costs_(flat, sharder, accumulate):
+    """Combines per-rank cost accumulators: a sum in "sum" mode; in "reference" mode (only the
+    last processed batch counts) the owner of the global last batch wins."""
+    if sharder.world == 1:
+        return flat
+    if accumulate == "reference" and not sharder.owns_last():
+        flat.zero_()
+    return allreduce_sum_(flat)
