@@ -10,19 +10,35 @@
 
 namespace plb {
 
+// Block = 32 columns x 8 split lanes: the K-split partials of one output element are summed by
+// 8 threads in parallel (fp64, fixed order => deterministic), then combined through shared memory.
 template <typename OutT>
 __global__ void __launch_bounds__(256) cross_finalize_kernel(const float *__restrict__ partial, int splits,
                                                              int64_t ld_m, int64_t ld_n, int64_t M, int64_t N,
                                                              const double *__restrict__ qa,
                                                              const double *__restrict__ qb, int mode,
                                                              OutT *__restrict__ cost, int64_t ldc, int accumulate) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double red[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t j = (int64_t)blockIdx.x * 32 + tx;
   const int64_t i = blockIdx.y;
-  if (j >= N) return;
   const int64_t split_stride = ld_m * ld_n;
-  const float *p = partial + i * ld_n + j;
-  double gs = 0.0;  // fp64 sum of the (short-chain) split partials
-  for (int s = 0; s < splits; ++s) gs += (double)p[(int64_t)s * split_stride];
+  double gs = 0.0;
+  if (j < N) {
+    const float *p = partial + i * ld_n + j;
+    int s = ty;
+    for (; s + 24 < splits; s += 32) {  // 4 independent loads in flight per thread
+      const float a = p[(int64_t)s * split_stride], b = p[(int64_t)(s + 8) * split_stride];
+      const float c = p[(int64_t)(s + 16) * split_stride], d = p[(int64_t)(s + 24) * split_stride];
+      gs += ((double)a + (double)b) + ((double)c + (double)d);
+    }
+    for (; s < splits; s += 8) gs += (double)p[(int64_t)s * split_stride];
+  }
+  red[ty][tx] = gs;
+  __syncthreads();
+  if (ty != 0 || j >= N) return;
+#pragma unroll
+  for (int k = 1; k < 8; ++k) gs += red[k][tx];
   const float g = (float)gs;
   float v = g;
   if (mode == PLB_MODE_NEG_CDIST) {
@@ -46,13 +62,13 @@ extern "C" int plb_cross_finalize(const float *partial, int32_t splits, int64_t 
   PLB_REQUIRE(mode == PLB_MODE_INNER || (mode == PLB_MODE_NEG_CDIST && qa && qb), PLB_EINVAL,
               "plb_cross_finalize: mode needs row norms");
   PLB_REQUIRE(M <= 65535, PLB_ESIZE, "plb_cross_finalize: M too large");
-  dim3 grid((unsigned)ceil_div(N, 256), (unsigned)M);
+  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)M), block(32, 8);
   cudaStream_t s = (cudaStream_t)stream;
   if (cost64)
-    cross_finalize_kernel<double><<<grid, 256, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost64, ldc,
+    cross_finalize_kernel<double><<<grid, block, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost64, ldc,
                                                        accumulate);
   else
-    cross_finalize_kernel<float><<<grid, 256, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost, ldc,
+    cross_finalize_kernel<float><<<grid, block, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost, ldc,
                                                       accumulate);
   return launch_status("cross_finalize_kernel");
 }

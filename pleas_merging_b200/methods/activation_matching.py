@@ -206,6 +206,12 @@ class CrossAccumulator:
         t.plan.alg_flops = 2.0 * t.ra * t.rb * t.K
         t.version = self.arena.version
 
+    def rebind_stale(self):
+        """Binds every tap against the final arena (outside any graph capture)."""
+        for t in self.taps:
+            if t.shape is not None and t.version != self.arena.version:
+                self._bind(t)
+
     def tap(self, idx, xa, xb):
         t = self.taps[idx]
         self.seen.add(idx)
@@ -256,21 +262,78 @@ def compute_matching_costs(spec: PermutationSpec, gm_cross: Module, dataloader, 
     return costs
 
 
-def _fused_costs(spec, model1, model2, dataloader, num_batches, mode, accumulate, distributed=False):
-    device = _model_device(model1)
-    acc = CrossAccumulator(spec, mode, device)
-    try:
+class CalibrationRunner:
+    """Streams calibration batches through the dual-model graph.
+
+    The per-batch pipeline is ~1 700 kernel launches for a ResNet-50 pair (two forwards + four
+    kernels per tap), which a Python launch loop cannot issue as fast as a B200 executes them.
+    So the first batch of each input shape runs eagerly (it binds the staging memory and warms
+    cuDNN), the second is captured into a CUDA graph, and every later batch is one graph replay
+    fed through a static input buffer."""
+
+    def __init__(self, spec, model1, model2, mode, accumulate="reference", use_cuda_graph=True):
+        self.device = _model_device(model1)
+        self.acc = CrossAccumulator(spec, mode, self.device)
         axes = [ax for pg in spec.values() for ax in pg.node]
-        gm = _dual_graph(model1, model2, axes, acc.emit)
+        self.gm = _dual_graph(model1, model2, axes, self.acc.emit)
+        self.reset = accumulate == "reference"
+        self.use_cuda_graph = use_cuda_graph
+        self.graphs = {}
+
+    def close(self):
+        self.graphs.clear()
+        self.acc.close()
+
+    def _eager(self, x):
+        self.acc.begin_batch(reset_costs=self.reset)
+        self.gm(x)
+
+    def run(self, x):
+        """One calibration batch (x on the models' device)."""
+        if not self.use_cuda_graph:
+            return self._eager(x)
+        key = (tuple(x.shape), x.dtype)
+        entry = self.graphs.get(key)
+        if entry is None:
+            self._eager(x)
+            self.acc.rebind_stale()
+            self.graphs[key] = "warm"
+            return
+        if entry == "warm":
+            static_x = x.clone()
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            try:
+                with torch.cuda.graph(graph):
+                    self._eager(static_x)
+            except Exception as e:  # capture is an optimisation: same kernels either way
+                import warnings
+
+                warnings.warn(f"CUDA-graph capture of the calibration step failed ({e}); running eagerly")
+                self.use_cuda_graph = False
+                torch.cuda.synchronize()
+                return self._eager(x)
+            self.graphs[key] = (graph, static_x)
+            graph.replay()
+            return
+        graph, static_x = entry
+        static_x.copy_(x, non_blocking=True)
+        graph.replay()
+
+
+def _fused_costs(spec, model1, model2, dataloader, num_batches, mode, accumulate, distributed=False,
+                 use_cuda_graph=True):
+    runner = CalibrationRunner(spec, model1, model2, mode, accumulate, use_cuda_graph)
+    try:
         sharder = BatchSharder(dataloader, num_batches, *(() if distributed else (0, 1)))
         with torch.inference_mode():
             for _, (x, _) in sharder:
-                acc.begin_batch(reset_costs=(accumulate == "reference"))
-                gm(x.to(device, non_blocking=True))
+                runner.run(x.to(runner.device, non_blocking=True))
+        acc = runner.acc
         combine_costs_(acc.flat, sharder, accumulate)
-        return {k: c for k, c in zip(acc.keys, acc.costs)}
+        return {k: c.clone() for k, c in zip(acc.keys, acc.costs)}
     finally:
-        acc.close()
+        runner.close()
 
 
 def activation_matching(
@@ -285,6 +348,7 @@ def activation_matching(
     *,
     accumulate="reference",
     distributed=False,
+    use_cuda_graph=True,
 ) -> Permutation:
     """Permute model2's units to match model1's activations (reference :139-177).
 
@@ -298,7 +362,7 @@ def activation_matching(
         raise ValueError("accumulate must be 'reference' or 'sum'")
     if cross_features in _FUSED_MODES:
         costs = _fused_costs(spec, model1, model2, dataloader, num_batches, _FUSED_MODES[cross_features], accumulate,
-                             distributed)
+                             distributed, use_cuda_graph)
     else:
         if distributed:
             raise NotImplementedError("distributed=True needs the library's own cross_features operators")

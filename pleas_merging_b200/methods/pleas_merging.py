@@ -376,7 +376,7 @@ def _train_adam(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, sepa
 
 def train(dataloader, model1, model2, model3, spec, perm, costs, budget_ratios, WANDB, MAX_STEPS, wandb_run,
           separate_classifier=False, merging="perm_gradmask", num_classes=1000, lr=5e-4, verbose=False,
-          model_type="rn50", *, solver="lstsq", ridge=1e-5, stats=None):
+          model_type="rn50", *, solver="lstsq", ridge=1e-6, stats=None):
     """Fit the merged model's layers to the source models' activations (reference :305-405).
 
     Same positional signature as the reference.  ``solver="lstsq"`` (default) is the closed
