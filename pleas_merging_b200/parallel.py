@@ -18,14 +18,6 @@ def world():
     return 0, 1
 
 
-def shard_batches(loader, num_batches, rank, world_size):
-    """Yields (global_index, batch) for this rank's share of the first num_batches batches.
-    Returns the total number of batches seen through ``.total`` of the generator's holder."""
-    for idx, (batch, _) in enumerate(zip(loader, range(num_batches))):
-        if idx % world_size == rank:
-            yield idx, batch
-
-
 class BatchSharder:
     """Iterates this rank's batches and remembers how many batches existed in total."""
 

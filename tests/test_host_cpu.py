@@ -1,0 +1,186 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every declared symbol, the
+spec compiler reproduces the reference's specs, the data model interoperates with the
+reference's, and the multi-GPU plumbing works across two gloo ranks."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, load_spec_json
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    from pleas_merging_b200 import _native, build
+
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "pleas_b200.h")).read()
+    declared = set(re.findall(r"\b(plb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.EXPORTED_SYMBOLS), declared ^ set(_native.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    lib.plb_version.restype = ctypes.c_int
+    assert lib.plb_version() >= 100
+    # host-only helper: plane geometry
+    lib.plb_plane_bytes.restype = ctypes.c_int64
+    lib.plb_plane_bytes.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32),
+                                    ctypes.POINTER(ctypes.c_int32)]
+    rg, kb = ctypes.c_int32(), ctypes.c_int32()
+    assert lib.plb_plane_bytes(200, 1000, ctypes.byref(rg), ctypes.byref(kb)) == 32 * 63 * 512
+    assert (rg.value, kb.value) == (32, 63)
+    assert lib.plb_plane_bytes(0, 5, None, None) < 0  # invalid argument, no crash
+
+
+def test_gemm_problem_struct_matches_header():
+    from pleas_merging_b200 import _native
+
+    assert ctypes.sizeof(_native.GemmProblem) == 5 * 8 + 8 * 4
+
+
+def test_product_fails_loudly_without_cuda():
+    """No CPU fallback: calling an operator on CPU tensors raises instead of computing."""
+    import pleas_merging_b200 as P
+
+    with pytest.raises(TypeError):
+        P.cross_features_cdist(torch.randn(2, 4, 3, 3), torch.randn(2, 4, 3, 3), 1)
+    if not torch.cuda.is_available():
+        from oracle import tinynet
+
+        m1, m2 = tinynet.make_pair()
+        spec = P.get_permutation_spec(m1, ((1, 3, 16, 16),))
+        with pytest.raises(RuntimeError):
+            P.activation_matching(spec, m1, m2, tinynet.make_loader(1, 2), 1)
+
+
+def _spec_json(spec):
+    return [{"key": [k.key, k.axis], "size": pg.size, "state": sorted([a.key, a.axis] for a in pg.state),
+             "node": sorted([a.key, a.axis] for a in pg.node)} for k, pg in spec.items()]
+
+
+@pytest.mark.parametrize("name", ["tiny", "resnet18", "resnet50", "resnet50_nofc", "resnet101"])
+def test_permutation_spec_equals_reference(name):
+    import torchvision
+
+    import pleas_merging_b200 as P
+    from oracle import tinynet
+
+    torch.manual_seed(0)
+    if name == "tiny":
+        model, shape = tinynet.TinyResNet(12, 10).eval(), (1, 3, 16, 16)
+    else:
+        model = getattr(torchvision.models, name.replace("_nofc", ""))().eval()
+        if name.endswith("_nofc"):
+            model.fc = torch.nn.Identity()
+        shape = (1, 3, 64, 64)
+    spec = P.get_permutation_spec(model, (shape,))
+    with open(os.path.join(GOLDEN, f"spec_{name}.json")) as f:
+        assert _spec_json(spec) == json.load(f)  # keys, order, sizes, state and node sets
+
+
+def test_spec_invariance_selfcheck():
+    import pleas_merging_b200 as P
+    from oracle import tinynet
+
+    m, _ = tinynet.make_pair()
+    spec = P.get_permutation_spec(m, ((1, 3, 16, 16),))
+    assert P.check_permutation_spec(m, spec, torch.randn(2, 3, 16, 16)) == set()
+
+
+def test_compiler_rejects_unknown_ops():
+    import pleas_merging_b200 as P
+
+    class Odd(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.l = torch.nn.Linear(4, 4)
+
+        def forward(self, x):
+            return torch.fft.fft(self.l(x)).real
+
+    with pytest.raises(NotImplementedError):
+        P.get_permutation_spec(Odd(), ((2, 4),))
+
+
+def test_axis_interoperates_with_reference_dataclass():
+    """Dicts keyed by the reference's frozen-dataclass Axis can be indexed with ours and vice versa."""
+    from dataclasses import dataclass
+
+    import pleas_merging_b200 as P
+
+    @dataclass(frozen=True)
+    class RefAxis:  # same definition as pleas/core/utils.py:16-31
+        key: str
+        axis: int
+
+    ours, theirs = P.Axis("layer1.0.conv1.weight", 0), RefAxis("layer1.0.conv1.weight", 0)
+    assert hash(ours) == hash(theirs) and ours == theirs and theirs == ours
+    assert {theirs: 1}[ours] == 1 and {ours: 2}[theirs] == 2
+    assert ours != P.Axis("layer1.0.conv1.weight", 1) and str(ours) == "layer1.0.conv1.weight:0"
+    assert P.Axis(*ours) == ours
+
+
+def test_perm_helpers_and_apply_perm_cpu():
+    import pleas_merging_b200 as P
+    from oracle import ref_oracle as O
+    from oracle import tinynet
+
+    m, _ = tinynet.make_pair()
+    spec = P.get_permutation_spec(m, ((1, 3, 16, 16),))
+    perm = P.make_random_perm(spec, generator=torch.Generator().manual_seed(0))
+    inv = P.invert_perm(perm)
+    assert all(torch.equal(perm[k][inv[k]], torch.arange(len(perm[k]))) for k in perm)
+    assert P.perm_eq(perm, {k: v.clone() for k, v in perm.items()}) and not P.perm_eq(perm, inv)
+    sd = P.apply_perm(perm, spec, m.state_dict())
+    jspec = load_spec_json("tiny")
+    ref = {k: v.numpy().copy() for k, v in m.state_dict().items() if v.dim() > 0}
+    for g in jspec:
+        O.apply_perm_group(g, perm[P.Axis(*g["key"])].numpy(), ref)
+    for k, v in ref.items():
+        assert (sd[k].numpy() == v).all(), k
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from pleas_merging_b200 import parallel
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=2)
+rank, world = parallel.world()
+loader = [(torch.full((2, 2), float(i)), 0) for i in range(7)]
+for mode in ("sum", "reference"):
+    sh = parallel.BatchSharder(loader, 5)            # 5 of the 7 batches, dealt round-robin
+    flat = torch.zeros(4)
+    seen = []
+    for idx, (x, _) in sh:
+        seen.append(idx)
+        if mode == "reference":
+            flat.zero_()
+        flat += x.flatten()
+    assert seen == list(range(rank, 5, 2)), seen
+    assert sh.total == 5 and sh.owns_last() == (rank == 0)   # batch 4 belongs to rank 0
+    parallel.combine_costs_(flat, sh, mode)
+    want = float(sum(range(5))) if mode == "sum" else 4.0
+    assert torch.equal(flat, torch.full((4,), want)), (mode, flat)
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_sharding_and_allreduce_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"ok {r}" in o, o
