@@ -94,8 +94,10 @@ typedef struct PlbGemmProblem {
 } PlbGemmProblem;
 
 /* bn in {64,128,256}.  total_ctas = sum over problems of m_tiles*n_tiles*splits.
- * impl: 0 = tcgen05 3xTF32 (product path), 1 = SIMT fp32 FMA reference kernel on the same
- * planes (debug / cross-check only). */
+ * impl: 16*chain_kb = persistent tcgen05 3xTF32 kernel with in-kernel promotion every chain_kb
+ * k-blocks (product path; total_ctas is then the number of work items, the grid is capped at
+ * the SM count); 0 = one-CTA-per-work-item tcgen05 kernel (no promotion: the caller bounds the
+ * chain with `splits`); 1 = SIMT fp32 FMA reference kernel on the same planes (cross-check only). */
 int plb_gemm_grouped(const PlbGemmProblem *problems_dev, int32_t n_problems, int32_t total_ctas,
                      int32_t bn, int32_t impl, void *stream);
 

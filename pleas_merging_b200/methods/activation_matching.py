@@ -197,7 +197,7 @@ class CrossAccumulator:
         rga, rgb = 16 * ((t.ra + 127) // 128), 16 * ((t.rb + 127) // 128)
         bn = ops.choose_bn(t.rb)
         m_tiles, n_tiles = (t.ra + 127) // 128, (t.rb + bn - 1) // bn
-        splits = ops.choose_splits(m_tiles * n_tiles, t.kb)
+        splits = ops.choose_splits(m_tiles * n_tiles, t.kb, 128, bn)
         self.arena.ensure(max(rga, rgb) * t.kb * 128, splits * m_tiles * 128 * n_tiles * bn)
         b = self.arena.buf
         t.pa = _View(b[0], b[1], t.ra, rga, t.kb)

@@ -195,7 +195,7 @@ class _LayerLS:
         for b_planes, n_cols, out in ((pu, self.K, self.G), (py, self.cout, self.R)):
             bn = ops.choose_bn(n_cols)
             m_tiles, n_tiles = (self.K + 127) // 128, (n_cols + bn - 1) // bn
-            splits = ops.choose_splits(m_tiles * n_tiles, kb)
+            splits = ops.choose_splits(m_tiles * n_tiles, kb, 128, bn)
             partial = ws.get("partial", splits * m_tiles * 128 * n_tiles * bn)
             plan = ops.GemmPlan(pu, b_planes, self.K, n_cols, kb, splits=splits, partial=partial)
             plan.run()

@@ -13,16 +13,23 @@ from . import _native as N
 
 MODE_INNER, MODE_NEG_CDIST = 0, 1
 NUM_SMS = 148
-# PLB_GEMM_IMPL=simt selects the SIMT fp32 cross-check kernel (debugging only; still CUDA)
-_GEMM_IMPL = {"tcgen05": 0, "simt": 1}[os.environ.get("PLB_GEMM_IMPL", "tcgen05")]
-
-
+# GEMM implementations behind plb_gemm_grouped:
+#   "tcgen05"    persistent tcgen05 3xTF32 kernel with in-kernel promotion (product path)
+#   "tcgen05_v1" one CTA per K chain, chains summed by the finalize kernel
+#   "simt"       SIMT fp32 FMA cross-check kernel on the same planes (debugging only; still CUDA)
+_GEMM_IMPL = os.environ.get("PLB_GEMM_IMPL", "tcgen05")
+assert _GEMM_IMPL in ("tcgen05", "tcgen05_v1", "simt")
 GEMM_TIMER = None  # set to a list by bench.py to collect (start, end, flops, bn) per GEMM launch
 
 
 def set_gemm_impl(name):
     global _GEMM_IMPL
-    _GEMM_IMPL = {"tcgen05": 0, "simt": 1}[name]
+    assert name in ("tcgen05", "tcgen05_v1", "simt")
+    _GEMM_IMPL = name
+
+
+def _impl_code(name):
+    return {"tcgen05": 16 * MAX_CHAIN_KB, "tcgen05_v1": 0, "simt": 1}[name]
 
 
 def _require_cuda_f32(t, what):
@@ -88,17 +95,36 @@ def choose_bn(n_rows):
 
 
 # The tensor core's fp32 accumulator rounds toward zero: measured bias is -1e-7 (relative) per
-# 16-wide k-block chained into one accumulator (profiles/experiments/exp_chain_length.py), so a
-# chain is capped and the K splits are summed in fp64 by the finalize kernel.
-MAX_CHAIN_KB = int(os.environ.get("PLB_MAX_CHAIN_KB", "16"))
+# 16-wide k-block chained into one accumulator (profiles/experiments/exp_chain_length.py).  A
+# chain is therefore capped at MAX_CHAIN_KB k-blocks; the persistent kernel promotes every chain
+# into fp32 registers (fully overlapped with the MMAs: chains of 4, 8 or 16 blocks cost the same,
+# profiles/r01_notes.md), the v1 kernel cuts K into one CTA per chain and finalize sums in fp64.
+MAX_CHAIN_KB = int(os.environ.get("PLB_MAX_CHAIN_KB", "4"))
 
 
-def choose_splits(tiles, k_blocks, target_ctas=NUM_SMS * 4, min_kb=4):
-    """K splits: enough to bound the accumulation chain, and enough that one problem alone
-    fills the GPU (small-C taps have a single output tile and K up to 401 408)."""
-    fill = min(target_ctas // max(tiles, 1), k_blocks // min_kb)
-    chain = -(-k_blocks // MAX_CHAIN_KB)
-    return max(1, min(max(fill, chain), k_blocks))
+def choose_splits(tiles, k_blocks, m_rows=128, n_rows=256, impl=None):
+    """Number of K splits of one problem.
+
+    Persistent kernel: splits only exist to fill the SMs (small-C taps have a single output tile
+    and K up to 401 408); every split costs a partial tile written and re-read, so the count
+    minimises a two-term time model (tensor time / wave efficiency + partial traffic).
+    v1 kernel: additionally one split per accumulation chain."""
+    impl = _GEMM_IMPL if impl is None else impl
+    if impl != "tcgen05":
+        fill = min(NUM_SMS * 4 // max(tiles, 1), k_blocks // 4)
+        chain = -(-k_blocks // 16)
+        return max(1, min(max(fill, chain), k_blocks))
+    max_s = max(1, min(k_blocks // 16, 2 * NUM_SMS))
+    flops = 2.0 * m_rows * n_rows * k_blocks * 16 * tiles
+    tile_bytes = 4.0 * m_rows * n_rows * tiles
+    best, best_t = 1, None
+    for sp in range(1, max_s + 1):
+        items = tiles * sp
+        eff = items / (-(-items // NUM_SMS) * NUM_SMS)
+        t = flops / (eff * 120e12) + 2.0 * sp * tile_bytes / 5e12 + 2e-6
+        if best_t is None or t < best_t * 0.98:
+            best, best_t = sp, t
+    return best
 
 
 class GemmPlan:
@@ -110,7 +136,7 @@ class GemmPlan:
         self.m_tiles = (M + 127) // 128
         self.n_tiles = (Nn + self.bn - 1) // self.bn
         tiles = self.m_tiles * self.n_tiles
-        self.splits = choose_splits(tiles, k_blocks) if splits is None else splits
+        self.splits = choose_splits(tiles, k_blocks, 128, self.bn) if splits is None else splits
         self.ld_m, self.ld_n = self.m_tiles * 128, self.n_tiles * self.bn
         dev = a.hi.device
         need = self.splits * self.ld_m * self.ld_n
@@ -140,7 +166,7 @@ class GemmPlan:
 
     def _launch(self, impl=None):
         N.check(N.lib().plb_gemm_grouped(self.table.data_ptr(), 1, self.total_ctas, self.bn,
-                                         _GEMM_IMPL if impl is None else impl, N.stream_ptr()),
+                                         _impl_code(_GEMM_IMPL if impl is None else impl), N.stream_ptr()),
                 "plb_gemm_grouped")
 
     def finalize(self, out, mode=MODE_INNER, qa=None, qb=None, accumulate=False):
