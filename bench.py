@@ -280,16 +280,17 @@ def run_b200(args):
     with torch.inference_mode():
         host = [(b.cpu().pin_memory(), 0) for b in dev_batches]
     Ke = K
-    loader = [host[i % n_dev] for i in range(Ke)]
-    P.activation_matching(spec, m1, m2, loader[:2], 2, accumulate="sum")  # warm the public path
+    loader = [host[i % n_dev] for i in range(Ke * world)]  # weak scaling: K batches per GPU
+    P.activation_matching(spec, m1, m2, loader[:2 * world], 2 * world, accumulate="sum",
+                          distributed=world > 1)  # warm the public path
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    perm, costs = P.activation_matching(spec, m1, m2, loader, Ke, output_costs=True, accumulate="sum",
+    perm, costs = P.activation_matching(spec, m1, m2, loader, Ke * world, output_costs=True, accumulate="sum",
                                         distributed=world > 1)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     d2h = sum(p.numel() * 8 for p in perm.values())
-    out["e2e"] = {"value": Ke * BATCH / dt, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * HW * HW * 4,
+    out["e2e"] = {"value": Ke * world * BATCH / dt, "unit": UNIT, "h2d_bytes_per_step": BATCH * 3 * HW * HW * 4,
                   "d2h_bytes_per_step": d2h / Ke, "wall_s": dt,
                   "note": "activation_matching(spec, m1, m2, pinned host loader, K, accumulate='sum'): H2D of "
                           "every batch, all taps, batched GPU LAP, D2H of the permutations"}

@@ -33,7 +33,7 @@ _SIGNATURES = {
                                        c_ptr, c_ptr, c_i32, c_i32, c_ptr]),
     "plb_gemm_grouped": (ctypes.c_int, [c_ptr, c_i32, c_i32, c_i32, c_i32, c_ptr]),
     "plb_cross_finalize": (ctypes.c_int, [c_ptr, c_i32, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i32, c_ptr,
-                                          c_ptr, c_i64, c_i32, c_ptr]),
+                                          c_ptr, c_i64, c_i32, c_i32, c_ptr]),
     "plb_lap_solve_batched": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr]),
     "plb_get_blocks": (ctypes.c_int, [c_ptr, c_i64, c_ptr, c_i32, c_f32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                       c_ptr]),

@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(256) cross_finalize_kernel(const float *__rest
                                                              int64_t ld_m, int64_t ld_n, int64_t M, int64_t N,
                                                              const double *__restrict__ qa,
                                                              const double *__restrict__ qb, int mode,
-                                                             OutT *__restrict__ cost, int64_t ldc, int accumulate) {
+                                                             OutT *__restrict__ cost, int64_t ldc, int accumulate, int sym_bn) {
   __shared__ double red[8][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int64_t j = (int64_t)blockIdx.x * 32 + tx;
@@ -25,7 +25,9 @@ __global__ void __launch_bounds__(256) cross_finalize_kernel(const float *__rest
   const int64_t split_stride = ld_m * ld_n;
   double gs = 0.0;
   if (j < N) {
-    const float *p = partial + i * ld_n + j;
+    // symmetric problems only computed the tiles touching the lower triangle: mirror the rest
+    const bool mirror = sym_bn > 0 && (128 * (i / 128) + 127 < (int64_t)sym_bn * (j / sym_bn));
+    const float *p = mirror ? partial + j * ld_n + i : partial + i * ld_n + j;
     int s = ty;
     for (; s + 24 < splits; s += 32) {  // 4 independent loads in flight per thread
       const float a = p[(int64_t)s * split_stride], b = p[(int64_t)(s + 8) * split_stride];
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(256) cross_finalize_kernel(const float *__rest
 
 extern "C" int plb_cross_finalize(const float *partial, int32_t splits, int64_t ld_m, int64_t ld_n, int64_t M,
                                   int64_t N, const double *qa, const double *qb, int32_t mode, float *cost,
-                                  double *cost64, int64_t ldc, int32_t accumulate, void *stream) {
+                                  double *cost64, int64_t ldc, int32_t accumulate, int32_t sym_bn, void *stream) {
   using namespace plb;
   PLB_REQUIRE(partial && (cost || cost64), PLB_EINVAL, "plb_cross_finalize: null pointer");
   PLB_REQUIRE(splits > 0 && M > 0 && N > 0 && M <= ld_m && N <= ld_n && ldc >= N, PLB_EINVAL,
@@ -62,13 +64,15 @@ extern "C" int plb_cross_finalize(const float *partial, int32_t splits, int64_t 
   PLB_REQUIRE(mode == PLB_MODE_INNER || (mode == PLB_MODE_NEG_CDIST && qa && qb), PLB_EINVAL,
               "plb_cross_finalize: mode needs row norms");
   PLB_REQUIRE(M <= 65535, PLB_ESIZE, "plb_cross_finalize: M too large");
+  PLB_REQUIRE(sym_bn == 0 || (M == N && (sym_bn == 64 || sym_bn == 128 || sym_bn == 256)), PLB_EINVAL,
+              "plb_cross_finalize: symmetric finalize needs a square problem and the GEMM's tile width");
   dim3 grid((unsigned)ceil_div(N, 32), (unsigned)M), block(32, 8);
   cudaStream_t s = (cudaStream_t)stream;
   if (cost64)
     cross_finalize_kernel<double><<<grid, block, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost64, ldc,
-                                                       accumulate);
+                                                       accumulate, sym_bn);
   else
     cross_finalize_kernel<float><<<grid, block, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost, ldc,
-                                                      accumulate);
+                                                      accumulate, sym_bn);
   return launch_status("cross_finalize_kernel");
 }

@@ -38,6 +38,13 @@ struct WorkItem {
   int m_tile, n_tile, split, kb0, nkb;
 };
 
+// Symmetric problems (A and B are the same operand, e.g. U^T U) only need tiles that touch the
+// lower triangle; finalize.cu mirrors the rest.
+template <int BN>
+__device__ __forceinline__ bool skipped(const WorkItem &w) {
+  return w.p->symmetric && (128 * w.m_tile + 127 < BN * w.n_tile);
+}
+
 __device__ __forceinline__ WorkItem decode_work(const PlbGemmProblem *probs, int nprob, int cta) {
   int lo = 0, hi = nprob - 1;
   while (lo < hi) {  // last problem whose cta_begin <= cta
@@ -71,6 +78,7 @@ __global__ void __launch_bounds__(192, 2) gemm3xtf32_kernel(const PlbGemmProblem
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const WorkItem w = decode_work(probs, nprob, blockIdx.x);
   const PlbGemmProblem *p = w.p;
+  if (skipped<BN>(w)) return;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -229,6 +237,7 @@ __global__ void __launch_bounds__(320, 1) gemm3xtf32_v2_kernel(const PlbGemmProb
       uint32_t it = 0;  // global stage counter across work items
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const WorkItem w = decode_work(probs, nprob, item);
+        if (skipped<BN>(w)) continue;
         const PlbGemmProblem *p = w.p;
         const int ga = p->a_row_groups, gb = p->b_row_groups;
         const int g0a = w.m_tile * 16, g0b = w.n_tile * (BN / 8);
@@ -253,6 +262,7 @@ __global__ void __launch_bounds__(320, 1) gemm3xtf32_v2_kernel(const PlbGemmProb
     uint32_t it = 0, chain = 0;  // global stage / chain counters
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const WorkItem w = decode_work(probs, nprob, item);
+      if (skipped<BN>(w)) continue;
       for (int i0 = 0; i0 < w.nkb; i0 += chain_kb, ++chain) {
         const uint32_t buf = chain & 1u;
         mbar_wait(&bar_acc_empty[buf], ((chain >> 1) & 1u) ^ 1u);  // epilogue has drained this buffer
@@ -291,6 +301,7 @@ __global__ void __launch_bounds__(320, 1) gemm3xtf32_v2_kernel(const PlbGemmProb
     uint32_t chain = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const WorkItem w = decode_work(probs, nprob, item);
+      if (skipped<BN>(w)) continue;
       const PlbGemmProblem *p = w.p;
       float acc[COLS];
 #pragma unroll
@@ -334,6 +345,7 @@ __global__ void __launch_bounds__(256) gemm_simt_ref_kernel(const PlbGemmProblem
   __shared__ float sb[kPackK][BN + 1];
   const WorkItem w = decode_work(probs, nprob, blockIdx.x);
   const PlbGemmProblem *p = w.p;
+  if (skipped<BN>(w)) return;
   const int tid = threadIdx.x;
   const int row = tid & 127, chalf = tid >> 7;
   float acc[BN / 2];

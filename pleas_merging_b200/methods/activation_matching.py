@@ -26,6 +26,7 @@ from torch.nn import Module
 from .. import ops
 from ..core.solvers import b200_solve_lsa, solve_lsa_batched
 from ..core.utils import Axis, Permutation, PermutationSpec
+from ..graphs import GraphedStep
 from ..parallel import BatchSharder, combine_costs_
 
 
@@ -263,13 +264,8 @@ def compute_matching_costs(spec: PermutationSpec, gm_cross: Module, dataloader, 
 
 
 class CalibrationRunner:
-    """Streams calibration batches through the dual-model graph.
-
-    The per-batch pipeline is ~1 700 kernel launches for a ResNet-50 pair (two forwards + four
-    kernels per tap), which a Python launch loop cannot issue as fast as a B200 executes them.
-    So the first batch of each input shape runs eagerly (it binds the staging memory and warms
-    cuDNN), the second is captured into a CUDA graph, and every later batch is one graph replay
-    fed through a static input buffer."""
+    """Streams calibration batches through the dual-model graph; the per-batch pipeline (two
+    forwards + pack / GEMM / epilogue per tap) is replayed as a CUDA graph (graphs.GraphedStep)."""
 
     def __init__(self, spec, model1, model2, mode, accumulate="reference", use_cuda_graph=True):
         self.device = _model_device(model1)
@@ -277,11 +273,10 @@ class CalibrationRunner:
         axes = [ax for pg in spec.values() for ax in pg.node]
         self.gm = _dual_graph(model1, model2, axes, self.acc.emit)
         self.reset = accumulate == "reference"
-        self.use_cuda_graph = use_cuda_graph
-        self.graphs = {}
+        self.step = GraphedStep(self._eager, self.acc.rebind_stale, use_cuda_graph)
 
     def close(self):
-        self.graphs.clear()
+        self.step.clear()
         self.acc.close()
 
     def _eager(self, x):
@@ -290,35 +285,7 @@ class CalibrationRunner:
 
     def run(self, x):
         """One calibration batch (x on the models' device)."""
-        if not self.use_cuda_graph:
-            return self._eager(x)
-        key = (tuple(x.shape), x.dtype)
-        entry = self.graphs.get(key)
-        if entry is None:
-            self._eager(x)
-            self.acc.rebind_stale()
-            self.graphs[key] = "warm"
-            return
-        if entry == "warm":
-            static_x = x.clone()
-            graph = torch.cuda.CUDAGraph()
-            torch.cuda.synchronize()
-            try:
-                with torch.cuda.graph(graph):
-                    self._eager(static_x)
-            except Exception as e:  # capture is an optimisation: same kernels either way
-                import warnings
-
-                warnings.warn(f"CUDA-graph capture of the calibration step failed ({e}); running eagerly")
-                self.use_cuda_graph = False
-                torch.cuda.synchronize()
-                return self._eager(x)
-            self.graphs[key] = (graph, static_x)
-            graph.replay()
-            return
-        graph, static_x = entry
-        static_x.copy_(x, non_blocking=True)
-        graph.replay()
+        self.step(x)
 
 
 def _fused_costs(spec, model1, model2, dataloader, num_batches, mode, accumulate, distributed=False,

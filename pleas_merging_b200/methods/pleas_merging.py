@@ -24,6 +24,8 @@ import torch
 
 from .. import ops
 from ..core.utils import Axis, get_attr
+from ..graphs import GraphedStep
+from ..parallel import BatchSharder, allreduce_sum_
 from .partial_matching import get_blocks
 
 
@@ -130,40 +132,33 @@ def _channel_map(b, device):
 
 
 class _Workspace:
-    """Growable staging shared by all layers (they run back to back on one stream)."""
+    """Staging shared by all layers (they run back to back on one stream): packed U / Y-bar planes
+    and the K-split partial tiles.  ``version`` changes whenever a buffer is reallocated."""
 
     def __init__(self, device):
-        self.device = device
-        self.cap = {}
-        self.buf = {}
+        self.device, self.cap, self.buf, self.version = device, {}, {}, 0
 
-    def get(self, name, floats):
+    def ensure(self, name, floats):
         if self.cap.get(name, 0) < floats:
-            self.cap[name] = int(floats * 1.2)
+            self.cap[name] = int(floats * 1.1) + 1024
             self.buf[name] = torch.empty(self.cap[name], dtype=torch.float32, device=self.device)
+            self.version += 1
         return self.buf[name]
-
-    def planes(self, name, rows, kb):
-        rg = 16 * ((rows + 127) // 128)
-        n = rg * kb * 128
-        from .activation_matching import _View
-
-        return _View(self.get(name + "_hi", n), self.get(name + "_lo", n), rows, rg, kb)
 
 
 class _LayerLS:
-    """Normal-equation accumulator of one trained layer."""
+    """Normal-equation accumulator of one trained layer: G = U^T U, R = U^T Y-bar in fp64."""
 
-    def __init__(self, name, layer, bi, bo, ip_shape, op_shape, device):
+    def __init__(self, name, layer, bi, bo, ip_shape, device):
         self.name = name
         self.is_conv = isinstance(layer, torch.nn.Conv2d)
         if self.is_conv:
             if layer.groups != 1:
                 raise NotImplementedError(f"{name}: grouped convolutions are not supported by the closed form")
-            self.kernel, self.stride = tuple(layer.kernel_size), tuple(layer.stride)
-            self.padding, self.dilation = tuple(layer.padding), tuple(layer.dilation)
             if isinstance(layer.padding, str):
                 raise NotImplementedError(f"{name}: string padding is not supported")
+            self.kernel, self.stride = tuple(layer.kernel_size), tuple(layer.stride)
+            self.padding, self.dilation = tuple(layer.padding), tuple(layer.dilation)
         else:
             if len(ip_shape) != 2:
                 raise NotImplementedError(f"{name}: Linear inputs must be [batch, features]")
@@ -174,9 +169,42 @@ class _LayerLS:
         self.omap, self.cout = _channel_map(bo, device)
         self.K = self.cin * self.kernel[0] * self.kernel[1] + int(self.has_bias)
         self.bi, self.bo = bi, bo
-        self.G = torch.zeros(self.K, self.K, dtype=torch.float64, device=device)
-        self.R = torch.zeros(self.K, self.cout, dtype=torch.float64, device=device)
+        self.G = self.R = None  # views into the runner's flat fp64 accumulator
         self.count = 0
+        self.bound = {}  # (L, workspace version) -> (pu, py, plan_g, plan_r)
+
+    def _geometry(self, n_cols, symmetric, kb):
+        """(bn, m_tiles, n_tiles, splits) of the GEMM U^T [U | Y] for a batch with kb k-blocks."""
+        bn = ops.choose_bn(n_cols)
+        m_tiles, n_tiles = (self.K + 127) // 128, (n_cols + bn - 1) // bn
+        active = m_tiles * n_tiles if not symmetric else sum(
+            1 for mt in range(m_tiles) for nt in range(n_tiles) if 128 * mt + 127 >= bn * nt)
+        return bn, m_tiles, n_tiles, ops.choose_splits(active, kb, 128, bn)
+
+    def requirements(self, L):
+        """(U-plane floats, Y-plane floats, partial floats) for a batch with L output positions."""
+        kb = (L + 15) // 16
+        rgu, rgy = 16 * ((self.K + 127) // 128), 16 * ((self.cout + 127) // 128)
+        need = 0
+        for n_cols, sym in ((self.K, True), (self.cout, False)):
+            bn, m_tiles, n_tiles, splits = self._geometry(n_cols, sym, kb)
+            need = max(need, splits * m_tiles * 128 * n_tiles * bn)
+        return rgu * kb * 128, rgy * kb * 128, need
+
+    def bind(self, L, ws):
+        from .activation_matching import _View
+
+        kb = (L + 15) // 16
+        rgu, rgy = 16 * ((self.K + 127) // 128), 16 * ((self.cout + 127) // 128)
+        pu = _View(ws.buf["u_hi"], ws.buf["u_lo"], self.K, rgu, kb)
+        py = _View(ws.buf["y_hi"], ws.buf["y_lo"], self.cout, rgy, kb)
+        plan_g = ops.GemmPlan(pu, pu, self.K, self.K, kb, symmetric=True, partial=ws.buf["partial"],
+                              splits=self._geometry(self.K, True, kb)[3])
+        plan_r = ops.GemmPlan(pu, py, self.K, self.cout, kb, partial=ws.buf["partial"],
+                              splits=self._geometry(self.cout, False, kb)[3])
+        plan_g.alg_flops = 2.0 * self.K * self.K * L
+        plan_r.alg_flops = 2.0 * self.K * self.cout * L
+        self.bound[L, ws.version] = (pu, py, plan_g, plan_r)
 
     def accumulate(self, acts1, acts2, ws):
         (ip1, op1), (ip2, op2) = acts1, acts2
@@ -185,22 +213,20 @@ class _LayerLS:
             op1, op2 = op1[:, :, None, None], op2[:, :, None, None]
         B, _, Ho, Wo = op1.shape
         L = B * Ho * Wo
-        kb = (L + 15) // 16
-        pu = ws.planes("u", self.K, kb)
-        py = ws.planes("y", self.cout, kb)
+        pu, py, plan_g, plan_r = self.bound[L, ws.version]
         ops.pack_im2col(ip1.float(), ip2.float(), *self.imap, self.cin, self.kernel, self.stride, self.padding,
                         self.dilation, (Ho, Wo), self.has_bias, pu)
         ops.pack_im2col(op1.float(), op2.float(), *self.omap, self.cout, (1, 1), (1, 1), (0, 0), (1, 1), (Ho, Wo),
                         False, py)
-        for b_planes, n_cols, out in ((pu, self.K, self.G), (py, self.cout, self.R)):
-            bn = ops.choose_bn(n_cols)
-            m_tiles, n_tiles = (self.K + 127) // 128, (n_cols + bn - 1) // bn
-            splits = ops.choose_splits(m_tiles * n_tiles, kb, 128, bn)
-            partial = ws.get("partial", splits * m_tiles * 128 * n_tiles * bn)
-            plan = ops.GemmPlan(pu, b_planes, self.K, n_cols, kb, splits=splits, partial=partial)
-            plan.run()
-            plan.finalize(out, ops.MODE_INNER, accumulate=True)
+        plan_g.run()
+        plan_g.finalize(self.G, ops.MODE_INNER, accumulate=True)
+        plan_r.run()
+        plan_r.finalize(self.R, ops.MODE_INNER, accumulate=True)
         self.count += L
+
+    def out_positions(self, acts1):
+        op = acts1[1]
+        return op.shape[0] * (op.shape[2] * op.shape[3] if op.dim() == 4 else 1)
 
     def mask2d(self, wshape):
         """Gradient mask over the flattened [Co, K] weight (+ bias column)."""
@@ -215,7 +241,7 @@ class _LayerLS:
         return mask > 0
 
     def solve(self, layer, ridge_rel):
-        """Returns the fitted flattened weight [Co, K] (fp64, CUDA) and per-layer losses."""
+        """Returns the fitted flattened weight [Co, K] (fp64, CUDA) and the init it started from."""
         dev = self.G.device
         W0 = layer.weight.detach().to(dev, torch.float64).reshape(self.cout, -1)
         if self.has_bias:
@@ -249,7 +275,7 @@ class _LayerLS:
                 raise RuntimeError(f"{self.name}: normal equations not positive definite at pivot {info - 1} "
                                    f"even with ridge {r:.3e}")
             self.ridge_used = max(getattr(self, "ridge_used", 0.0), r)
-            if bool(free.all()):
+            if idx is None:
                 W[rows] = W0[rows] + rhs.T
             else:
                 upd = torch.zeros(len(rows), self.K, dtype=torch.float64, device=dev)
@@ -258,48 +284,114 @@ class _LayerLS:
         return W, W0
 
 
+class LstsqRunner:
+    """Streams calibration batches through both source models (forward hooks capture every
+    trained layer's input and output) and accumulates all layers' normal equations; the
+    per-batch pipeline is replayed as a CUDA graph."""
+
+    def __init__(self, model1, model2, model3, perm_blocks, num_classes, separate_classifier, model_type,
+                 use_cuda_graph=True):
+        self.device = next(iter(model1.parameters())).device
+        if self.device.type != "cuda":
+            raise RuntimeError("pleas_merging_b200 runs on a CUDA device: move the models to cuda first")
+        self.model1, self.model2 = model1, model2
+        self.perm_blocks, self.num_classes = perm_blocks, num_classes
+        self.separate_classifier, self.model_type = separate_classifier, model_type
+        self.acts1, self.acts2 = {}, {}
+        self.hooks = capture_inputs(model1, self.acts1) + capture_inputs(model2, self.acts2)
+        self.layers3 = {n: m for n, m in model3.named_modules() if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear))}
+        self.accs, self.flat, self.ws = None, None, _Workspace(self.device)
+        self.step = GraphedStep(self._eager, self._rebind, use_cuda_graph)
+        self._last_L = {}
+
+    def close(self):
+        self.step.clear()
+        for h in self.hooks:
+            h.remove()
+        self.acts1.clear()
+        self.acts2.clear()
+
+    def _create(self):
+        self.accs = {}
+        for name, layer in self.layers3.items():
+            if name not in self.acts1 or name not in self.acts2:
+                print(f"Key error on {name}")  # same message as the reference (pleas_merging.py:274)
+                continue
+            bi, bo = _layer_blocks(self.perm_blocks, name, self.acts1[name][0].shape[1], self.num_classes,
+                                   self.separate_classifier, self.model_type)
+            self.accs[name] = _LayerLS(name, layer, bi, bo, tuple(self.acts1[name][0].shape), self.device)
+        # one flat fp64 accumulator for every layer's [G | R]: a single all-reduce in multi-GPU runs
+        total = sum(a.K * (a.K + a.cout) for a in self.accs.values())
+        self.flat = torch.zeros(total, dtype=torch.float64, device=self.device)
+        off = 0
+        for a in self.accs.values():
+            a.G = self.flat[off:off + a.K * a.K].view(a.K, a.K)
+            off += a.K * a.K
+            a.R = self.flat[off:off + a.K * a.cout].view(a.K, a.cout)
+            off += a.K * a.cout
+
+    def _bind_all(self):
+        """Sizes the shared workspace for this batch shape and binds every layer's plans to it."""
+        Ls = {n: a.out_positions(self.acts1[n]) for n, a in self.accs.items()}
+        req = [a.requirements(Ls[n]) for n, a in self.accs.items()]
+        for nm, floats in (("u_hi", max(r[0] for r in req)), ("u_lo", max(r[0] for r in req)),
+                           ("y_hi", max(r[1] for r in req)), ("y_lo", max(r[1] for r in req)),
+                           ("partial", max(r[2] for r in req))):
+            self.ws.ensure(nm, floats)
+        for n, a in self.accs.items():
+            if (Ls[n], self.ws.version) not in a.bound:
+                a.bind(Ls[n], self.ws)
+        self._last_L = Ls
+
+    def _rebind(self):
+        pass  # _bind_all already bound everything against the final workspace of this shape
+
+    def _eager(self, x):
+        self.acts1.clear()
+        self.acts2.clear()
+        self.model1(x)
+        self.model2(x)
+        if self.accs is None:
+            self._create()
+        Ls = {n: a.out_positions(self.acts1[n]) for n, a in self.accs.items()}
+        if Ls != self._last_L or any((Ls[n], self.ws.version) not in a.bound for n, a in self.accs.items()):
+            self._bind_all()
+        for n, a in self.accs.items():
+            a.accumulate(self.acts1[n], self.acts2[n], self.ws)
+
+    def run(self, x):
+        self.step(x)
+
+
 def layer_objective(W, G, R, yy_plus=0.0):
     """sum_o (w_o G w_o - 2 w_o r_o): the layer's squared error up to the constant ||Y||^2."""
     return float(((W @ G) * W).sum() - 2 * (W * R.T).sum()) + yy_plus
 
 
 def _train_lstsq(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, separate_classifier, num_classes,
-                 model_type, ridge, verbose, stats):
-    device = next(iter(model1.parameters())).device
-    acts1, acts2 = {}, {}
-    hooks = capture_inputs(model1, acts1) + capture_inputs(model2, acts2)
+                 model_type, ridge, verbose, stats, distributed=False, use_cuda_graph=True):
     model1.eval()
     model2.eval()
-    layers3 = {n: m for n, m in model3.named_modules() if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear))}
-    accs, ws = {}, _Workspace(device)
+    runner = LstsqRunner(model1, model2, model3, perm_blocks, num_classes, separate_classifier, model_type,
+                         use_cuda_graph)
     try:
+        # the reference's loop breaks when idx > MAX_STEPS, i.e. it consumes MAX_STEPS + 1 batches
+        sharder = BatchSharder(((b[0], 0) for b in dataloader), MAX_STEPS + 1, *(() if distributed else (0, 1)))
         with torch.no_grad():
-            for idx, batch in enumerate(dataloader):
-                if idx > MAX_STEPS:
-                    break
-                x = batch[0].to(device, non_blocking=True)
-                acts1.clear()
-                acts2.clear()
-                model1(x)
-                model2(x)
-                for name, layer in layers3.items():
-                    if name not in acts1 or name not in acts2:
-                        print(f"Key error on {name}")
-                        continue
-                    if name not in accs:
-                        bi, bo = _layer_blocks(perm_blocks, name, acts1[name][0].shape[1], num_classes,
-                                               separate_classifier, model_type)
-                        accs[name] = _LayerLS(name, layer, bi, bo, tuple(acts1[name][0].shape),
-                                              tuple(acts1[name][1].shape), device)
-                    accs[name].accumulate(acts1[name], acts2[name], ws)
-            for name, acc in accs.items():
-                layer = layers3[name]
+            for _, (x, _) in sharder:
+                runner.run(x.to(runner.device, non_blocking=True))
+            if runner.accs is None:
+                return model3
+            allreduce_sum_(runner.flat) if distributed else None
+            for name, acc in runner.accs.items():
+                layer = runner.layers3[name]
                 W, W0 = acc.solve(layer, ridge)
                 if stats is not None:
                     stats[name] = {"objective_init": layer_objective(W0, acc.G, acc.R),
                                    "objective_fit": layer_objective(W, acc.G, acc.R),
-                                   "rows": acc.count, "cout": acc.cout,
-                                   "ridge_rel": getattr(acc, "ridge_used", 0.0) / max(float(acc.G.diagonal().mean()), 1e-300)}
+                                   "rows": acc.count, "cout": acc.cout, "K": acc.K,
+                                   "ridge_rel": getattr(acc, "ridge_used", 0.0)
+                                   / max(float(acc.G.diagonal().mean()), 1e-300)}
                 if verbose:
                     print(f"{name}: K={acc.K} Co={acc.cout} rows={acc.count}")
                 kw = acc.K - int(acc.has_bias)
@@ -307,8 +399,7 @@ def _train_lstsq(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, sep
                 if acc.has_bias:
                     layer.bias.data.copy_(W[:, kw].to(layer.bias.dtype))
     finally:
-        for h in hooks:
-            h.remove()
+        runner.close()
     return model3
 
 
@@ -376,13 +467,15 @@ def _train_adam(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, sepa
 
 def train(dataloader, model1, model2, model3, spec, perm, costs, budget_ratios, WANDB, MAX_STEPS, wandb_run,
           separate_classifier=False, merging="perm_gradmask", num_classes=1000, lr=5e-4, verbose=False,
-          model_type="rn50", *, solver="lstsq", ridge=1e-6, stats=None):
+          model_type="rn50", *, solver="lstsq", ridge=1e-6, stats=None, distributed=False, use_cuda_graph=True):
     """Fit the merged model's layers to the source models' activations (reference :305-405).
 
     Same positional signature as the reference.  ``solver="lstsq"`` (default) is the closed
     form over the first ``MAX_STEPS + 1`` batches (the reference's loop consumes that many);
     ``solver="adam"`` replays the reference optimiser.  ``ridge`` is relative to the mean
-    diagonal of each layer's Gram matrix and is escalated tenfold when a pivot fails.  ``stats`` (dict) receives per-layer objectives."""
+    diagonal of each layer's Gram matrix and is escalated tenfold when a pivot fails.  ``stats`` (dict) receives per-layer objectives.
+    ``distributed=True`` (initialised torch.distributed job, same loader on every rank) deals the
+    batches round-robin and sums the normal equations with one all-reduce; every rank solves."""
     blocks = get_blocks(spec, perm, costs, budget_ratios, False)
     perm_blocks = copy(blocks)
     for axis, pg in spec.items():
@@ -397,4 +490,4 @@ def train(dataloader, model1, model2, model3, spec, perm, costs, budget_ratios, 
         raise NotImplementedError("the closed form implements the default 'perm_gradmask' targets; "
                                   "use solver='adam' for the alternative targets")
     return _train_lstsq(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, separate_classifier, num_classes,
-                        model_type, ridge, verbose, stats)
+                        model_type, ridge, verbose, stats, distributed, use_cuda_graph)

@@ -136,7 +136,10 @@ class GemmPlan:
         self.m_tiles = (M + 127) // 128
         self.n_tiles = (Nn + self.bn - 1) // self.bn
         tiles = self.m_tiles * self.n_tiles
-        self.splits = choose_splits(tiles, k_blocks, 128, self.bn) if splits is None else splits
+        self.symmetric = bool(symmetric)
+        active = tiles if not symmetric else sum(
+            1 for mt in range(self.m_tiles) for nt in range(self.n_tiles) if 128 * mt + 127 >= self.bn * nt)
+        self.splits = choose_splits(active, k_blocks, 128, self.bn) if splits is None else splits
         self.ld_m, self.ld_n = self.m_tiles * 128, self.n_tiles * self.bn
         dev = a.hi.device
         need = self.splits * self.ld_m * self.ld_n
@@ -177,7 +180,8 @@ class GemmPlan:
             c32, c64 = out.data_ptr(), None
         N.check(N.lib().plb_cross_finalize(self.partial.data_ptr(), self.splits, self.ld_m, self.ld_n, self.M,
                                            self.N, N.ptr(qa), N.ptr(qb), mode, c32, c64, out.stride(0),
-                                           int(accumulate), N.stream_ptr()), "plb_cross_finalize")
+                                           int(accumulate), self.bn if self.symmetric else 0, N.stream_ptr()),
+                "plb_cross_finalize")
 
 
 def cross_statistic(x, y, axis, mode):

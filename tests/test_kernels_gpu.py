@@ -280,3 +280,57 @@ def test_chol_reports_non_spd():
     G[17, 17] = -1.0
     info = ops.chol_solve_(G.cuda(), torch.ones(40, 2, dtype=torch.float64).cuda(), 0.0)
     assert info.item() == 18
+
+
+@pytest.mark.parametrize("impl", ["simt", "tcgen05_v1", "tcgen05"])
+@pytest.mark.parametrize("rows,K", [(40, 100), (300, 500), (700, 2000)])
+def test_symmetric_gram_lower_tiles_mirrored(rows, K, impl):
+    """U U^T with symmetric=True computes only the tiles touching the lower triangle; the
+    finalize kernel mirrors the rest — result equals the full product (fp64 accumulator)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(rows)
+    u = torch.randn(rows, K, generator=g)
+    kb = (K + 15) // 16
+    pu = ops.Planes(rows, kb, "cuda")
+    ops.pack_split(u.cuda(), 0, pu)
+    plan = ops.GemmPlan(pu, pu, rows, rows, kb, symmetric=True)
+    plan.run(impl)
+    out = torch.full((rows, rows), 1.0, dtype=torch.float64, device="cuda")
+    plan.finalize(out, accumulate=True)
+    ref = 1.0 + u.double().numpy() @ u.double().numpy().T
+    got = out.cpu().numpy()
+    assert np.abs(got - ref).max() <= 2.5e-6 * np.abs(ref).max()
+    # mirrored tiles are exact copies; inside diagonal tiles (i,j)/(j,i) differ by MMA summation order only
+    assert np.abs(got - got.T).max() <= 1e-6 * np.abs(ref).max()
+
+
+def test_pack_im2col_vs_unfold():
+    import torch.nn.functional as F
+
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    x1, x2 = torch.randn(3, 10, 9, 8, generator=g), torch.randn(3, 10, 9, 8, generator=g)
+    b1, b2 = torch.randperm(10, generator=g)[:6], torch.randperm(10, generator=g)[:6]
+    b1c = torch.tensor([i for i in range(10) if i not in b1.tolist()])
+    b2c = torch.tensor([i for i in range(10) if i not in b2.tolist()])
+    xbar = torch.cat([(x1[:, b1] + x2[:, b2]) / 2, x1[:, b1c], x2[:, b2c]], 1)  # pleas_merging.py:146
+    for kernel, stride, pad, dil, bias in (((3, 3), (1, 1), (1, 1), (1, 1), False), ((1, 1), (2, 2), (0, 0), (1, 1), True),
+                                           ((3, 2), (2, 1), (0, 1), (1, 2), True)):
+        U = F.unfold(xbar, kernel, dil, pad, stride)  # [B, K, L']
+        Ho = (9 + 2 * pad[0] - dil[0] * (kernel[0] - 1) - 1) // stride[0] + 1
+        Wo = (8 + 2 * pad[1] - dil[1] * (kernel[1] - 1) - 1) // stride[1] + 1
+        ref = U.permute(1, 0, 2).reshape(U.shape[1], -1)  # rows (c,dy,dx), k = (n, ho, wo)
+        if bias:
+            ref = torch.cat([ref, torch.ones(1, ref.shape[1])], 0)
+        neg = lambda n: torch.full((n,), -1, dtype=torch.int64)
+        c1 = torch.cat([b1, b1c, neg(4)]).int().cuda()
+        c2 = torch.cat([b2, neg(4), b2c]).int().cuda()
+        s1 = torch.cat([torch.full((6,), 0.5), torch.ones(4), torch.zeros(4)]).cuda()
+        s2 = torch.cat([torch.full((6,), 0.5), torch.zeros(4), torch.ones(4)]).cuda()
+        rows, Kc = ref.shape
+        planes = ops.Planes(rows, (Kc + 15) // 16, "cuda")
+        ops.pack_im2col(x1.cuda(), x2.cuda(), c1, c2, s1, s2, 14, kernel, stride, pad, dil, (Ho, Wo), bias, planes)
+        hi = unpack_planes(planes.hi, rows, Kc, planes.row_groups)
+        lo = unpack_planes(planes.lo, rows, Kc, planes.row_groups)
+        got = hi.astype(np.float64) + lo
+        assert np.abs(got - ref.numpy()).max() <= 2.0 ** -21 * max(np.abs(ref.numpy()).max(), 1.0)
