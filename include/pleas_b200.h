@@ -106,7 +106,8 @@ int plb_gemm_grouped(const PlbGemmProblem *problems_dev, int32_t n_problems, int
  * (activation_matching.py:28, 46; per-group accumulation :129-134).  accumulate = 0
  * overwrites.  cost64 != NULL selects an fp64 accumulator (normal equations).  sym_bn != 0:
  * the GEMM ran a symmetric problem with tile width sym_bn and only produced the tiles touching
- * the lower triangle; the upper part is read mirrored. */
+ * the lower triangle; only those tiles of `cost` are written (they cover the lower triangle
+ * including the diagonal) — the caller mirrors the accumulator when it needs the full matrix. */
 int plb_cross_finalize(const float *partial, int32_t splits, int64_t ld_m, int64_t ld_n,
                        int64_t M, int64_t N, const double *qa, const double *qb, int32_t mode,
                        float *cost, double *cost64, int64_t ldc, int32_t accumulate, int32_t sym_bn,

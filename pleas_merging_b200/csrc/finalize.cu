@@ -10,37 +10,44 @@
 
 namespace plb {
 
-// Block = 32 columns x 8 split lanes: the K-split partials of one output element are summed by
-// 8 threads in parallel (fp64, fixed order => deterministic), then combined through shared memory.
-template <typename OutT>
+// Block = 32*(8/SL) columns x SL split lanes: with many K splits, SL = 8 threads sum one output
+// element's partials in parallel (fp64, fixed order => deterministic) and combine through shared
+// memory; with few splits SL = 1 and the block covers 256 consecutive columns.  Symmetric
+// problems only computed the tiles touching the lower triangle: those are the only ones written
+// (the caller mirrors the accumulator once at the end), so every access stays coalesced.
+template <typename OutT, int SL>
 __global__ void __launch_bounds__(256) cross_finalize_kernel(const float *__restrict__ partial, int splits,
                                                              int64_t ld_m, int64_t ld_n, int64_t M, int64_t N,
                                                              const double *__restrict__ qa,
                                                              const double *__restrict__ qb, int mode,
-                                                             OutT *__restrict__ cost, int64_t ldc, int accumulate, int sym_bn) {
-  __shared__ double red[8][33];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int64_t j = (int64_t)blockIdx.x * 32 + tx;
+                                                             OutT *__restrict__ cost, int64_t ldc, int accumulate,
+                                                             int sym_bn) {
+  constexpr int COLS = 256 / SL;
+  __shared__ double red[SL][COLS + 1];
+  const int tx = threadIdx.x % COLS, ty = threadIdx.x / COLS;
+  const int64_t j = (int64_t)blockIdx.x * COLS + tx;
   const int64_t i = blockIdx.y;
   const int64_t split_stride = ld_m * ld_n;
+  const bool live = j < N && !(sym_bn > 0 && (128 * (i / 128) + 127 < (int64_t)sym_bn * (j / sym_bn)));
   double gs = 0.0;
-  if (j < N) {
-    // symmetric problems only computed the tiles touching the lower triangle: mirror the rest
-    const bool mirror = sym_bn > 0 && (128 * (i / 128) + 127 < (int64_t)sym_bn * (j / sym_bn));
-    const float *p = mirror ? partial + j * ld_n + i : partial + i * ld_n + j;
+  if (live) {
+    const float *p = partial + i * ld_n + j;
     int s = ty;
-    for (; s + 24 < splits; s += 32) {  // 4 independent loads in flight per thread
-      const float a = p[(int64_t)s * split_stride], b = p[(int64_t)(s + 8) * split_stride];
-      const float c = p[(int64_t)(s + 16) * split_stride], d = p[(int64_t)(s + 24) * split_stride];
+    for (; s + 3 * SL < splits; s += 4 * SL) {  // 4 independent loads in flight per thread
+      const float a = p[(int64_t)s * split_stride], b = p[(int64_t)(s + SL) * split_stride];
+      const float c = p[(int64_t)(s + 2 * SL) * split_stride], d = p[(int64_t)(s + 3 * SL) * split_stride];
       gs += ((double)a + (double)b) + ((double)c + (double)d);
     }
-    for (; s < splits; s += 8) gs += (double)p[(int64_t)s * split_stride];
+    for (; s < splits; s += SL) gs += (double)p[(int64_t)s * split_stride];
   }
-  red[ty][tx] = gs;
-  __syncthreads();
-  if (ty != 0 || j >= N) return;
+  if (SL > 1) {
+    red[ty][tx] = gs;
+    __syncthreads();
+    if (ty != 0) return;
 #pragma unroll
-  for (int k = 1; k < 8; ++k) gs += red[k][tx];
+    for (int k = 1; k < SL; ++k) gs += red[k][tx];
+  }
+  if (!live) return;
   const float g = (float)gs;
   float v = g;
   if (mode == PLB_MODE_NEG_CDIST) {
@@ -50,6 +57,21 @@ __global__ void __launch_bounds__(256) cross_finalize_kernel(const float *__rest
   OutT *c = cost + i * ldc + j;
   const OutT add = (sizeof(OutT) == 8 && mode == PLB_MODE_INNER) ? (OutT)gs : (OutT)v;
   *c = accumulate ? (OutT)(*c + add) : add;
+}
+
+template <typename OutT>
+static void launch_finalize(const float *partial, int splits, int64_t ld_m, int64_t ld_n, int64_t M, int64_t N,
+                            const double *qa, const double *qb, int mode, OutT *cost, int64_t ldc, int accumulate,
+                            int sym_bn, cudaStream_t s) {
+  if (splits >= 4) {
+    dim3 grid((unsigned)ceil_div(N, 32), (unsigned)M);
+    cross_finalize_kernel<OutT, 8><<<grid, 256, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost, ldc,
+                                                        accumulate, sym_bn);
+  } else {
+    dim3 grid((unsigned)ceil_div(N, 256), (unsigned)M);
+    cross_finalize_kernel<OutT, 1><<<grid, 256, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost, ldc,
+                                                        accumulate, sym_bn);
+  }
 }
 
 }  // namespace plb
@@ -66,13 +88,10 @@ extern "C" int plb_cross_finalize(const float *partial, int32_t splits, int64_t 
   PLB_REQUIRE(M <= 65535, PLB_ESIZE, "plb_cross_finalize: M too large");
   PLB_REQUIRE(sym_bn == 0 || (M == N && (sym_bn == 64 || sym_bn == 128 || sym_bn == 256)), PLB_EINVAL,
               "plb_cross_finalize: symmetric finalize needs a square problem and the GEMM's tile width");
-  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)M), block(32, 8);
   cudaStream_t s = (cudaStream_t)stream;
   if (cost64)
-    cross_finalize_kernel<double><<<grid, block, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost64, ldc,
-                                                       accumulate, sym_bn);
+    launch_finalize<double>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost64, ldc, accumulate, sym_bn, s);
   else
-    cross_finalize_kernel<float><<<grid, block, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost, ldc,
-                                                      accumulate, sym_bn);
+    launch_finalize<float>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost, ldc, accumulate, sym_bn, s);
   return launch_status("cross_finalize_kernel");
 }

@@ -130,28 +130,42 @@ __global__ void __launch_bounds__(256) pack_im2col_kernel(const float *__restric
   const uint32_t HoWo = (uint32_t)(gm.Ho * gm.Wo);
   const int64_t plane = gm.H * gm.W;
   const int kb_end = min(k_blocks, (int)(blockIdx.x + 1) * kKbPerBlock);
+  const int Wo = (int)gm.Wo, Ho = (int)gm.Ho;
+  const int64_t img = (int64_t)gm.cin_src * plane;
+  const float *b1 = (c1 >= 0) ? x1 + (int64_t)c1 * plane : nullptr;
+  const float *b2 = (c2 >= 0) ? x2 + (int64_t)c2 * plane : nullptr;
+#pragma unroll 2
   for (int kb = blockIdx.x * kKbPerBlock + warp; kb < kb_end; kb += 8) {
     const uint32_t k = (uint32_t)kb * kPackK + jj * 4;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (row < rows) {
+    if (row < rows && k < K) {
+      if (is_ones) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const uint32_t ke = k + e;
-        if (ke >= K) continue;
-        if (is_ones) {
-          v[e] = 1.f;
-          continue;
+        for (int e = 0; e < 4; ++e) v[e] = (k + e < K) ? 1.f : 0.f;
+      } else {
+        // decode (n, ho, wo) once, then step along the output row
+        uint32_t n = k / HoWo;
+        const uint32_t p = k - n * HoWo;
+        int ho = (int)(p / (uint32_t)Wo), wo = (int)(p - (uint32_t)ho * (uint32_t)Wo);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (k + e < K) {
+            const int h = ho * gm.sh - gm.ph + dy * gm.dh, wq = wo * gm.sw - gm.pw + dx * gm.dw;
+            if (h >= 0 && h < gm.H && wq >= 0 && wq < gm.W) {
+              const int64_t off = (int64_t)n * img + (int64_t)h * gm.W + wq;
+              const float a = b1 ? __ldg(b1 + off) : 0.f;
+              const float b = b2 ? __ldg(b2 + off) : 0.f;
+              v[e] = fmaf(w1, a, w2 * b);  // (a + b) / 2 for merged channels: one rounding of the sum
+            }
+          }
+          if (++wo == Wo) {
+            wo = 0;
+            if (++ho == Ho) {
+              ho = 0;
+              ++n;
+            }
+          }
         }
-        const uint32_t n = ke / HoWo, p = ke - n * HoWo;
-        const int ho = (int)(p / (uint32_t)gm.Wo), wo = (int)(p - (uint32_t)ho * (uint32_t)gm.Wo);
-        const int h = ho * gm.sh - gm.ph + dy * gm.dh, wq = wo * gm.sw - gm.pw + dx * gm.dw;
-        if (h < 0 || h >= gm.H || wq < 0 || wq >= gm.W) continue;
-        const int64_t sp = (int64_t)h * gm.W + wq;
-        float a = 0.f, b = 0.f;
-        if (c1 >= 0) a = __ldg(x1 + ((int64_t)n * gm.cin_src + c1) * plane + sp);
-        if (c2 >= 0) b = __ldg(x2 + ((int64_t)n * gm.cin_src + c2) * plane + sp);
-        // (a + b) / 2 for merged channels: exact products, one rounding of the sum
-        v[e] = fmaf(w1, a, w2 * b);
       }
     }
     split_store(v, hi, lo, panel_offset(kb_offset + kb, g, row_groups) + (jj * 8 + r) * 4);

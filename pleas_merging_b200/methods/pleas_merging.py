@@ -243,6 +243,10 @@ class _LayerLS:
     def solve(self, layer, ridge_rel):
         """Returns the fitted flattened weight [Co, K] (fp64, CUDA) and the init it started from."""
         dev = self.G.device
+        # the symmetric GEMM / finalize only maintain the tiles touching the lower triangle
+        low = torch.tril(self.G)
+        self.G.copy_(low + torch.tril(self.G, -1).T)
+        del low
         W0 = layer.weight.detach().to(dev, torch.float64).reshape(self.cout, -1)
         if self.has_bias:
             W0 = torch.cat([W0, layer.bias.detach().to(dev, torch.float64)[:, None]], 1)
