@@ -239,9 +239,11 @@ def run_b200(args):
         # (events cannot bracket nodes of a replay), so the same steps are re-run un-captured with
         # events around every GEMM launch on the launching stream
         ops.GEMM_TIMER = []
+        torch.cuda.nvtx.range_push("plb_eager")
         for i in range(min(K, 5)):
             runner._eager(dev_batches[(W + i) % n_dev])
         torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
         timer, ops.GEMM_TIMER = ops.GEMM_TIMER, None
         launches = launches_per_step * K
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in timer)

@@ -108,7 +108,8 @@ def _tap_dispatch(sink_id: int, tap_id: int, xa, xb):
 
 class _Arena:
     """Staging memory shared by all taps (they run back to back on one stream): packed hi/lo
-    planes of both operands and the K-split partial tiles."""
+    planes of both operands and the K-split partial tiles.  Buffers that are outgrown are kept
+    alive: CUDA graphs captured against them stay valid."""
 
     def __init__(self, device):
         self.device = device
@@ -117,13 +118,16 @@ class _Arena:
         self.version = 0
         self.buf = None
         self.partial = None
+        self._retired = []
 
     def ensure(self, plane_floats, partial_floats):
         if plane_floats > self.plane_floats:
+            self._retired.append(self.buf)
             self.plane_floats = int(plane_floats * 1.25)
             self.buf = torch.empty(4, self.plane_floats, dtype=torch.float32, device=self.device)
             self.version += 1
         if partial_floats > self.partial_floats:
+            self._retired.append(self.partial)
             self.partial_floats = int(partial_floats * 1.25)
             self.partial = torch.empty(self.partial_floats, dtype=torch.float32, device=self.device)
             self.version += 1
@@ -136,8 +140,13 @@ class _View:
         self.hi, self.lo, self.rows, self.row_groups, self.k_blocks = hi, lo, rows, row_groups, k_blocks
 
 
+class _TapState:
+    """Geometry, row-norm buffer and GEMM plan of one tap for one pair of activation shapes."""
+    __slots__ = ("ra", "rb", "kb", "K", "q", "plan", "version", "pa", "pb")
+
+
 class _Tap:
-    __slots__ = ("name", "axis", "group", "shape", "ra", "rb", "kb", "K", "q", "plan", "version", "pa", "pb")
+    __slots__ = ("name", "axis", "group", "states")
 
 
 class CrossAccumulator:
@@ -158,8 +167,8 @@ class CrossAccumulator:
             for ax in spec[k].node:
                 self.group_of[ax.key, ax.axis] = gi
         self.taps = []
-        self.seen = set()
         self.arena = _Arena(device)
+        self._retired = []  # plans replaced by a rebind; captured graphs may still point at them
         self.sink_id = next(_sink_ids)
         _SINKS[self.sink_id] = self
 
@@ -168,14 +177,14 @@ class CrossAccumulator:
 
     def emit(self, g, name, axis, na, nb):
         t = _Tap()
-        t.name, t.axis, t.group, t.shape, t.version = name, axis, self.group_of[name, axis], None, -1
+        t.name, t.axis, t.group, t.states = name, axis, self.group_of[name, axis], {}
         self.taps.append(t)
         return g.call_function(_tap_dispatch, (self.sink_id, len(self.taps) - 1, na, nb))
 
     def begin_batch(self, reset_costs):
         if reset_costs:
             self.flat.zero_()
-        qs = [t.q for t in self.taps if t.shape is not None and t.q is not None]
+        qs = [st.q for t in self.taps for st in t.states.values() if st.q is not None]
         if qs:
             torch._foreach_zero_(qs)
 
@@ -187,46 +196,49 @@ class CrossAccumulator:
         n = self.costs[t.group].shape[0]
         if (ra, rb) != (n, n):
             raise ValueError(f"tap {t.name}:{t.axis} has {ra}x{rb} units but its group has {n}")
-        t.shape, t.ra, t.rb, t.kb = (tuple(xa.shape), tuple(xb.shape)), ra, rb, (oa * ia + 15) // 16
-        t.K = oa * ia
-        t.q = torch.zeros(ra + rb, dtype=torch.float64, device=self.device) \
+        st = _TapState()
+        st.ra, st.rb, st.K, st.kb = ra, rb, oa * ia, (oa * ia + 15) // 16
+        st.q = torch.zeros(ra + rb, dtype=torch.float64, device=self.device) \
             if self.mode == ops.MODE_NEG_CDIST else None
-        t.version = -1
+        st.plan, st.version = None, -1
+        return st
 
-    def _bind(self, t):
+    def _bind(self, st):
         """(Re)creates the tap's GEMM problem entry against the current arena."""
-        rga, rgb = 16 * ((t.ra + 127) // 128), 16 * ((t.rb + 127) // 128)
-        bn = ops.choose_bn(t.rb)
-        m_tiles, n_tiles = (t.ra + 127) // 128, (t.rb + bn - 1) // bn
-        splits = ops.choose_splits(m_tiles * n_tiles, t.kb, 128, bn)
-        self.arena.ensure(max(rga, rgb) * t.kb * 128, splits * m_tiles * 128 * n_tiles * bn)
+        rga, rgb = 16 * ((st.ra + 127) // 128), 16 * ((st.rb + 127) // 128)
+        bn = ops.choose_bn(st.rb)
+        m_tiles, n_tiles = (st.ra + 127) // 128, (st.rb + bn - 1) // bn
+        splits = ops.choose_splits(m_tiles * n_tiles, st.kb, 128, bn)
+        self.arena.ensure(max(rga, rgb) * st.kb * 128, splits * m_tiles * 128 * n_tiles * bn)
         b = self.arena.buf
-        t.pa = _View(b[0], b[1], t.ra, rga, t.kb)
-        t.pb = _View(b[2], b[3], t.rb, rgb, t.kb)
-        t.plan = ops.GemmPlan(t.pa, t.pb, t.ra, t.rb, t.kb, splits=splits, partial=self.arena.partial)
-        t.plan.alg_flops = 2.0 * t.ra * t.rb * t.K
-        t.version = self.arena.version
+        if st.plan is not None:
+            self._retired.append((st.plan, st.pa, st.pb))
+        st.pa = _View(b[0], b[1], st.ra, rga, st.kb)
+        st.pb = _View(b[2], b[3], st.rb, rgb, st.kb)
+        st.plan = ops.GemmPlan(st.pa, st.pb, st.ra, st.rb, st.kb, splits=splits, partial=self.arena.partial)
+        st.plan.alg_flops = 2.0 * st.ra * st.rb * st.K
+        st.version = self.arena.version
 
     def rebind_stale(self):
-        """Binds every tap against the final arena (outside any graph capture)."""
+        """Binds every tap state against the final arena (outside any graph capture)."""
         for t in self.taps:
-            if t.shape is not None and t.version != self.arena.version:
-                self._bind(t)
+            for st in t.states.values():
+                if st.version != self.arena.version:
+                    self._bind(st)
 
     def tap(self, idx, xa, xb):
         t = self.taps[idx]
-        self.seen.add(idx)
-        if t.shape != (tuple(xa.shape), tuple(xb.shape)):
-            self._prepare(t, xa, xb)
-        if t.version != self.arena.version:
-            self._bind(t)
-            if t.version != self.arena.version:  # _bind grew the arena: bind against the new one
-                self._bind(t)
-        qa, qb = (t.q[:t.ra], t.q[t.ra:]) if t.q is not None else (None, None)
-        ops.pack_split(xa, t.axis, t.pa, sumsq=qa)
-        ops.pack_split(xb, t.axis, t.pb, sumsq=qb)
-        t.plan.run()
-        t.plan.finalize(self.costs[t.group], self.mode, qa, qb, accumulate=True)
+        key = (tuple(xa.shape), tuple(xb.shape))
+        st = t.states.get(key)
+        if st is None:
+            st = t.states[key] = self._prepare(t, xa, xb)
+        if st.version != self.arena.version:
+            self._bind(st)
+        qa, qb = (st.q[:st.ra], st.q[st.ra:]) if st.q is not None else (None, None)
+        ops.pack_split(xa, t.axis, st.pa, sumsq=qa)
+        ops.pack_split(xb, t.axis, st.pb, sumsq=qb)
+        st.plan.run()
+        st.plan.finalize(self.costs[t.group], self.mode, qa, qb, accumulate=True)
 
 
 # ------------------------------------------------------------------ public API

@@ -137,9 +137,11 @@ class _Workspace:
 
     def __init__(self, device):
         self.device, self.cap, self.buf, self.version = device, {}, {}, 0
+        self._retired = []  # outgrown buffers stay alive: captured CUDA graphs may point at them
 
     def ensure(self, name, floats):
         if self.cap.get(name, 0) < floats:
+            self._retired.append(self.buf.get(name))
             self.cap[name] = int(floats * 1.1) + 1024
             self.buf[name] = torch.empty(self.cap[name], dtype=torch.float32, device=self.device)
             self.version += 1

@@ -281,3 +281,64 @@ def test_activation_matching_rn50_full_width_vs_oracle():
         assert_perm_or_objective(perm[k].numpy(), operm, oc, str(k))
         flips += int((perm[k].numpy() != operm).sum())
     print("rn50 assignments differing from the oracle:", flips)
+
+
+def _jspec(P, spec):
+    return [{"key": (k.key, k.axis), "size": pg.size, "state": sorted((a.key, a.axis) for a in pg.state),
+             "node": sorted((a.key, a.axis) for a in pg.node)} for k, pg in spec.items()]
+
+
+@pytest.mark.parametrize("accumulate", ["reference", "sum"])
+def test_ragged_batches_and_short_loader(accumulate):
+    """Batches of different sizes (each shape gets its own CUDA graph) and num_batches larger than
+    the loader (the reference's zip stops at the shorter one)."""
+    P = _pkg()
+    m1, m2 = tinynet.make_pair(12, 10)
+    spec = P.get_permutation_spec(m1, ((1, 3, 16, 16),))
+    g = torch.Generator().manual_seed(77)
+    loader = [(torch.randn(b, 3, 16, 16, generator=g), 0) for b in (4, 4, 4, 3, 4, 3, 1)]
+    operm, ocosts = O.activation_matching(_jspec(P, spec), m1, m2, loader, 50, "cdist", accumulate)
+    perm, costs = P.activation_matching(spec, m1.cuda(), m2.cuda(), loader, 50, output_costs=True,
+                                        accumulate=accumulate)
+    for k in spec:
+        assert relerr(costs[k].cpu().numpy(), ocosts[(k.key, k.axis)]) <= 1e-4, k
+        assert_perm_or_objective(perm[k].numpy(), operm[(k.key, k.axis)], ocosts[(k.key, k.axis)], str(k))
+
+
+def test_models_in_train_mode_use_batch_statistics():
+    """The reference's drivers never call .eval() before activation matching: BN then
+    normalises with batch statistics and updates its running stats.  The user's modules are run
+    unchanged, eagerly and under CUDA-graph replay."""
+    P = _pkg()
+    a1, a2 = tinynet.make_pair(12, 10)
+    b1, b2 = copy.deepcopy(a1), copy.deepcopy(a2)
+    for m in (a1, a2, b1, b2):
+        m.train()
+    spec = P.get_permutation_spec(copy.deepcopy(a1).eval(), ((1, 3, 16, 16),))
+    loader = tinynet.make_loader(4, 6, 16, seed=8)
+    operm, ocosts = O.activation_matching(_jspec(P, spec), a1, a2, loader, 4, "cdist", "sum")
+    g1, g2 = b1.cuda(), b2.cuda()
+    perm, costs = P.activation_matching(spec, g1, g2, loader, 4, output_costs=True, accumulate="sum")
+    for k in spec:
+        assert relerr(costs[k].cpu().numpy(), ocosts[(k.key, k.axis)]) <= 1e-4, k
+        assert_perm_or_objective(perm[k].numpy(), operm[(k.key, k.axis)], ocosts[(k.key, k.axis)], str(k))
+    # running statistics advanced exactly like on the CPU (4 batches each)
+    for (n, p), (_, q) in zip(a1.named_buffers(), g1.named_buffers()):
+        assert torch.allclose(p, q.cpu(), rtol=1e-4, atol=1e-5), n
+
+
+def test_train_with_ragged_last_batch_and_graphs_off():
+    """Closed form with a ragged last batch equals the eager (no CUDA graph) run."""
+    P = _pkg()
+    m1, m2, spec = _tiny(P)
+    g = torch.Generator().manual_seed(5)
+    loader = [(torch.randn(b, 3, 16, 16, generator=g), 0) for b in (4, 4, 4, 4, 2)]
+    perm, costs = P.activation_matching(spec, m1, m2, loader, 5, output_costs=True, accumulate="sum")
+    outs = []
+    for graphs in (True, False):
+        m3 = P.partial_merge(spec, m1, m2, perm, costs, 0.3)
+        P.train(loader, m1, m2, m3, spec, perm, costs, 0.3, False, 10, None, num_classes=10, model_type="rn18",
+                use_cuda_graph=graphs)
+        outs.append({k: v.clone() for k, v in m3.state_dict().items()})
+    for k in outs[0]:
+        assert torch.allclose(outs[0][k], outs[1][k], rtol=1e-5, atol=1e-7), k
