@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--pleas-steps", type=int, default=None, help="MAX_STEPS of the PLeaS pass (default 400, "
                     "or 4*steps when steps < 100)")
     ap.add_argument("--no-merge", action="store_true", help="skip the one-off whole-merge timing")
+    ap.add_argument("--tf32-convs", action="store_true", help="let cuDNN use TF32 for the source models' convolutions "
+                    "(PyTorch's default; NOT the headline: activations then differ from the fp32 CPU reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=8, help="samples per CPU-baseline batch")
     return ap.parse_args()
@@ -188,7 +190,7 @@ def run_b200(args):
     AM = importlib.import_module("pleas_merging_b200.methods.activation_matching")
 
     # exact-fp32 library forwards: the permutations must reproduce the reference's
-    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = bool(args.tf32_convs)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = True
 
@@ -259,7 +261,8 @@ def run_b200(args):
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"{args.model} pair (random init, eval), activation_matching accumulation over "
                                   f"{K} batches of {BATCH}x3x{HW}x{HW} per GPU, -cdist statistic on {taps} taps, "
-                                  f"accumulate=sum, 3xTF32 tcgen05 GEMM, exact-fp32 cuDNN forwards",
+                                  f"accumulate=sum, 3xTF32 tcgen05 GEMM, "
+                                  + ("TF32 cuDNN forwards (secondary number)" if args.tf32_convs else "exact-fp32 cuDNN forwards"),
                       "parallelism": f"batch-sharded x{world}, one NCCL all-reduce of the cost matrices",
                       "l2": "inputs larger than L2: every step streams ~10 GB of activations"},
            "gpu_launches": launches}
@@ -268,7 +271,11 @@ def run_b200(args):
     achieved = 3.0 * gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     out["roofline"] = {
         "bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
-        "traffic": None, "kernel": "gemm3xtf32_kernel",
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the ncu --set full capture
+        # profiles/gemm_v2_c2048_r01_raw.csv (C=2048, K=1568 tap: the 13.15-GFLOP shape that makes up
+        # 72 of the 174 launches and 88 % of the GEMM FLOPs of a step); its algorithmic operand bytes are
+        # (2048+2048)*1568*8 = 51.4 MB of packed planes, i.e. no re-reads
+        "traffic": 53.36e6, "traffic_algorithmic_bytes": 51.4e6, "kernel": "gemm3xtf32_v2_kernel",
         "note": f"achieved = 3 x algorithmic FLOPs (3xTF32 issues three tensor-pipe passes; algorithmic = "
                 f"2*C^2*K per tap, {gemm_flops / min(K, 5) / 1e12:.3f} TFLOP per step) / summed CUDA-event time of "
                 f"{len(timer)} GEMM launches ({min(K, 5)} steps re-run un-captured right after the timed "

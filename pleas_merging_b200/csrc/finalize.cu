@@ -10,19 +10,72 @@
 
 namespace plb {
 
-// Block = 32*(8/SL) columns x SL split lanes: with many K splits, SL = 8 threads sum one output
-// element's partials in parallel (fp64, fixed order => deterministic) and combine through shared
-// memory; with few splits SL = 1 and the block covers 256 consecutive columns.  Symmetric
-// problems only computed the tiles touching the lower triangle: those are the only ones written
-// (the caller mirrors the accumulator once at the end), so every access stays coalesced.
-template <typename OutT, int SL>
-__global__ void __launch_bounds__(256) cross_finalize_kernel(const float *__restrict__ partial, int splits,
-                                                             int64_t ld_m, int64_t ld_n, int64_t M, int64_t N,
-                                                             const double *__restrict__ qa,
-                                                             const double *__restrict__ qb, int mode,
-                                                             OutT *__restrict__ cost, int64_t ldc, int accumulate,
-                                                             int sym_bn) {
-  constexpr int COLS = 256 / SL;
+// Two shapes of the same epilogue.
+//  * many K splits (SL = 8): 8 threads sum one output element's partials in parallel (fp64, fixed
+//    order => deterministic) and combine through shared memory; block = 32 columns x 8 lanes.
+//  * few splits (SL = 1): the kernel is a pure stream (read partial + read-modify-write cost), so
+//    each thread owns kRows rows of one column and issues all its loads before using any of them
+//    (one element per thread left the kernel latency-bound at 0.7 TB/s); block = 256 columns.
+// Symmetric problems only computed the tiles touching the lower triangle: those are the only ones
+// written (the caller mirrors the accumulator once at the end), so every access stays coalesced.
+constexpr int kRows = 4;
+
+template <typename OutT>
+__device__ __forceinline__ void epilogue_store(double gs, int64_t i, int64_t j, const double *qa, const double *qb,
+                                               int mode, OutT *cost, int64_t ldc, int accumulate, OutT old) {
+  const float g = (float)gs;
+  float v = g;
+  if (mode == PLB_MODE_NEG_CDIST) {
+    const float d2 = ((float)qa[i] + (float)qb[j]) - 2.0f * g;
+    v = -sqrtf(fmaxf(d2, 0.f));
+  }
+  const OutT add = (sizeof(OutT) == 8 && mode == PLB_MODE_INNER) ? (OutT)gs : (OutT)v;
+  cost[i * ldc + j] = accumulate ? (OutT)(old + add) : add;
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) cross_finalize_stream_kernel(const float *__restrict__ partial, int splits,
+                                                                    int64_t ld_m, int64_t ld_n, int64_t M, int64_t N,
+                                                                    const double *__restrict__ qa,
+                                                                    const double *__restrict__ qb, int mode,
+                                                                    OutT *__restrict__ cost, int64_t ldc,
+                                                                    int accumulate, int sym_bn) {
+  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.y * kRows;
+  if (j >= N) return;
+  const int64_t split_stride = ld_m * ld_n;
+  bool live[kRows];
+  float pv[kRows][3];
+  OutT old[kRows];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+    const int64_t i = i0 + r;
+    live[r] = i < M && !(sym_bn > 0 && (128 * (i / 128) + 127 < (int64_t)sym_bn * (j / sym_bn)));
+    old[r] = (OutT)0;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) pv[r][s] = 0.f;
+    if (live[r]) {
+#pragma unroll
+      for (int s = 0; s < 3; ++s)
+        if (s < splits) pv[r][s] = partial[(int64_t)s * split_stride + i * ld_n + j];
+      if (accumulate) old[r] = cost[i * ldc + j];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kRows; ++r)
+    if (live[r])
+      epilogue_store<OutT>(((double)pv[r][0] + (double)pv[r][1]) + (double)pv[r][2], i0 + r, j, qa, qb, mode, cost,
+                           ldc, accumulate, old[r]);
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) cross_finalize_reduce_kernel(const float *__restrict__ partial, int splits,
+                                                                    int64_t ld_m, int64_t ld_n, int64_t M, int64_t N,
+                                                                    const double *__restrict__ qa,
+                                                                    const double *__restrict__ qb, int mode,
+                                                                    OutT *__restrict__ cost, int64_t ldc,
+                                                                    int accumulate, int sym_bn) {
+  constexpr int SL = 8, COLS = 32;
   __shared__ double red[SL][COLS + 1];
   const int tx = threadIdx.x % COLS, ty = threadIdx.x / COLS;
   const int64_t j = (int64_t)blockIdx.x * COLS + tx;
@@ -40,37 +93,26 @@ __global__ void __launch_bounds__(256) cross_finalize_kernel(const float *__rest
     }
     for (; s < splits; s += SL) gs += (double)p[(int64_t)s * split_stride];
   }
-  if (SL > 1) {
-    red[ty][tx] = gs;
-    __syncthreads();
-    if (ty != 0) return;
+  red[ty][tx] = gs;
+  __syncthreads();
+  if (ty != 0 || !live) return;
 #pragma unroll
-    for (int k = 1; k < SL; ++k) gs += red[k][tx];
-  }
-  if (!live) return;
-  const float g = (float)gs;
-  float v = g;
-  if (mode == PLB_MODE_NEG_CDIST) {
-    const float d2 = ((float)qa[i] + (float)qb[j]) - 2.0f * g;
-    v = -sqrtf(fmaxf(d2, 0.f));
-  }
-  OutT *c = cost + i * ldc + j;
-  const OutT add = (sizeof(OutT) == 8 && mode == PLB_MODE_INNER) ? (OutT)gs : (OutT)v;
-  *c = accumulate ? (OutT)(*c + add) : add;
+  for (int k = 1; k < SL; ++k) gs += red[k][tx];
+  epilogue_store<OutT>(gs, i, j, qa, qb, mode, cost, ldc, accumulate, accumulate ? cost[i * ldc + j] : (OutT)0);
 }
 
 template <typename OutT>
 static void launch_finalize(const float *partial, int splits, int64_t ld_m, int64_t ld_n, int64_t M, int64_t N,
                             const double *qa, const double *qb, int mode, OutT *cost, int64_t ldc, int accumulate,
                             int sym_bn, cudaStream_t s) {
-  if (splits >= 4) {
+  if (splits > 3) {
     dim3 grid((unsigned)ceil_div(N, 32), (unsigned)M);
-    cross_finalize_kernel<OutT, 8><<<grid, 256, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost, ldc,
-                                                        accumulate, sym_bn);
+    cross_finalize_reduce_kernel<OutT><<<grid, 256, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost,
+                                                            ldc, accumulate, sym_bn);
   } else {
-    dim3 grid((unsigned)ceil_div(N, 256), (unsigned)M);
-    cross_finalize_kernel<OutT, 1><<<grid, 256, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost, ldc,
-                                                        accumulate, sym_bn);
+    dim3 grid((unsigned)ceil_div(N, 256), (unsigned)ceil_div(M, kRows));
+    cross_finalize_stream_kernel<OutT><<<grid, 256, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost,
+                                                            ldc, accumulate, sym_bn);
   }
 }
 
@@ -93,5 +135,5 @@ extern "C" int plb_cross_finalize(const float *partial, int32_t splits, int64_t 
     launch_finalize<double>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost64, ldc, accumulate, sym_bn, s);
   else
     launch_finalize<float>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost, ldc, accumulate, sym_bn, s);
-  return launch_status("cross_finalize_kernel");
+  return launch_status("cross_finalize");
 }
