@@ -318,14 +318,15 @@ def run_b200(args):
         t_merge = time.perf_counter() - t0
         ploader = [host[i % n_dev] for i in range(ps + 1)]
         t0 = time.perf_counter()
+        tstats = {}
         P.train(ploader, m1, m2, model3, spec, perm, costs, 0.0, False, ps, None, num_classes=1000,
-                model_type="rn50")
+                model_type="rn50", stats=tstats)
         torch.cuda.synchronize()
         t_train = time.perf_counter() - t0
         out["merge"] = {"activation_matching_s": dt, "am_batches": Ke, "partial_merge_s": t_merge,
                         "pleas_train_s": t_train, "pleas_batches": ps + 1,
                         "merge_wall_s": dt + t_merge + t_train,
-                        "pleas_samples_per_s": (ps + 1) * BATCH / t_train}
+                        "pleas_samples_per_s": (ps + 1) * BATCH / t_train, "pleas_timing": tstats.get("_timing")}
 
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, spec)

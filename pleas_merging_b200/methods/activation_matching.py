@@ -27,7 +27,7 @@ from .. import ops
 from ..core.solvers import b200_solve_lsa, solve_lsa_batched
 from ..core.utils import Axis, Permutation, PermutationSpec
 from ..graphs import GraphedStep
-from ..parallel import BatchSharder, combine_costs_
+from ..parallel import BatchSharder, combine_costs_, device_prefetch
 
 
 # ------------------------------------------------------------------ plug-compatible operators
@@ -306,8 +306,8 @@ def _fused_costs(spec, model1, model2, dataloader, num_batches, mode, accumulate
     try:
         sharder = BatchSharder(dataloader, num_batches, *(() if distributed else (0, 1)))
         with torch.inference_mode():
-            for _, (x, _) in sharder:
-                runner.run(x.to(runner.device, non_blocking=True))
+            for _, x in device_prefetch(sharder, runner.device):
+                runner.run(x)
         acc = runner.acc
         combine_costs_(acc.flat, sharder, accumulate)
         return {k: c.clone() for k, c in zip(acc.keys, acc.costs)}

@@ -18,6 +18,7 @@ default ``solver="lstsq"`` therefore streams the calibration batches ONCE and
 optimizer and schedule) for weight-level parity checks.  Gradient masks reproduce the
 reference's index order ``mask[si1, so2]``.
 """
+import time
 from copy import copy, deepcopy
 
 import torch
@@ -25,7 +26,7 @@ import torch
 from .. import ops
 from ..core.utils import Axis, get_attr
 from ..graphs import GraphedStep
-from ..parallel import BatchSharder, allreduce_sum_
+from ..parallel import BatchSharder, allreduce_sum_, device_prefetch
 from .partial_matching import get_blocks
 
 
@@ -380,15 +381,20 @@ def _train_lstsq(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, sep
     model2.eval()
     runner = LstsqRunner(model1, model2, model3, perm_blocks, num_classes, separate_classifier, model_type,
                          use_cuda_graph)
+    t_start = time.perf_counter()
     try:
         # the reference's loop breaks when idx > MAX_STEPS, i.e. it consumes MAX_STEPS + 1 batches
         sharder = BatchSharder(((b[0], 0) for b in dataloader), MAX_STEPS + 1, *(() if distributed else (0, 1)))
         with torch.no_grad():
-            for _, (x, _) in sharder:
-                runner.run(x.to(runner.device, non_blocking=True))
+            for _, x in device_prefetch(sharder, runner.device):
+                runner.run(x)
             if runner.accs is None:
                 return model3
             allreduce_sum_(runner.flat) if distributed else None
+            if stats is not None:
+                torch.cuda.synchronize()
+                stats["_timing"] = {"accumulate_s": time.perf_counter() - t_start}
+                t_solve = time.perf_counter()
             for name, acc in runner.accs.items():
                 layer = runner.layers3[name]
                 W, W0 = acc.solve(layer, ridge)
@@ -404,6 +410,9 @@ def _train_lstsq(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, sep
                 layer.weight.data.copy_(W[:, :kw].reshape(layer.weight.shape).to(layer.weight.dtype))
                 if acc.has_bias:
                     layer.bias.data.copy_(W[:, kw].to(layer.bias.dtype))
+            if stats is not None:
+                torch.cuda.synchronize()
+                stats["_timing"]["solve_s"] = time.perf_counter() - t_solve
     finally:
         runner.close()
     return model3

@@ -54,3 +54,38 @@ def combine_costs_(flat, sharder, accumulate):
     if accumulate == "reference" and not sharder.owns_last():
         flat.zero_()
     return allreduce_sum_(flat)
+
+
+def device_prefetch(indexed_batches, device):
+    """Yields (index, x_on_device) one batch ahead: the host-to-device copy of batch i+1 is issued
+    on a side stream while batch i computes, so PCIe time is hidden behind the kernels."""
+    device = torch.device(device)
+    main = torch.cuda.current_stream(device)
+    side = torch.cuda.Stream(device)
+
+    def stage(item):
+        idx, (x, _) = item
+        if x.device == device:
+            return idx, x, None
+        with torch.cuda.stream(side):
+            y = x.to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(side)
+        return idx, y, ev
+
+    it = iter(indexed_batches)
+    try:
+        cur = stage(next(it))
+    except StopIteration:
+        return
+    while cur is not None:
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            nxt = None
+        idx, x, ev = cur
+        if ev is not None:
+            main.wait_event(ev)
+            x.record_stream(main)
+        yield idx, x
+        cur = nxt

@@ -162,6 +162,7 @@ def test_train_closed_form_vs_reference(tiny_golden, name):
         assert mine <= gold[n]["loss_adam"] * (1 + 1e-4) + 1e-9, (n, mine, gold[n])
         assert mine <= gold[n]["loss_lstsq"] * (1 + 2e-2) + 1e-7, (n, mine, gold[n])
         assert stats[n]["objective_fit"] <= stats[n]["objective_init"] + 1e-9
+    assert set(stats["_timing"]) == {"accumulate_s", "solve_s"}
 
 
 def _oracle_layer_losses(P, tiny_golden, perm, costs, ratios, model3):
