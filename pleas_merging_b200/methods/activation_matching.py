@@ -17,6 +17,7 @@ a tuple with ``Axis`` keys, so every batch overwrites and only the last processe
 counts; ``"sum"`` is the paper-intended sum over batches.
 """
 import itertools
+import os
 from collections.abc import Collection
 
 import torch
@@ -140,9 +141,15 @@ class _View:
         self.hi, self.lo, self.rows, self.row_groups, self.k_blocks = hi, lo, rows, row_groups, k_blocks
 
 
+# Taps whose GEMM is below this many FLOPs are "small": a launch of their own is mostly prologue,
+# pipeline ramp and tail (~19 us for ~4 us of work on a ResNet-50 pair), so their GEMMs are deferred
+# to the end of the batch and run as one grouped persistent launch per tile width.
+DEFER_FLOPS = float(os.environ.get("PLB_DEFER_FLOPS", "3e9"))
+
+
 class _TapState:
     """Geometry, row-norm buffer and GEMM plan of one tap for one pair of activation shapes."""
-    __slots__ = ("ra", "rb", "kb", "K", "q", "plan", "version", "pa", "pb")
+    __slots__ = ("ra", "rb", "kb", "K", "q", "plan", "version", "pa", "pb", "deferred", "group")
 
 
 class _Tap:
@@ -169,6 +176,8 @@ class CrossAccumulator:
         self.taps = []
         self.arena = _Arena(device)
         self._retired = []  # plans replaced by a rebind; captured graphs may still point at them
+        self._pending = []  # deferred (small) taps of the batch in flight
+        self._groups = {}   # tuple of deferred states -> GroupedGemm
         self.sink_id = next(_sink_ids)
         _SINKS[self.sink_id] = self
 
@@ -182,6 +191,7 @@ class CrossAccumulator:
         return g.call_function(_tap_dispatch, (self.sink_id, len(self.taps) - 1, na, nb))
 
     def begin_batch(self, reset_costs):
+        self._pending = []
         if reset_costs:
             self.flat.zero_()
         qs = [st.q for t in self.taps for st in t.states.values() if st.q is not None]
@@ -200,7 +210,16 @@ class CrossAccumulator:
         st.ra, st.rb, st.K, st.kb = ra, rb, oa * ia, (oa * ia + 15) // 16
         st.q = torch.zeros(ra + rb, dtype=torch.float64, device=self.device) \
             if self.mode == ops.MODE_NEG_CDIST else None
-        st.plan, st.version = None, -1
+        st.plan, st.version, st.group = None, -1, t.group
+        st.deferred = 2.0 * ra * rb * st.K < DEFER_FLOPS
+        if st.deferred:  # own planes and partial tiles: they must survive until the end of the batch
+            bn = ops.choose_bn(rb)
+            m_tiles, n_tiles = (ra + 127) // 128, (rb + bn - 1) // bn
+            splits = max(1, min(st.kb // 32, 16))
+            st.pa, st.pb = ops.Planes(ra, st.kb, self.device), ops.Planes(rb, st.kb, self.device)
+            st.plan = ops.GemmPlan(st.pa, st.pb, ra, rb, st.kb, splits=splits)
+            st.plan.alg_flops = 2.0 * ra * rb * st.K
+            st.version = None
         return st
 
     def _bind(self, st):
@@ -223,7 +242,7 @@ class CrossAccumulator:
         """Binds every tap state against the final arena (outside any graph capture)."""
         for t in self.taps:
             for st in t.states.values():
-                if st.version != self.arena.version:
+                if not st.deferred and st.version != self.arena.version:
                     self._bind(st)
 
     def tap(self, idx, xa, xb):
@@ -232,13 +251,32 @@ class CrossAccumulator:
         st = t.states.get(key)
         if st is None:
             st = t.states[key] = self._prepare(t, xa, xb)
-        if st.version != self.arena.version:
+        if not st.deferred and st.version != self.arena.version:
             self._bind(st)
         qa, qb = (st.q[:st.ra], st.q[st.ra:]) if st.q is not None else (None, None)
         ops.pack_split(xa, t.axis, st.pa, sumsq=qa)
         ops.pack_split(xb, t.axis, st.pb, sumsq=qb)
+        if st.deferred:
+            self._pending.append(st)
+            return
         st.plan.run()
         st.plan.finalize(self.costs[t.group], self.mode, qa, qb, accumulate=True)
+
+    def end_batch(self):
+        """Runs the deferred small taps: one grouped GEMM launch per tile width, then their
+        epilogues (in tap order, so the accumulation order is deterministic)."""
+        pending, self._pending = self._pending, []
+        for bn in (64, 128, 256):
+            sts = tuple(st for st in pending if st.plan.bn == bn)
+            if not sts:
+                continue
+            grp = self._groups.get(sts)
+            if grp is None:
+                grp = self._groups[sts] = ops.GroupedGemm([st.plan for st in sts])
+            grp.run()
+        for st in pending:
+            qa, qb = (st.q[:st.ra], st.q[st.ra:]) if st.q is not None else (None, None)
+            st.plan.finalize(self.costs[st.group], self.mode, qa, qb, accumulate=True)
 
 
 # ------------------------------------------------------------------ public API
@@ -294,6 +332,7 @@ class CalibrationRunner:
     def _eager(self, x):
         self.acc.begin_batch(reset_costs=self.reset)
         self.gm(x)
+        self.acc.end_batch()
 
     def run(self, x):
         """One calibration batch (x on the models' device)."""

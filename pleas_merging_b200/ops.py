@@ -152,6 +152,7 @@ class GemmPlan:
         p = N.GemmProblem(a.hi.data_ptr(), a.lo.data_ptr(), b.hi.data_ptr(), b.lo.data_ptr(),
                           self.partial.data_ptr(), a.row_groups, b.row_groups, k_blocks, self.m_tiles,
                           self.n_tiles, self.splits, 0, int(symmetric))
+        self.problem = p  # host copy of the table entry (grouped launches re-base cta_begin)
         raw = bytes(p)
         self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
         self._keep = (a, b)
@@ -182,6 +183,35 @@ class GemmPlan:
                                            self.N, N.ptr(qa), N.ptr(qb), mode, c32, c64, out.stride(0),
                                            int(accumulate), self.bn if self.symmetric else 0, N.stream_ptr()),
                 "plb_cross_finalize")
+
+
+class GroupedGemm:
+    """Several small problems of one tile width in ONE persistent launch (their CTAs share the
+    148 SMs), e.g. the ~100 small taps of a ResNet-50 calibration batch."""
+
+    def __init__(self, plans):
+        assert plans and len({p.bn for p in plans}) == 1
+        self.plans, self.bn = list(plans), plans[0].bn
+        raw, begin = bytearray(), 0
+        for p in self.plans:
+            q = N.GemmProblem.from_buffer_copy(bytes(p.problem))
+            q.cta_begin = begin
+            begin += p.total_ctas
+            raw += bytes(q)
+        self.total_items = begin
+        self.table = torch.frombuffer(raw, dtype=torch.uint8).to(self.plans[0].partial.device)
+        self.alg_flops = sum(p.alg_flops for p in self.plans)
+
+    def run(self, impl=None):
+        name = _GEMM_IMPL if impl is None else impl
+        if GEMM_TIMER is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        N.check(N.lib().plb_gemm_grouped(self.table.data_ptr(), len(self.plans), self.total_items, self.bn,
+                                         _impl_code(name), N.stream_ptr()), "plb_gemm_grouped")
+        if GEMM_TIMER is not None:
+            e1.record()
+            GEMM_TIMER.append((e0, e1, self.alg_flops, self.bn))
 
 
 def cross_statistic(x, y, axis, mode):
