@@ -10,6 +10,6 @@ from .core.solvers import b200_solve_lsa
 from .core.utils import (Axis, Permutation, PermutationGroup, PermutationSpec, apply_perm, invert_perm,
                          make_identity_perm, make_random_perm, perm_eq)
 from .methods import (activation_matching, cross_features_cdist, cross_features_inner_product, get_blocks,
-                      partial_merge, train, weight_matching)
+                      partial_merge, reset_bn_stats, train, weight_matching)
 
 __version__ = "0.1.0"

@@ -2,9 +2,10 @@
 from .activation_matching import (activation_matching, build_cross_module, compute_matching_costs,
                                   cross_features_cdist, cross_features_inner_product)
 from .partial_matching import build_partial_merge_model, expand_ratios, get_blocks, partial_merge
+from .bn_stats import reset_bn_stats
 from .pleas_merging import train
 from .weight_matching import weight_matching
 
 __all__ = ["activation_matching", "build_cross_module", "compute_matching_costs", "cross_features_cdist",
            "cross_features_inner_product", "weight_matching", "partial_merge", "get_blocks", "expand_ratios",
-           "build_partial_merge_model", "train"]
+           "build_partial_merge_model", "train", "reset_bn_stats"]

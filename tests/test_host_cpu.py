@@ -57,6 +57,15 @@ def test_product_fails_loudly_without_cuda():
             P.activation_matching(spec, m1, m2, tinynet.make_loader(1, 2), 1)
 
 
+def test_missing_library_raises(monkeypatch, tmp_path):
+    from pleas_merging_b200 import _native
+
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(_native, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _native.lib()
+
+
 def _spec_json(spec):
     return [{"key": [k.key, k.axis], "size": pg.size, "state": sorted([a.key, a.axis] for a in pg.state),
              "node": sorted([a.key, a.axis] for a in pg.node)} for k, pg in spec.items()]

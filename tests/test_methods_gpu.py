@@ -343,3 +343,42 @@ def test_train_with_ragged_last_batch_and_graphs_off():
         outs.append({k: v.clone() for k, v in m3.state_dict().items()})
     for k in outs[0]:
         assert torch.allclose(outs[0][k], outs[1][k], rtol=1e-5, atol=1e-7), k
+
+
+@pytest.mark.parametrize("reset", [True, False])
+def test_reset_bn_stats_matches_driver_loop(reset):
+    """BN re-estimation equals the reference drivers' loop (run_domainnet.py:327-341) run on CPU."""
+    P = _pkg()
+    m, _ = tinynet.make_pair(12, 10)
+    ref = copy.deepcopy(m)
+    loader = tinynet.make_loader(6, 4, 16, seed=3)
+    ref.train()
+    if reset:
+        for mod in ref.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.reset_running_stats()
+    with torch.no_grad():
+        for idx, (x, _) in enumerate(loader):
+            ref(x)
+            if idx + 1 >= 5:
+                break
+    out = P.reset_bn_stats(m.cuda(), loader, num_batches=5, reset=reset)
+    assert out is m and not m.training
+    for (n, a), (_, b) in zip(ref.named_buffers(), m.named_buffers()):
+        assert torch.allclose(a, b.cpu().to(a.dtype), rtol=1e-4, atol=1e-6), n
+
+
+def test_readme_basic_usage_flow_runs():
+    """The reference README flow (spec -> AM -> partial_merge -> PLeaS -> BN reset) end to end."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "basic_usage.py")
+    spec = importlib.util.spec_from_file_location("basic_usage", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    model, stats = mod.main("resnet18", num_batches=3, batch=4, hw=64, max_steps=3, verbose=False)
+    layers = [k for k in stats if not k.startswith("_")]
+    assert len(layers) == 21 and all(stats[k]["objective_fit"] <= stats[k]["objective_init"] + 1e-6 for k in layers)
+    with torch.no_grad():
+        assert bool(torch.isfinite(model(torch.randn(2, 3, 64, 64).cuda())).all())
