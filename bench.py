@@ -31,13 +31,19 @@ METRIC = "rn50_pair_merge_calib_samples_per_s"
 UNIT = "samples/s"
 
 
+def num_classes_of(model_name):
+    return 345 if model_name == "resnet101_domainnet" else 1000
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--model", default="resnet50")
+    ap.add_argument("--model", default="resnet50", help="torchvision arch; 'resnet101_domainnet' = config 4 "
+                    "(ResNet-101 with a 345-class head, run_domainnet.py:182-186)")
+    ap.add_argument("--batch", type=int, default=None, help="samples per batch (default 32; 16 for config 4)")
     ap.add_argument("--pleas-steps", type=int, default=None, help="MAX_STEPS of the PLeaS pass (default 400, "
                     "or 4*steps when steps < 100)")
     ap.add_argument("--no-merge", action="store_true", help="skip the one-off whole-merge timing")
@@ -45,7 +51,14 @@ def parse():
                     "(PyTorch's default; NOT the headline: activations then differ from the fp32 CPU reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=8, help="samples per CPU-baseline batch")
-    return ap.parse_args()
+    args = ap.parse_args()
+    global BATCH, METRIC
+    if args.batch is None:
+        args.batch = 16 if args.model == "resnet101_domainnet" else 32
+    BATCH = args.batch
+    if args.model != "resnet50":
+        METRIC = f"{args.model}_pair_merge_calib_samples_per_s"
+    return args
 
 
 def peaks():
@@ -96,10 +109,15 @@ def make_models(name, device=None):
     import torch
     import torchvision
 
-    torch.manual_seed(0)
-    m1 = getattr(torchvision.models, name)().eval()
-    torch.manual_seed(1)
-    m2 = getattr(torchvision.models, name)().eval()
+    def build(seed):
+        torch.manual_seed(seed)
+        if name == "resnet101_domainnet":
+            m = torchvision.models.resnet101()
+            m.fc = torch.nn.Linear(2048, 345)
+            return m.eval()
+        return getattr(torchvision.models, name)().eval()
+
+    m1, m2 = build(0), build(1)
     if device is not None:
         m1, m2 = m1.to(device), m2.to(device)
     return m1, m2
@@ -241,11 +259,13 @@ def run_b200(args):
         # (events cannot bracket nodes of a replay), so the same steps are re-run un-captured with
         # events around every GEMM launch on the launching stream
         ops.GEMM_TIMER = []
+        overlap_was, acc.overlap = acc.overlap, False  # time the kernel alone, not time-sliced with cuDNN
         torch.cuda.nvtx.range_push("plb_eager")
         for i in range(min(K, 5)):
             runner._eager(dev_batches[(W + i) % n_dev])
         torch.cuda.synchronize()
         torch.cuda.nvtx.range_pop()
+        acc.overlap = overlap_was
         timer, ops.GEMM_TIMER = ops.GEMM_TIMER, None
         launches = launches_per_step * K
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in timer)
@@ -319,8 +339,8 @@ def run_b200(args):
         ploader = [host[i % n_dev] for i in range(ps + 1)]
         t0 = time.perf_counter()
         tstats = {}
-        P.train(ploader, m1, m2, model3, spec, perm, costs, 0.0, False, ps, None, num_classes=1000,
-                model_type="rn50", stats=tstats)
+        P.train(ploader, m1, m2, model3, spec, perm, costs, 0.0, False, ps, None,
+                num_classes=num_classes_of(args.model), model_type="rn50", stats=tstats)
         torch.cuda.synchronize()
         t_train = time.perf_counter() - t0
         out["merge"] = {"activation_matching_s": dt, "am_batches": Ke, "partial_merge_s": t_merge,

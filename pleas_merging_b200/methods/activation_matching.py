@@ -17,6 +17,7 @@ a tuple with ``Axis`` keys, so every batch overwrites and only the last processe
 counts; ``"sum"`` is the paper-intended sum over batches.
 """
 import itertools
+import operator
 import os
 from collections.abc import Collection
 
@@ -55,11 +56,28 @@ def _tap_axes(axes: Collection) -> dict:
     return {k: sorted(v) for k, v in taps.items()}
 
 
-def _dual_graph(model1: Module, model2: Module, axes: Collection, emit):
+_INPLACE_FUNCTIONS = {operator.iadd, operator.isub, operator.imul, operator.itruediv, torch.relu_}
+
+
+def _mutates_inputs(node, root):
+    """Conservative test for fx nodes that may overwrite one of their inputs in place."""
+    if node.op == "call_module":
+        return bool(getattr(root.get_submodule(node.target), "inplace", False))
+    if node.op == "call_method":
+        return node.target.endswith("_") and not node.target.endswith("__")
+    if node.op == "call_function":
+        return node.target in _INPLACE_FUNCTIONS or bool(node.kwargs.get("inplace", False)) \
+            or getattr(node.target, "__name__", "").endswith("_")
+    return False
+
+
+def _dual_graph(model1: Module, model2: Module, axes: Collection, emit, emit_sync=None):
     """Runs both models side by side in one fx graph (model2 must trace to model1's graph, as
     in the reference, :68).  After every tapped node ``emit(graph, name, axis, node_a, node_b)``
     inserts the tap consumer right behind its producers — torchvision's in-place ReLU
-    overwrites the preceding tap's storage, so consumers must not be deferred."""
+    overwrites the preceding tap's storage, so consumers must not be deferred.  ``emit_sync(graph)``
+    (optional) is inserted before every node that may mutate an input: a consumer that reads taps
+    asynchronously gets the chance to finish first."""
     traced = torch.fx.symbolic_trace(model1)
     taps = _tap_axes(axes)
     g = torch.fx.Graph()
@@ -75,6 +93,8 @@ def _dual_graph(model1: Module, model2: Module, axes: Collection, emit):
             out_a = torch.fx.node.map_arg(node.args[0], lambda n: env[0][n])
             out_b = torch.fx.node.map_arg(node.args[0], lambda n: env[1][n])
             continue
+        if emit_sync is not None and _mutates_inputs(node, traced):
+            emit_sync(g)
         for side in (0, 1):
             new = g.node_copy(node, lambda n, side=side: env[side][n])
             if node.op in ("call_module", "get_attr"):
@@ -107,30 +127,39 @@ def _tap_dispatch(sink_id: int, tap_id: int, xa, xb):
     return None
 
 
-class _Arena:
-    """Staging memory shared by all taps (they run back to back on one stream): packed hi/lo
-    planes of both operands and the K-split partial tiles.  Buffers that are outgrown are kept
-    alive: CUDA graphs captured against them stay valid."""
+def _sync_dispatch(sink_id: int):
+    """fx ``call_function`` target: the main stream waits for the packs still reading taps."""
+    _SINKS[sink_id].sync_packs()
+    return None
 
-    def __init__(self, device):
-        self.device = device
+
+class _Arena:
+    """Staging memory for the large taps: a ring of ``slots`` arenas, each holding the packed hi/lo
+    planes of both operands and the K-split partial tiles of one tap.  With the pack and GEMM
+    streams decoupled, tap t+1 is packed into the next slot while tap t is still being multiplied.
+    Buffers that are outgrown are kept alive: CUDA graphs captured against them stay valid."""
+
+    def __init__(self, device, slots=1):
+        self.device, self.slots = device, slots
         self.plane_floats = 0
         self.partial_floats = 0
         self.version = 0
-        self.buf = None
-        self.partial = None
+        self.buf = [None] * slots
+        self.partial = [None] * slots
         self._retired = []
 
     def ensure(self, plane_floats, partial_floats):
         if plane_floats > self.plane_floats:
             self._retired.append(self.buf)
             self.plane_floats = int(plane_floats * 1.25)
-            self.buf = torch.empty(4, self.plane_floats, dtype=torch.float32, device=self.device)
+            self.buf = [torch.empty(4, self.plane_floats, dtype=torch.float32, device=self.device)
+                        for _ in range(self.slots)]
             self.version += 1
         if partial_floats > self.partial_floats:
             self._retired.append(self.partial)
             self.partial_floats = int(partial_floats * 1.25)
-            self.partial = torch.empty(self.partial_floats, dtype=torch.float32, device=self.device)
+            self.partial = [torch.empty(self.partial_floats, dtype=torch.float32, device=self.device)
+                            for _ in range(self.slots)]
             self.version += 1
 
 
@@ -149,7 +178,7 @@ DEFER_FLOPS = float(os.environ.get("PLB_DEFER_FLOPS", "3e9"))
 
 class _TapState:
     """Geometry, row-norm buffer and GEMM plan of one tap for one pair of activation shapes."""
-    __slots__ = ("ra", "rb", "kb", "K", "q", "plan", "version", "pa", "pb", "deferred", "group")
+    __slots__ = ("ra", "rb", "kb", "K", "q", "plan", "version", "pa", "pb", "deferred", "group", "slot")
 
 
 class _Tap:
@@ -160,8 +189,18 @@ class CrossAccumulator:
     """Receives (activation_a, activation_b) at every tap, in graph order, and accumulates the
     chosen cross statistic into its permutation group's cost matrix."""
 
-    def __init__(self, spec: PermutationSpec, mode: int, device):
+    def __init__(self, spec: PermutationSpec, mode: int, device, overlap=True):
         self.mode, self.device = mode, device
+        # The statistics pipeline (HBM-bound packs, tensor-bound GEMMs) runs on a side stream and
+        # overlaps the models' forward kernels (FFMA-bound cuDNN convolutions) on the main stream.
+        # Packs get their own stream (the main stream only ever waits for packs, before an in-place
+        # op overwrites a tap) and the GEMM + epilogue stream trails it through a ring of arenas.
+        self.overlap = overlap
+        self.s_pack = torch.cuda.Stream(device) if overlap else None
+        self.s_gemm = torch.cuda.Stream(device) if overlap else None
+        self._pack_events, self._live = [], []
+        self._slot_free = {}   # arena slot -> event recorded when its last GEMM + epilogue finished
+        self._next_slot = 0
         self.keys = list(spec.keys())
         sizes = [spec[k].size for k in self.keys]
         self.flat = torch.zeros(sum(n * n for n in sizes), dtype=torch.float32, device=device)
@@ -174,7 +213,7 @@ class CrossAccumulator:
             for ax in spec[k].node:
                 self.group_of[ax.key, ax.axis] = gi
         self.taps = []
-        self.arena = _Arena(device)
+        self.arena = _Arena(device, slots=4 if overlap else 1)
         self._retired = []  # plans replaced by a rebind; captured graphs may still point at them
         self._pending = []  # deferred (small) taps of the batch in flight
         self._groups = {}   # tuple of deferred states -> GroupedGemm
@@ -184,6 +223,16 @@ class CrossAccumulator:
     def close(self):
         _SINKS.pop(self.sink_id, None)
 
+    def emit_sync(self, g):
+        return g.call_function(_sync_dispatch, (self.sink_id,))
+
+    def sync_packs(self):
+        if self._pack_events:
+            main = torch.cuda.current_stream(self.device)
+            for ev in self._pack_events:
+                main.wait_event(ev)
+            self._pack_events = []
+
     def emit(self, g, name, axis, na, nb):
         t = _Tap()
         t.name, t.axis, t.group, t.states = name, axis, self.group_of[name, axis], {}
@@ -191,7 +240,8 @@ class CrossAccumulator:
         return g.call_function(_tap_dispatch, (self.sink_id, len(self.taps) - 1, na, nb))
 
     def begin_batch(self, reset_costs):
-        self._pending = []
+        self._pending, self._pack_events, self._live = [], [], []
+        self._slot_free, self._next_slot = {}, 0
         if reset_costs:
             self.flat.zero_()
         qs = [st.q for t in self.taps for st in t.states.values() if st.q is not None]
@@ -210,7 +260,7 @@ class CrossAccumulator:
         st.ra, st.rb, st.K, st.kb = ra, rb, oa * ia, (oa * ia + 15) // 16
         st.q = torch.zeros(ra + rb, dtype=torch.float64, device=self.device) \
             if self.mode == ops.MODE_NEG_CDIST else None
-        st.plan, st.version, st.group = None, -1, t.group
+        st.plan, st.version, st.group, st.slot = None, -1, t.group, None
         st.deferred = 2.0 * ra * rb * st.K < DEFER_FLOPS
         if st.deferred:  # own planes and partial tiles: they must survive until the end of the batch
             bn = ops.choose_bn(rb)
@@ -229,12 +279,15 @@ class CrossAccumulator:
         m_tiles, n_tiles = (st.ra + 127) // 128, (st.rb + bn - 1) // bn
         splits = ops.choose_splits(m_tiles * n_tiles, st.kb, 128, bn)
         self.arena.ensure(max(rga, rgb) * st.kb * 128, splits * m_tiles * 128 * n_tiles * bn)
-        b = self.arena.buf
+        if st.slot is None:  # taps run in the same order every batch, so a tap keeps its slot
+            st.slot = self._next_slot
+        b = self.arena.buf[st.slot]
         if st.plan is not None:
             self._retired.append((st.plan, st.pa, st.pb))
         st.pa = _View(b[0], b[1], st.ra, rga, st.kb)
         st.pb = _View(b[2], b[3], st.rb, rgb, st.kb)
-        st.plan = ops.GemmPlan(st.pa, st.pb, st.ra, st.rb, st.kb, splits=splits, partial=self.arena.partial)
+        st.plan = ops.GemmPlan(st.pa, st.pb, st.ra, st.rb, st.kb, splits=splits,
+                               partial=self.arena.partial[st.slot])
         st.plan.alg_flops = 2.0 * st.ra * st.rb * st.K
         st.version = self.arena.version
 
@@ -245,26 +298,76 @@ class CrossAccumulator:
                 if not st.deferred and st.version != self.arena.version:
                     self._bind(st)
 
-    def tap(self, idx, xa, xb):
+    def _state(self, idx, xa, xb):
         t = self.taps[idx]
         key = (tuple(xa.shape), tuple(xb.shape))
         st = t.states.get(key)
         if st is None:
             st = t.states[key] = self._prepare(t, xa, xb)
-        if not st.deferred and st.version != self.arena.version:
-            self._bind(st)
+        if not st.deferred:
+            if st.version != self.arena.version:
+                self._bind(st)
+            self._next_slot = (st.slot + 1) % self.arena.slots
+        return t, st
+
+    def _pack(self, t, st, xa, xb):
         qa, qb = (st.q[:st.ra], st.q[st.ra:]) if st.q is not None else (None, None)
         ops.pack_split(xa, t.axis, st.pa, sumsq=qa)
         ops.pack_split(xb, t.axis, st.pb, sumsq=qb)
+
+    def _multiply(self, st):
+        qa, qb = (st.q[:st.ra], st.q[st.ra:]) if st.q is not None else (None, None)
+        st.plan.run()
+        st.plan.finalize(self.costs[st.group], self.mode, qa, qb, accumulate=True)
+
+    def tap(self, idx, xa, xb):
+        t, st = self._state(idx, xa, xb)
+        if not self.overlap:
+            self._pack(t, st, xa, xb)
+            if st.deferred:
+                self._pending.append(st)
+            else:
+                self._multiply(st)
+            return
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self._live.append((xa, xb))  # the activations' memory must not be reused while a side stream reads it
+        with torch.cuda.stream(self.s_pack):
+            self.s_pack.wait_event(ready)
+            if not st.deferred and st.slot in self._slot_free:
+                self.s_pack.wait_event(self._slot_free[st.slot])  # the slot's previous tap is done with it
+            self._pack(t, st, xa, xb)
+            packed = torch.cuda.Event()
+            packed.record(self.s_pack)
+        self._pack_events.append(packed)
         if st.deferred:
             self._pending.append(st)
             return
-        st.plan.run()
-        st.plan.finalize(self.costs[t.group], self.mode, qa, qb, accumulate=True)
+        with torch.cuda.stream(self.s_gemm):
+            self.s_gemm.wait_event(packed)
+            self._multiply(st)
+            free = torch.cuda.Event()
+            free.record(self.s_gemm)
+        self._slot_free[st.slot] = free
 
     def end_batch(self):
         """Runs the deferred small taps: one grouped GEMM launch per tile width, then their
-        epilogues (in tap order, so the accumulation order is deterministic)."""
+        epilogues (in tap order, so the accumulation order is deterministic); joins the side streams."""
+        if not self.overlap:
+            return self._end_batch()
+        main = torch.cuda.current_stream(self.device)
+        packs_done = torch.cuda.Event()
+        packs_done.record(self.s_pack)
+        with torch.cuda.stream(self.s_gemm):
+            self.s_gemm.wait_event(packs_done)
+            self._end_batch()
+            done = torch.cuda.Event()
+            done.record(self.s_gemm)
+        main.wait_event(done)
+        self._pack_events, self._live, self._slot_free = [], [], {}
+
+    def _end_batch(self):
         pending, self._pending = self._pending, []
         for bn in (64, 128, 256):
             sts = tuple(st for st in pending if st.plan.bn == bn)
@@ -275,8 +378,11 @@ class CrossAccumulator:
                 grp = self._groups[sts] = ops.GroupedGemm([st.plan for st in sts])
             grp.run()
         for st in pending:
-            qa, qb = (st.q[:st.ra], st.q[st.ra:]) if st.q is not None else (None, None)
-            st.plan.finalize(self.costs[st.group], self.mode, qa, qb, accumulate=True)
+            self._multiply_epilogue(st)
+
+    def _multiply_epilogue(self, st):
+        qa, qb = (st.q[:st.ra], st.q[st.ra:]) if st.q is not None else (None, None)
+        st.plan.finalize(self.costs[st.group], self.mode, qa, qb, accumulate=True)
 
 
 # ------------------------------------------------------------------ public API
@@ -317,11 +423,15 @@ class CalibrationRunner:
     """Streams calibration batches through the dual-model graph; the per-batch pipeline (two
     forwards + pack / GEMM / epilogue per tap) is replayed as a CUDA graph (graphs.GraphedStep)."""
 
-    def __init__(self, spec, model1, model2, mode, accumulate="reference", use_cuda_graph=True):
+    def __init__(self, spec, model1, model2, mode, accumulate="reference", use_cuda_graph=True, overlap=None):
         self.device = _model_device(model1)
-        self.acc = CrossAccumulator(spec, mode, self.device)
+        if overlap is None:
+            # opt-in: the multi-stream pipeline saves ~5 % per batch on a ResNet-50 pair but its first
+            # batch and graph capture cost ~0.35 s more, which only pays off beyond ~200 batches
+            overlap = os.environ.get("PLB_OVERLAP", "0") == "1"
+        self.acc = CrossAccumulator(spec, mode, self.device, overlap=overlap)
         axes = [ax for pg in spec.values() for ax in pg.node]
-        self.gm = _dual_graph(model1, model2, axes, self.acc.emit)
+        self.gm = _dual_graph(model1, model2, axes, self.acc.emit, self.acc.emit_sync if overlap else None)
         self.reset = accumulate == "reference"
         self.step = GraphedStep(self._eager, self.acc.rebind_stale, use_cuda_graph)
 
@@ -341,15 +451,29 @@ class CalibrationRunner:
 
 def _fused_costs(spec, model1, model2, dataloader, num_batches, mode, accumulate, distributed=False,
                  use_cuda_graph=True):
+    debug = os.environ.get("PLB_DEBUG_TIMING") == "1"
+    if debug:
+        import time
+        torch.cuda.synchronize()
+        marks = [("start", time.perf_counter())]
     runner = CalibrationRunner(spec, model1, model2, mode, accumulate, use_cuda_graph)
     try:
         sharder = BatchSharder(dataloader, num_batches, *(() if distributed else (0, 1)))
         with torch.inference_mode():
-            for _, x in device_prefetch(sharder, runner.device):
+            for i, x in device_prefetch(sharder, runner.device):
                 runner.run(x)
+                if debug and i < 3:
+                    torch.cuda.synchronize()
+                    marks.append((f"batch{i}", time.perf_counter()))
         acc = runner.acc
         combine_costs_(acc.flat, sharder, accumulate)
-        return {k: c.clone() for k, c in zip(acc.keys, acc.costs)}
+        out = {k: c.clone() for k, c in zip(acc.keys, acc.costs)}
+        if debug:
+            torch.cuda.synchronize()
+            marks.append(("loop_end", time.perf_counter()))
+            print("[plb timing] " + " ".join(f"{n}+{t - marks[0][1]:.3f}" for n, t in marks[1:]),
+                  f"reserved {torch.cuda.memory_reserved() / 2**30:.1f} GiB", flush=True)
+        return out
     finally:
         runner.close()
 
@@ -388,7 +512,13 @@ def activation_matching(
         gm = build_cross_module(model1, model2, axes, cross_features)
         costs = compute_matching_costs(spec, gm, dataloader, num_batches, accumulate)
     if lsa_solver is b200_solve_lsa:
+        if os.environ.get("PLB_DEBUG_TIMING") == "1":
+            import time
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
         perm = dict(zip(costs.keys(), solve_lsa_batched(costs.values())))
+        if os.environ.get("PLB_DEBUG_TIMING") == "1":
+            print(f"[plb timing] batched LAP {time.perf_counter() - t0:.3f}s", flush=True)
     else:
         perm = {k: lsa_solver(v) for k, v in costs.items()}
     if output_costs:
