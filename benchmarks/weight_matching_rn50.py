@@ -21,9 +21,9 @@ BUDGETS = [1.0, 1.2, 1.55, 1.8, 2.0]  # experiments/configs/merge_configs.py:25-
 
 
 def zip_ratios(spec, budget):
-    i = BUDGETS.index(budget)
-    merged_layers = tuple(f"layer{j}" for j in range(1, 5 - i))
-    return {k: (0.0 if (not k.key.startswith("layer") or k.key.startswith(merged_layers)) else 1.0) for k in spec}
+    from pleas_merging_b200.methods.budget import get_zip_ratios
+
+    return get_zip_ratios(spec, budget, BUDGETS)
 
 
 def main(model="resnet50", cpu=True):
@@ -71,9 +71,27 @@ def main(model="resnet50", cpu=True):
         n3 = sum(v.numel() for k, v in m3.state_dict().items() if "running" not in k and "num_batches" not in k)
         with torch.no_grad():
             y = m3(torch.randn(2, 3, 64, 64, device="cuda"))
-        print(json.dumps({"bench": "partial_merge", "budget": budget, "seconds": round(dt, 3),
-                          "param_ratio_vs_one_model": round(n3 / n1, 3), "output_ok": bool(torch.isfinite(y).all())}),
-              flush=True)
+        rec = {"bench": "partial_merge", "budget": budget, "seconds": round(dt, 3),
+               "param_ratio_vs_one_model": round(n3 / n1, 3), "output_ok": bool(torch.isfinite(y).all())}
+        if budget == 1.55 and "--no-train" not in sys.argv:
+            # PLeaS closed form on the partially merged model: masked row classes, wider layers
+            g = torch.Generator().manual_seed(5)
+            loader = [(torch.randn(16, 3, 128, 128, generator=g), 0) for _ in range(6)]
+            stats = {}
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            P.train(loader, g1, g2, m3, spec, perm, costs, ratios, False, 5, None, stats=stats)
+            torch.cuda.synchronize()
+            layers = [k for k in stats if not k.startswith("_")]
+            rec.update(pleas_seconds=round(time.perf_counter() - t0, 2), pleas_layers=len(layers),
+                       pleas_timing=stats["_timing"],
+                       objective_never_worse=all(stats[k]["objective_fit"] <= stats[k]["objective_init"] + 1e-6
+                                                 for k in layers),
+                       max_K=max(stats[k]["K"] for k in layers),
+                       max_ridge_rel=max(stats[k]["ridge_rel"] for k in layers))
+            with torch.no_grad():
+                rec["output_ok_after_pleas"] = bool(torch.isfinite(m3(torch.randn(2, 3, 64, 64, device="cuda"))).all())
+        print(json.dumps(rec), flush=True)
 
 
 if __name__ == "__main__":

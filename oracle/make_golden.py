@@ -22,6 +22,7 @@ on seeded synthetic inputs and stores inputs-by-seed + outputs as small fixtures
                       get_model_orig_activations
   rn18_golden.pt      ResNet-18 pair at 64x64: activation_matching permutations +
                       objectives (both cross-feature functions), weight_matching perms
+  budget_golden.json  count_linear_flops terms and partial_merge_flops values (tiny, RN18, RN50)
 """
 import json
 import os
@@ -332,13 +333,41 @@ def gen_rn18(ref):
           "wm lap calls", calls[0])
 
 
+def gen_budget(ref):
+    """count_linear_flops (pleas/core/utils.py:558-617) and partial_merge_flops
+    (pleas/methods/partial_matching.py:205-226) on three models -> budget_golden.json."""
+    import torchvision
+
+    out = {}
+    for name in ("tiny", "resnet18", "resnet50"):
+        torch.manual_seed(0)
+        if name == "tiny":
+            m, shape = tinynet.TinyResNet(12, 10).eval(), (1, 3, 16, 16)
+        else:
+            m, shape = getattr(torchvision.models, name)().eval(), (1, 3, 64, 64)
+        spec = ref.compiler.get_permutation_spec(m, (shape,))
+        flops, terms = ref.utils.count_linear_flops(spec, m, (shape,))
+        keys = list(spec.keys())
+        cases = {"r0": 0.0, "r1": 1.0, "r03": 0.3,
+                 "mixed": {k: [0.0, 0.25, 1.0, 0.6][i % 4] for i, k in enumerate(keys)}}
+        out[name] = {
+            "flops": int(flops),
+            "terms": [[int(c)] + [[a.key, a.axis] for a in axes] for c, *axes in terms],
+            "merge_flops": {cn: float(ref.pm.partial_merge_flops(spec, terms, r)) for cn, r in cases.items()},
+            "mixed_ratios": [[k.key, k.axis, cases["mixed"][k]] for k in keys],
+        }
+    with open(os.path.join(GOLD, "budget_golden.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print("budget_golden:", {k: v["flops"] for k, v in out.items()})
+
+
 def main():
     if os.environ.get("PYTHONHASHSEED") != "0":
         sys.exit("run with PYTHONHASHSEED=0 (pins the reference's set iteration order)")
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     ref = load_reference()
-    which = sys.argv[1:] or ["lap", "specs", "tiny", "rn18"]
+    which = sys.argv[1:] or ["lap", "specs", "tiny", "rn18", "budget"]
     if "lap" in which:
         gen_lap()
     if "specs" in which:
@@ -347,6 +376,8 @@ def main():
         gen_tiny(ref)
     if "rn18" in which:
         gen_rn18(ref)
+    if "budget" in which:
+        gen_budget(ref)
 
 
 if __name__ == "__main__":

@@ -311,6 +311,10 @@ class CrossAccumulator:
         return t, st
 
     def _pack(self, t, st, xa, xb):
+        if xa.dtype != torch.float32:  # half / bf16 models: the statistics are computed in fp32
+            xa = xa.float()
+        if xb.dtype != torch.float32:
+            xb = xb.float()
         qa, qb = (st.q[:st.ra], st.q[st.ra:]) if st.q is not None else (None, None)
         ops.pack_split(xa, t.axis, st.pa, sumsq=qa)
         ops.pack_split(xb, t.axis, st.pb, sumsq=qb)

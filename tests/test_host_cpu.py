@@ -193,3 +193,47 @@ def test_two_rank_sharding_and_allreduce_gloo(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"ok {r}" in o, o
+
+
+@pytest.mark.parametrize("name", ["tiny", "resnet18", "resnet50"])
+def test_flop_accounting_equals_reference(name):
+    """count_linear_flops / partial_merge_flops against values produced by the unmodified reference
+    (tests/golden/budget_golden.json; pleas/core/utils.py:558-617, partial_matching.py:205-226)."""
+    import torchvision
+
+    import pleas_merging_b200 as P
+    from oracle import tinynet
+    from pleas_merging_b200.methods.budget import count_linear_flops, partial_merge_flops
+
+    with open(os.path.join(GOLDEN, "budget_golden.json")) as f:
+        gold = json.load(f)[name]
+    torch.manual_seed(0)
+    if name == "tiny":
+        m, shape = tinynet.TinyResNet(12, 10).eval(), (1, 3, 16, 16)
+    else:
+        m, shape = getattr(torchvision.models, name)().eval(), (1, 3, 64, 64)
+    spec = P.get_permutation_spec(m, (shape,))
+    flops, terms = count_linear_flops(spec, m, (shape,))
+    assert int(flops) == gold["flops"]
+    assert [[int(c)] + [[a.key, a.axis] for a in axes] for c, *axes in terms] == gold["terms"]
+    mixed = {P.Axis(k, a): r for k, a, r in gold["mixed_ratios"]}
+    for cn, r in (("r0", 0.0), ("r1", 1.0), ("r03", 0.3), ("mixed", mixed)):
+        assert partial_merge_flops(spec, terms, r) == pytest.approx(gold["merge_flops"][cn], rel=1e-12), cn
+    assert partial_merge_flops(spec, terms, 0.0) == pytest.approx(flops, rel=1e-12)
+
+
+def test_zip_ratios_rule():
+    import torchvision
+
+    import pleas_merging_b200 as P
+    from pleas_merging_b200.methods.budget import get_zip_ratios
+
+    spec = P.get_permutation_spec(torchvision.models.resnet18().eval(), ((1, 3, 64, 64),))
+    base = [1.0, 1.24, 1.46, 1.71, 2.0]  # experiments/configs/merge_configs.py:25 (rn18)
+    assert set(get_zip_ratios(spec, 1.0, base).values()) == {0.0}
+    r = get_zip_ratios(spec, 1.46, base)  # layers 1-2 merged, 3-4 separate, stem merged
+    for k, v in r.items():
+        want = 1.0 if k.key.startswith(("layer3", "layer4")) else 0.0
+        assert v == want, k
+    r2 = get_zip_ratios(spec, 2.0, base)
+    assert all((v == 1.0) == k.key.startswith("layer") for k, v in r2.items())
