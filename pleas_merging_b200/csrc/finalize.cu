@@ -13,7 +13,7 @@ namespace plb {
 // Two shapes of the same epilogue.
 //  * many K splits (SL = 8): 8 threads sum one output element's partials in parallel (fp64, fixed
 //    order => deterministic) and combine through shared memory; block = 32 columns x 8 lanes.
-//  * few splits (SL = 1): the kernel is a pure stream (read partial + read-modify-write cost), so
+//  * up to 48 splits: the kernel is a pure stream (read partial + read-modify-write cost), so
 //    each thread owns kRows rows of one column and issues all its loads before using any of them
 //    (one element per thread left the kernel latency-bound at 0.7 TB/s); block = 256 columns.
 // Symmetric problems only computed the tiles touching the lower triangle: those are the only ones
@@ -45,27 +45,36 @@ __global__ void __launch_bounds__(256) cross_finalize_stream_kernel(const float 
   if (j >= N) return;
   const int64_t split_stride = ld_m * ld_n;
   bool live[kRows];
-  float pv[kRows][3];
+  const float *p[kRows];
   OutT old[kRows];
+  double gs[kRows];
 #pragma unroll
   for (int r = 0; r < kRows; ++r) {
     const int64_t i = i0 + r;
     live[r] = i < M && !(sym_bn > 0 && (128 * (i / 128) + 127 < (int64_t)sym_bn * (j / sym_bn)));
-    old[r] = (OutT)0;
+    // dead rows read a valid dummy location (row i0's column j is inside the padded partial tile)
+    p[r] = partial + (live[r] ? i : i0) * ld_n + j;
+    old[r] = (live[r] && accumulate) ? cost[i * ldc + j] : (OutT)0;
+    gs[r] = 0.0;
+  }
+  int s = 0;
+  for (; s + 1 < splits; s += 2) {  // 2 splits x kRows rows = 8 independent loads in flight
+    float v0[kRows], v1[kRows];
 #pragma unroll
-    for (int s = 0; s < 3; ++s) pv[r][s] = 0.f;
-    if (live[r]) {
-#pragma unroll
-      for (int s = 0; s < 3; ++s)
-        if (s < splits) pv[r][s] = partial[(int64_t)s * split_stride + i * ld_n + j];
-      if (accumulate) old[r] = cost[i * ldc + j];
+    for (int r = 0; r < kRows; ++r) {
+      v0[r] = p[r][(int64_t)s * split_stride];
+      v1[r] = p[r][(int64_t)(s + 1) * split_stride];
     }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) gs[r] += (double)v0[r] + (double)v1[r];
+  }
+  if (s < splits) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) gs[r] += (double)p[r][(int64_t)s * split_stride];
   }
 #pragma unroll
   for (int r = 0; r < kRows; ++r)
-    if (live[r])
-      epilogue_store<OutT>(((double)pv[r][0] + (double)pv[r][1]) + (double)pv[r][2], i0 + r, j, qa, qb, mode, cost,
-                           ldc, accumulate, old[r]);
+    if (live[r]) epilogue_store<OutT>(gs[r], i0 + r, j, qa, qb, mode, cost, ldc, accumulate, old[r]);
 }
 
 template <typename OutT>
@@ -105,7 +114,7 @@ template <typename OutT>
 static void launch_finalize(const float *partial, int splits, int64_t ld_m, int64_t ld_n, int64_t M, int64_t N,
                             const double *qa, const double *qb, int mode, OutT *cost, int64_t ldc, int accumulate,
                             int sym_bn, cudaStream_t s) {
-  if (splits > 3) {
+  if (splits > 48) {
     dim3 grid((unsigned)ceil_div(N, 32), (unsigned)M);
     cross_finalize_reduce_kernel<OutT><<<grid, 256, 0, s>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost,
                                                             ldc, accumulate, sym_bn);

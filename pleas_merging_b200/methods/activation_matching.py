@@ -189,11 +189,11 @@ class CrossAccumulator:
     """Receives (activation_a, activation_b) at every tap, in graph order, and accumulates the
     chosen cross statistic into its permutation group's cost matrix."""
 
-    def __init__(self, spec: PermutationSpec, mode: int, device, overlap=True):
+    def __init__(self, spec: PermutationSpec, mode: int, device, overlap=False):
         self.mode, self.device = mode, device
-        # The statistics pipeline (HBM-bound packs, tensor-bound GEMMs) runs on a side stream and
-        # overlaps the models' forward kernels (FFMA-bound cuDNN convolutions) on the main stream.
-        # Packs get their own stream (the main stream only ever waits for packs, before an in-place
+        # overlap=True (opt-in, PLB_OVERLAP=1): the statistics pipeline (HBM-bound packs, tensor-bound
+        # GEMMs) runs on side streams and overlaps the models' forward kernels (FFMA-bound cuDNN
+        # convolutions) on the main stream.  Packs get their own stream (the main stream only ever waits for packs, before an in-place
         # op overwrites a tap) and the GEMM + epilogue stream trails it through a ring of arenas.
         self.overlap = overlap
         self.s_pack = torch.cuda.Stream(device) if overlap else None
