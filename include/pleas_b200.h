@@ -90,10 +90,11 @@ typedef struct PlbGemmProblem {
   int32_t k_blocks;         /* 16-wide k-blocks to contract */
   int32_t m_tiles, n_tiles, splits;
   int32_t cta_begin;        /* first CTA of this problem in the grouped grid */
-  int32_t symmetric;        /* 1: A and B are the same operand; only tiles with n0+bn > m0 run */
+  int32_t symmetric;        /* 1: A and B are the same operand; only the tiles touching the lower
+                               triangle are enumerated: row-tile mt has min(n_tiles, (128*mt+127)/bn+1) */
 } PlbGemmProblem;
 
-/* bn in {64,128,256}.  total_ctas = sum over problems of m_tiles*n_tiles*splits.
+/* bn in {64,128,256}.  total_ctas = sum over problems of (active tiles)*splits.
  * impl: 16*chain_kb = persistent tcgen05 3xTF32 kernel with in-kernel promotion every chain_kb
  * k-blocks (product path; total_ctas is then the number of work items, the grid is capped at
  * the SM count); 0 = one-CTA-per-work-item tcgen05 kernel (no promotion: the caller bounds the

@@ -38,13 +38,12 @@ struct WorkItem {
   int m_tile, n_tile, split, kb0, nkb;
 };
 
-// Symmetric problems (A and B are the same operand, e.g. U^T U) only need tiles that touch the
-// lower triangle; finalize.cu mirrors the rest.
-template <int BN>
-__device__ __forceinline__ bool skipped(const WorkItem &w) {
-  return w.p->symmetric && (128 * w.m_tile + 127 < BN * w.n_tile);
-}
 
+// Work items of a problem are numbered (tile, split) with the split fastest.  Symmetric problems
+// (A and B are the same operand, e.g. U^T U) only enumerate the tiles that touch the lower triangle
+// — row-tile mt has min(n_tiles, (128 mt + 127) / BN + 1) of them — so the persistent CTAs, which
+// take items round-robin, stay balanced; finalize.cu never reads the tiles that are not produced.
+template <int BN>
 __device__ __forceinline__ WorkItem decode_work(const PlbGemmProblem *probs, int nprob, int cta) {
   int lo = 0, hi = nprob - 1;
   while (lo < hi) {  // last problem whose cta_begin <= cta
@@ -57,8 +56,19 @@ __device__ __forceinline__ WorkItem decode_work(const PlbGemmProblem *probs, int
   int splits = w.p->splits;
   w.split = local % splits;
   int t = local / splits;
-  w.n_tile = t % w.p->n_tiles;
-  w.m_tile = t / w.p->n_tiles;
+  if (w.p->symmetric) {
+    int mt = 0;
+    for (;; ++mt) {
+      const int cnt = min(w.p->n_tiles, (128 * mt + 127) / BN + 1);
+      if (t < cnt) break;
+      t -= cnt;
+    }
+    w.m_tile = mt;
+    w.n_tile = t;
+  } else {
+    w.n_tile = t % w.p->n_tiles;
+    w.m_tile = t / w.p->n_tiles;
+  }
   int64_t kb = w.p->k_blocks;
   w.kb0 = (int)(kb * w.split / splits);
   w.nkb = (int)(kb * (w.split + 1) / splits) - w.kb0;
@@ -76,9 +86,8 @@ __global__ void __launch_bounds__(192, 2) gemm3xtf32_kernel(const PlbGemmProblem
 
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const WorkItem w = decode_work(probs, nprob, blockIdx.x);
+  const WorkItem w = decode_work<BN>(probs, nprob, blockIdx.x);
   const PlbGemmProblem *p = w.p;
-  if (skipped<BN>(w)) return;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -236,8 +245,7 @@ __global__ void __launch_bounds__(320, 1) gemm3xtf32_v2_kernel(const PlbGemmProb
     if (lane == 0) {
       uint32_t it = 0;  // global stage counter across work items
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const WorkItem w = decode_work(probs, nprob, item);
-        if (skipped<BN>(w)) continue;
+        const WorkItem w = decode_work<BN>(probs, nprob, item);
         const PlbGemmProblem *p = w.p;
         const int ga = p->a_row_groups, gb = p->b_row_groups;
         const int g0a = w.m_tile * 16, g0b = w.n_tile * (BN / 8);
@@ -261,8 +269,7 @@ __global__ void __launch_bounds__(320, 1) gemm3xtf32_v2_kernel(const PlbGemmProb
     constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
     uint32_t it = 0, chain = 0;  // global stage / chain counters
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const WorkItem w = decode_work(probs, nprob, item);
-      if (skipped<BN>(w)) continue;
+      const WorkItem w = decode_work<BN>(probs, nprob, item);
       for (int i0 = 0; i0 < w.nkb; i0 += chain_kb, ++chain) {
         const uint32_t buf = chain & 1u;
         mbar_wait(&bar_acc_empty[buf], ((chain >> 1) & 1u) ^ 1u);  // epilogue has drained this buffer
@@ -300,8 +307,7 @@ __global__ void __launch_bounds__(320, 1) gemm3xtf32_v2_kernel(const PlbGemmProb
     const int half = (warp - 2) >> 2;    // which half of the BN columns
     uint32_t chain = 0;
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const WorkItem w = decode_work(probs, nprob, item);
-      if (skipped<BN>(w)) continue;
+      const WorkItem w = decode_work<BN>(probs, nprob, item);
       const PlbGemmProblem *p = w.p;
       float acc[COLS];
 #pragma unroll
@@ -343,9 +349,8 @@ template <int BN>
 __global__ void __launch_bounds__(256) gemm_simt_ref_kernel(const PlbGemmProblem *__restrict__ probs, int nprob) {
   __shared__ float sa[kPackK][128 + 1];
   __shared__ float sb[kPackK][BN + 1];
-  const WorkItem w = decode_work(probs, nprob, blockIdx.x);
+  const WorkItem w = decode_work<BN>(probs, nprob, blockIdx.x);
   const PlbGemmProblem *p = w.p;
-  if (skipped<BN>(w)) return;
   const int tid = threadIdx.x;
   const int row = tid & 127, chalf = tid >> 7;
   float acc[BN / 2];

@@ -148,7 +148,7 @@ class GemmPlan:
         elif partial.numel() < need:
             raise ValueError("GemmPlan: partial workspace too small")
         self.partial = partial
-        self.total_ctas = tiles * self.splits
+        self.total_ctas = active * self.splits  # symmetric problems enumerate only their active tiles
         p = N.GemmProblem(a.hi.data_ptr(), a.lo.data_ptr(), b.hi.data_ptr(), b.lo.data_ptr(),
                           self.partial.data_ptr(), a.row_groups, b.row_groups, k_blocks, self.m_tiles,
                           self.n_tiles, self.splits, 0, int(symmetric))
