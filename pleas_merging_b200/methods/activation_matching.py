@@ -119,6 +119,24 @@ def build_cross_module(model1: Module, model2: Module, axes: Collection, cross_f
 
 _SINKS = {}
 _sink_ids = itertools.count()
+_DEBUG_TIMES = {}
+
+
+class _timed:
+    """PLB_DEBUG_TIMING=1: accumulates host wall time of the set-up paths."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if os.environ.get("PLB_DEBUG_TIMING") == "1":
+            import time
+            self.t0 = time.perf_counter()
+
+    def __exit__(self, *exc):
+        if os.environ.get("PLB_DEBUG_TIMING") == "1":
+            import time
+            _DEBUG_TIMES[self.name] = _DEBUG_TIMES.get(self.name, 0.0) + time.perf_counter() - self.t0
 
 
 def _tap_dispatch(sink_id: int, tap_id: int, xa, xb):
@@ -217,11 +235,14 @@ class CrossAccumulator:
         self._retired = []  # plans replaced by a rebind; captured graphs may still point at them
         self._pending = []  # deferred (small) taps of the batch in flight
         self._groups = {}   # tuple of deferred states -> GroupedGemm
+        self.pool = ops.SlabPool(device)      # planes / partial tiles / row norms of the deferred taps
+        self.tables = ops.TableArena(device)  # GEMM problem-table entries
         self.sink_id = next(_sink_ids)
         _SINKS[self.sink_id] = self
 
     def close(self):
         _SINKS.pop(self.sink_id, None)
+        self.pool.release()
 
     def emit_sync(self, g):
         return g.call_function(_sync_dispatch, (self.sink_id,))
@@ -258,7 +279,8 @@ class CrossAccumulator:
             raise ValueError(f"tap {t.name}:{t.axis} has {ra}x{rb} units but its group has {n}")
         st = _TapState()
         st.ra, st.rb, st.K, st.kb = ra, rb, oa * ia, (oa * ia + 15) // 16
-        st.q = torch.zeros(ra + rb, dtype=torch.float64, device=self.device) \
+        # fp64 row norms live in the slab too (zeroed by begin_batch before the first use)
+        st.q = self.pool.empty(2 * (ra + rb)).view(torch.float64).zero_() \
             if self.mode == ops.MODE_NEG_CDIST else None
         st.plan, st.version, st.group, st.slot = None, -1, t.group, None
         st.deferred = 2.0 * ra * rb * st.K < DEFER_FLOPS
@@ -266,8 +288,9 @@ class CrossAccumulator:
             bn = ops.choose_bn(rb)
             m_tiles, n_tiles = (ra + 127) // 128, (rb + bn - 1) // bn
             splits = max(1, min(st.kb // 32, 16))
-            st.pa, st.pb = ops.Planes(ra, st.kb, self.device), ops.Planes(rb, st.kb, self.device)
-            st.plan = ops.GemmPlan(st.pa, st.pb, ra, rb, st.kb, splits=splits)
+            st.pa = ops.Planes(ra, st.kb, self.device, pool=self.pool)
+            st.pb = ops.Planes(rb, st.kb, self.device, pool=self.pool)
+            st.plan = ops.GemmPlan(st.pa, st.pb, ra, rb, st.kb, splits=splits, pool=self.pool, tables=self.tables)
             st.plan.alg_flops = 2.0 * ra * rb * st.K
             st.version = None
         return st
@@ -287,7 +310,7 @@ class CrossAccumulator:
         st.pa = _View(b[0], b[1], st.ra, rga, st.kb)
         st.pb = _View(b[2], b[3], st.rb, rgb, st.kb)
         st.plan = ops.GemmPlan(st.pa, st.pb, st.ra, st.rb, st.kb, splits=splits,
-                               partial=self.arena.partial[st.slot])
+                               partial=self.arena.partial[st.slot], tables=self.tables)
         st.plan.alg_flops = 2.0 * st.ra * st.rb * st.K
         st.version = self.arena.version
 
@@ -303,10 +326,12 @@ class CrossAccumulator:
         key = (tuple(xa.shape), tuple(xb.shape))
         st = t.states.get(key)
         if st is None:
-            st = t.states[key] = self._prepare(t, xa, xb)
+            with _timed("prepare"):
+                st = t.states[key] = self._prepare(t, xa, xb)
         if not st.deferred:
             if st.version != self.arena.version:
-                self._bind(st)
+                with _timed("bind"):
+                    self._bind(st)
             self._next_slot = (st.slot + 1) % self.arena.slots
         return t, st
 
@@ -379,7 +404,8 @@ class CrossAccumulator:
                 continue
             grp = self._groups.get(sts)
             if grp is None:
-                grp = self._groups[sts] = ops.GroupedGemm([st.plan for st in sts])
+                with _timed("group"):
+                    grp = self._groups[sts] = ops.GroupedGemm([st.plan for st in sts], tables=self.tables)
             grp.run()
         for st in pending:
             self._multiply_epilogue(st)
@@ -476,7 +502,9 @@ def _fused_costs(spec, model1, model2, dataloader, num_batches, mode, accumulate
             torch.cuda.synchronize()
             marks.append(("loop_end", time.perf_counter()))
             print("[plb timing] " + " ".join(f"{n}+{t - marks[0][1]:.3f}" for n, t in marks[1:]),
-                  f"reserved {torch.cuda.memory_reserved() / 2**30:.1f} GiB", flush=True)
+                  f"reserved {torch.cuda.memory_reserved() / 2**30:.1f} GiB",
+                  "setup " + " ".join(f"{k}={v:.3f}s" for k, v in _DEBUG_TIMES.items()), flush=True)
+            _DEBUG_TIMES.clear()
         return out
     finally:
         runner.close()

@@ -45,18 +45,88 @@ def plane_geometry(rows, K):
     return rg, kb, rg * kb * 128
 
 
+class SlabPool:
+    """Bump allocator over a few large device chunks.
+
+    Every cudaMalloc is device-synchronous, so hundreds of per-tap ``torch.empty`` calls in the
+    first calibration batch stall the host behind the queued forward kernels (measured: 1.4-2.4 s
+    for a ResNet-50 pair).  A pool takes chunks of 0.5 GB and up (doubling), hands out 256-byte
+    aligned float32 views, and on ``release()`` returns its chunks to a per-device free list that
+    later pools reuse, so repeated calls allocate nothing."""
+    _free = {}  # device -> list of float32 chunks
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.chunks, self.used = [], 0
+        self.next_floats = 1 << 27  # 0.5 GB
+
+    def empty(self, nfloats):
+        nfloats = max(int(nfloats), 1)
+        need = (nfloats + 63) // 64 * 64
+        if not self.chunks or self.used + need > self.chunks[-1].numel():
+            free = SlabPool._free.setdefault(self.device, [])
+            fit = [c for c in free if c.numel() >= need]
+            if fit:
+                chunk = min(fit, key=lambda c: c.numel())
+                free[:] = [c for c in free if c is not chunk]  # identity, not tensor ==
+            else:
+                chunk = torch.empty(max(need, self.next_floats), dtype=torch.float32, device=self.device)
+                self.next_floats = min(self.next_floats * 2, 1 << 30)
+            self.chunks.append(chunk)
+            self.used = 0
+        out = self.chunks[-1][self.used:self.used + nfloats]
+        self.used += need
+        return out
+
+    def release(self):
+        SlabPool._free.setdefault(self.device, []).extend(self.chunks)
+        self.chunks, self.used = [], 0
+
+
+class TableArena:
+    """Device memory for GEMM problem-table entries, filled through a pinned staging mirror with
+    asynchronous copies (a pageable cudaMemcpy per plan would synchronise the device each time)."""
+    ENTRY = ctypes.sizeof(N.GemmProblem)
+
+    def __init__(self, device, capacity=4096):
+        self.device, self.capacity, self.count = torch.device(device), capacity, 0
+        self.dev = torch.empty(capacity * self.ENTRY, dtype=torch.uint8, device=self.device)
+        self.host = torch.empty(capacity * self.ENTRY, dtype=torch.uint8).pin_memory()
+        self._older = []
+
+    def put(self, raw):
+        n = len(raw)
+        assert n % self.ENTRY == 0
+        k = n // self.ENTRY
+        if self.count + k > self.capacity:  # start a fresh block; views into the old one stay valid
+            self._older.append((self.dev, self.host))
+            self.capacity = max(self.capacity, 2 * k)
+            self.dev = torch.empty(self.capacity * self.ENTRY, dtype=torch.uint8, device=self.device)
+            self.host = torch.empty(self.capacity * self.ENTRY, dtype=torch.uint8).pin_memory()
+            self.count = 0
+        lo, hi = self.count * self.ENTRY, (self.count + k) * self.ENTRY
+        self.host[lo:hi] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+        view = self.dev[lo:hi]
+        view.copy_(self.host[lo:hi], non_blocking=True)
+        self.count += k
+        return view
+
+
 class Planes:
     """hi/lo packed planes of one [rows, K] operand (or several K-concatenated ones)."""
 
-    def __init__(self, rows, k_blocks, device):
+    def __init__(self, rows, k_blocks, device, pool=None):
         self.rows = rows
         self.row_groups = 16 * ((rows + 127) // 128)
         self.k_blocks = k_blocks
         n = self.row_groups * k_blocks * 128
         # no zero-fill needed: pad row groups only feed output rows/cols nobody reads, and the
         # pack kernel writes zeros for k >= K and for rows >= rows inside real groups
-        self.hi = torch.empty(n, dtype=torch.float32, device=device)
-        self.lo = torch.empty(n, dtype=torch.float32, device=device)
+        if pool is not None:
+            self.hi, self.lo = pool.empty(n), pool.empty(n)
+        else:
+            self.hi = torch.empty(n, dtype=torch.float32, device=device)
+            self.lo = torch.empty(n, dtype=torch.float32, device=device)
 
 
 def as_rows_view(x, axis):
@@ -130,7 +200,7 @@ def choose_splits(tiles, k_blocks, m_rows=128, n_rows=256, impl=None):
 class GemmPlan:
     """One 3xTF32 GEMM over packed planes: partial tiles + problem-table entry on device."""
 
-    def __init__(self, a, b, M, Nn, k_blocks, splits=None, symmetric=False, partial=None):
+    def __init__(self, a, b, M, Nn, k_blocks, splits=None, symmetric=False, partial=None, pool=None, tables=None):
         self.M, self.N = M, Nn
         self.bn = choose_bn(Nn)
         self.m_tiles = (M + 127) // 128
@@ -144,7 +214,7 @@ class GemmPlan:
         dev = a.hi.device
         need = self.splits * self.ld_m * self.ld_n
         if partial is None:
-            partial = torch.empty(need, dtype=torch.float32, device=dev)
+            partial = pool.empty(need) if pool is not None else torch.empty(need, dtype=torch.float32, device=dev)
         elif partial.numel() < need:
             raise ValueError("GemmPlan: partial workspace too small")
         self.partial = partial
@@ -154,7 +224,8 @@ class GemmPlan:
                           self.n_tiles, self.splits, 0, int(symmetric))
         self.problem = p  # host copy of the table entry (grouped launches re-base cta_begin)
         raw = bytes(p)
-        self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self.table = tables.put(raw) if tables is not None else \
+            torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
         self._keep = (a, b)
         self.alg_flops = 2.0 * M * Nn * k_blocks * 16  # callers that know the unpadded K overwrite
 
@@ -189,7 +260,7 @@ class GroupedGemm:
     """Several small problems of one tile width in ONE persistent launch (their CTAs share the
     148 SMs), e.g. the ~100 small taps of a ResNet-50 calibration batch."""
 
-    def __init__(self, plans):
+    def __init__(self, plans, tables=None):
         assert plans and len({p.bn for p in plans}) == 1
         self.plans, self.bn = list(plans), plans[0].bn
         raw, begin = bytearray(), 0
@@ -199,7 +270,8 @@ class GroupedGemm:
             begin += p.total_ctas
             raw += bytes(q)
         self.total_items = begin
-        self.table = torch.frombuffer(raw, dtype=torch.uint8).to(self.plans[0].partial.device)
+        self.table = tables.put(bytes(raw)) if tables is not None else \
+            torch.frombuffer(raw, dtype=torch.uint8).to(self.plans[0].partial.device)
         self.alg_flops = sum(p.alg_flops for p in self.plans)
 
     def run(self, impl=None):

@@ -27,6 +27,6 @@ for rep in range(2):
     t2 = sync()
     costs = {k: c.clone() for k, c in zip(runner.acc.keys, runner.acc.costs)}
     perms = solve_lsa_batched(costs.values()); t3 = sync()
-    runner.close(); t4 = sync()
+    runner.close(); del runner; import gc; gc.collect(); t4 = sync()
     print(f"rep{rep}: build {t1-t0:.3f}s  batches " + " ".join(f"[{i}]@{t-t1:.3f}" for i, t in marks) +
           f"  loop {t2-t1:.3f}s  lap {t3-t2:.3f}s  close {t4-t3:.3f}s  mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB reserved {torch.cuda.memory_reserved()/2**30:.1f} GiB")
