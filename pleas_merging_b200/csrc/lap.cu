@@ -18,6 +18,7 @@
 // (45 B per column: n <= 4096 fits the 227 KB CTA limit); only the cost row is read from
 // global/L2 per iteration, coalesced.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -256,8 +257,17 @@ extern "C" int plb_lap_solve_batched(const float *const *cost, const int32_t *n,
     }
     configured = smem;
   }
-  int threads = (int)(ceil_div(max_n, 64) * 32);  // ~2 columns per thread
-  threads = threads < 64 ? 64 : (threads > 1024 ? 1024 : threads);
+  // columns per thread (PLB_LAP_COLS_PER_THREAD, default 1): measured on B200, one column per
+  // thread wins up to the 1024-thread cap (n=256: 2.3 ms vs 2.7 / 3.7 / 5.5 ms at 2 / 4 / 8 columns) —
+  // the per-column fp64 relaxation costs more than the wider block-wide reduction
+  static int cols_per_thread = 0;
+  if (cols_per_thread == 0) {
+    const char *e = getenv("PLB_LAP_COLS_PER_THREAD");
+    cols_per_thread = e ? atoi(e) : 1;
+    if (cols_per_thread < 1) cols_per_thread = 1;
+  }
+  int threads = (int)(ceil_div(max_n, 32 * cols_per_thread) * 32);
+  threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
   lap_kernel<<<n_problems, threads, smem, (cudaStream_t)stream>>>(cost, n, ld, col4row, objective, status, maximize);
   return launch_status("lap_kernel");
 }
