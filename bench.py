@@ -128,6 +128,9 @@ def make_models(name, device=None):
 def run_reference(args):
     """The reference's CPU path (oracle port) on a bounded sample: K steps of `cpu_sample`
     samples each through matching_costs (two forwards + 174 -cdist taps), all host threads."""
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host thread it can
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(os.cpu_count())
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
