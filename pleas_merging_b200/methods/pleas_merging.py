@@ -14,6 +14,10 @@ default ``solver="lstsq"`` therefore streams the calibration batches ONCE and
     directions the data never excites keep their init value, exactly like a gradient method
     started at ``W0``; entries whose gradient mask is zero stay at ``W0``.
 
+The alternative targets of the reference (``merging="reg_mean" | "perm_separatels" |
+"perm_mixedls"``, :125-144) stack two sample groups along the batch axis; here each group is one
+more pack + GEMM pass with its own channel maps into the same accumulators.
+
 ``solver="adam"`` replays the reference's Adam trajectory (same hooks, targets, masks,
 optimizer and schedule) for weight-level parity checks.  Gradient masks reproduce the
 reference's index order ``mask[si1, so2]``.
@@ -119,17 +123,39 @@ def get_model_orig_activations(acts1, acts2, bi, bo, merging="perm_gradmask"):
 
 # ------------------------------------------------------------------ least-squares path
 
-def _channel_map(b, device):
-    """Merged-channel -> (source channel in model 1, in model 2, weights) for
-    cat[(a[b1] + b[b2]) / 2, a[b1c], b[b2c]]."""
-    b1, b2, b1c, b2c = (t.to("cpu", torch.int64) for t in b)
+def _maps(idx1, idx2, w1, w2, device):
+    """(chan1, chan2, scale1, scale2) device tensors from per-channel source indices (-1 = none)."""
+    c1 = torch.as_tensor(idx1, dtype=torch.int32)
+    c2 = torch.as_tensor(idx2, dtype=torch.int32)
+    s1 = torch.as_tensor(w1, dtype=torch.float32)
+    s2 = torch.as_tensor(w2, dtype=torch.float32)
+    return tuple(t.to(device) for t in (c1, c2, s1, s2))
+
+
+def _target_passes(b, merging, device, src_channels, is_input):
+    """Sample groups of one side (inputs or targets) of the least-squares problem as channel maps
+    for the pack kernel, one entry per group stacked along the batch axis by the reference
+    (pleas_merging.py:125-147).  Returns (list of maps, merged channel count)."""
+    b1, b2, b1c, b2c = (t.to("cpu", torch.int64).tolist() for t in b)
     nm, ms = len(b1), len(b1c)
-    neg = lambda n: torch.full((n,), -1, dtype=torch.int64)
-    c1 = torch.cat([b1, b1c, neg(ms)]).to(torch.int32)
-    c2 = torch.cat([b2, neg(ms), b2c]).to(torch.int32)
-    s1 = torch.cat([torch.full((nm,), 0.5), torch.ones(ms), torch.zeros(ms)])
-    s2 = torch.cat([torch.full((nm,), 0.5), torch.zeros(ms), torch.ones(ms)])
-    return tuple(t.to(device) for t in (c1, c2, s1, s2)), nm + 2 * ms
+    none, zeros, ones, half = [-1] * ms, [0.0] * ms, [1.0] * ms, [0.5] * nm
+    if merging == "reg_mean":  # no permutation: the two models' samples are stacked as they are
+        ident = list(range(src_channels))
+        one = [1.0] * src_channels
+        off = [-1] * src_channels
+        zero = [0.0] * src_channels
+        return [_maps(ident, off, one, zero, device), _maps(off, ident, zero, one, device)], src_channels
+    if "perm_separatels" in merging or ("perm_mixedls" in merging and not is_input):
+        # group 1: model 1 only [x1[b1], x1[b1c], 0]; group 2: model 2 only [x2[b2], 0, x2[b2c]]
+        g1 = _maps(b1 + b1c + none, [-1] * (nm + 2 * ms), [1.0] * nm + ones + zeros, [0.0] * (nm + 2 * ms), device)
+        g2 = _maps([-1] * (nm + 2 * ms), b2 + none + b2c, [0.0] * (nm + 2 * ms), [1.0] * nm + zeros + ones, device)
+        return [g1, g2], nm + 2 * ms
+    if "perm_mixedls" in merging:  # inputs: averaged merged units, each model's own separate units
+        g1 = _maps(b1 + b1c + none, b2 + none + none, half + ones + zeros, half + zeros + zeros, device)
+        g2 = _maps(b1 + none + none, b2 + none + b2c, half + zeros + zeros, half + zeros + ones, device)
+        return [g1, g2], nm + 2 * ms
+    # default 'perm_gradmask': one group, cat[(x1[b1] + x2[b2]) / 2, x1[b1c], x2[b2c]]
+    return [_maps(b1 + b1c + none, b2 + none + b2c, half + ones + zeros, half + zeros + ones, device)], nm + 2 * ms
 
 
 class _Workspace:
@@ -152,7 +178,7 @@ class _Workspace:
 class _LayerLS:
     """Normal-equation accumulator of one trained layer: G = U^T U, R = U^T Y-bar in fp64."""
 
-    def __init__(self, name, layer, bi, bo, ip_shape, device):
+    def __init__(self, name, layer, bi, bo, ip_shape, device, merging="perm_gradmask", cout_src=None):
         self.name = name
         self.is_conv = isinstance(layer, torch.nn.Conv2d)
         if self.is_conv:
@@ -168,8 +194,9 @@ class _LayerLS:
             self.kernel = self.stride = self.dilation = (1, 1)
             self.padding = (0, 0)
         self.has_bias = layer.bias is not None
-        self.imap, self.cin = _channel_map(bi, device)
-        self.omap, self.cout = _channel_map(bo, device)
+        self.ipasses, self.cin = _target_passes(bi, merging, device, ip_shape[1], True)
+        self.opasses, self.cout = _target_passes(bo, merging, device, cout_src, False)
+        assert len(self.ipasses) == len(self.opasses)
         self.K = self.cin * self.kernel[0] * self.kernel[1] + int(self.has_bias)
         self.bi, self.bo = bi, bo
         self.G = self.R = None  # views into the runner's flat fp64 accumulator
@@ -217,15 +244,16 @@ class _LayerLS:
         B, _, Ho, Wo = op1.shape
         L = B * Ho * Wo
         pu, py, plan_g, plan_r = self.bound[L, ws.version]
-        ops.pack_im2col(ip1.float(), ip2.float(), *self.imap, self.cin, self.kernel, self.stride, self.padding,
-                        self.dilation, (Ho, Wo), self.has_bias, pu)
-        ops.pack_im2col(op1.float(), op2.float(), *self.omap, self.cout, (1, 1), (1, 1), (0, 0), (1, 1), (Ho, Wo),
-                        False, py)
-        plan_g.run()
-        plan_g.finalize(self.G, ops.MODE_INNER, accumulate=True)
-        plan_r.run()
-        plan_r.finalize(self.R, ops.MODE_INNER, accumulate=True)
-        self.count += L
+        ip1, ip2, op1, op2 = ip1.float(), ip2.float(), op1.float(), op2.float()
+        for imap, omap in zip(self.ipasses, self.opasses):  # one pass per stacked sample group
+            ops.pack_im2col(ip1, ip2, *imap, self.cin, self.kernel, self.stride, self.padding, self.dilation,
+                            (Ho, Wo), self.has_bias, pu)
+            ops.pack_im2col(op1, op2, *omap, self.cout, (1, 1), (1, 1), (0, 0), (1, 1), (Ho, Wo), False, py)
+            plan_g.run()
+            plan_g.finalize(self.G, ops.MODE_INNER, accumulate=True)
+            plan_r.run()
+            plan_r.finalize(self.R, ops.MODE_INNER, accumulate=True)
+            self.count += L
 
     def out_positions(self, acts1):
         op = acts1[1]
@@ -297,7 +325,8 @@ class LstsqRunner:
     per-batch pipeline is replayed as a CUDA graph."""
 
     def __init__(self, model1, model2, model3, perm_blocks, num_classes, separate_classifier, model_type,
-                 use_cuda_graph=True):
+                 use_cuda_graph=True, merging="perm_gradmask"):
+        self.merging = merging
         self.device = next(iter(model1.parameters())).device
         if self.device.type != "cuda":
             raise RuntimeError("pleas_merging_b200 runs on a CUDA device: move the models to cuda first")
@@ -326,7 +355,8 @@ class LstsqRunner:
                 continue
             bi, bo = _layer_blocks(self.perm_blocks, name, self.acts1[name][0].shape[1], self.num_classes,
                                    self.separate_classifier, self.model_type)
-            self.accs[name] = _LayerLS(name, layer, bi, bo, tuple(self.acts1[name][0].shape), self.device)
+            self.accs[name] = _LayerLS(name, layer, bi, bo, tuple(self.acts1[name][0].shape), self.device,
+                                       self.merging, self.acts1[name][1].shape[1])
         # one flat fp64 accumulator for every layer's [G | R]: a single all-reduce in multi-GPU runs
         total = sum(a.K * (a.K + a.cout) for a in self.accs.values())
         self.flat = torch.zeros(total, dtype=torch.float64, device=self.device)
@@ -376,11 +406,12 @@ def layer_objective(W, G, R, yy_plus=0.0):
 
 
 def _train_lstsq(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, separate_classifier, num_classes,
-                 model_type, ridge, verbose, stats, distributed=False, use_cuda_graph=True):
+                 model_type, ridge, verbose, stats, distributed=False, use_cuda_graph=True,
+                 merging="perm_gradmask"):
     model1.eval()
     model2.eval()
     runner = LstsqRunner(model1, model2, model3, perm_blocks, num_classes, separate_classifier, model_type,
-                         use_cuda_graph)
+                         use_cuda_graph, merging)
     t_start = time.perf_counter()
     try:
         # the reference's loop breaks when idx > MAX_STEPS, i.e. it consumes MAX_STEPS + 1 batches
@@ -501,8 +532,5 @@ def train(dataloader, model1, model2, model3, spec, perm, costs, budget_ratios, 
                            num_classes, lr, verbose, model_type, WANDB, wandb_run)
     if solver != "lstsq":
         raise ValueError("solver must be 'lstsq' or 'adam'")
-    if merging != "perm_gradmask":
-        raise NotImplementedError("the closed form implements the default 'perm_gradmask' targets; "
-                                  "use solver='adam' for the alternative targets")
     return _train_lstsq(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, separate_classifier, num_classes,
-                        model_type, ridge, verbose, stats, distributed, use_cuda_graph)
+                        model_type, ridge, verbose, stats, distributed, use_cuda_graph, merging)

@@ -382,3 +382,74 @@ def test_readme_basic_usage_flow_runs():
     assert len(layers) == 21 and all(stats[k]["objective_fit"] <= stats[k]["objective_init"] + 1e-6 for k in layers)
     with torch.no_grad():
         assert bool(torch.isfinite(model(torch.randn(2, 3, 64, 64).cuda())).all())
+
+
+@pytest.mark.parametrize("merging,ratio", [("perm_separatels", 0.5), ("perm_mixedls", 0.5), ("reg_mean", 0.0),
+                                           ("perm_gradmask", 0.5)])
+def test_closed_form_alternative_targets(merging, ratio):
+    """The closed form on the reference's alternative least-squares targets (pleas_merging.py:125-147):
+    per layer, its objective equals the fp64 optimum of the explicitly stacked (X-bar, Y-bar) problem
+    built with the torch restatement of get_model_orig_activations, masked entries held at the init."""
+    import importlib
+    import torch.nn.functional as F
+
+    P = _pkg()
+    PM = importlib.import_module("pleas_merging_b200.methods.pleas_merging")
+    m1, m2, spec = _tiny(P)
+    loader = tinynet.make_loader(6, 4, 16, seed=21)
+    perm, costs = P.activation_matching(spec, m1, m2, loader, 6, output_costs=True, accumulate="sum")
+    model3 = P.partial_merge(spec, m1, m2, perm, costs, ratio)
+    init = {k: v.detach().clone() for k, v in model3.state_dict().items()}
+    P.train(loader, m1, m2, model3, spec, perm, costs, ratio, False, 5, None, num_classes=10, model_type="rn18",
+            merging=merging)
+    fitted = model3.state_dict()
+    # explicit fp64 problem
+    blocks = P.get_blocks(spec, perm, costs, ratio)
+    pb = dict(blocks)
+    for axis, pg in spec.items():
+        for ax in pg.state:
+            pb[ax] = pb[axis]
+    a1, a2 = {}, {}
+    hooks = PM.capture_inputs(m1, a1) + PM.capture_inputs(m2, a2)
+    Us, Ts = {}, {}
+    with torch.no_grad():
+        for x, _ in loader:
+            m1(x.cuda())
+            m2(x.cuda())
+            for name, layer in m1.named_modules():
+                if not isinstance(layer, (torch.nn.Conv2d, torch.nn.Linear)):
+                    continue
+                bi, bo = PM._layer_blocks(pb, name, a1[name][0].shape[1], 10, False, "rn18")
+                X, Y = PM.get_model_orig_activations(a1[name], a2[name], bi, bo, merging)
+                X, Y = X.double(), Y.double()
+                if isinstance(layer, torch.nn.Conv2d):
+                    U = F.unfold(X, layer.kernel_size, layer.dilation, layer.padding, layer.stride)
+                    U = U.transpose(1, 2).reshape(-1, U.shape[1])
+                    T = Y.flatten(2).transpose(1, 2).reshape(-1, Y.shape[1])
+                else:
+                    U, T = X, Y
+                if layer.bias is not None:
+                    U = torch.cat([U, torch.ones(U.shape[0], 1, dtype=U.dtype, device=U.device)], 1)
+                Us.setdefault(name, []).append(U)
+                Ts.setdefault(name, []).append(T)
+    for h in hooks:
+        h.remove()
+    for name in Us:
+        U, T = torch.cat(Us[name]), torch.cat(Ts[name])
+
+        def flat(sd):
+            W = sd[f"{name}.weight"].double().flatten(1)
+            return torch.cat([W, sd[f"{name}.bias"].double()[:, None]], 1) if f"{name}.bias" in sd else W
+
+        W0, Wf = flat(init), flat(fitted)
+        loss = lambda W: float(((U @ W.T - T) ** 2).sum())
+        # fp64 optimum: minimum-norm update from W0 (unmasked layers only keeps this check simple)
+        dW = torch.linalg.lstsq(U.cpu(), (T - U @ W0.T).cpu(), driver="gelsd").solution.T.to(U.device)  # rank-deficient U
+        best = loss(W0 + dW)
+        scale = float((T ** 2).sum()) + 1e-12
+        assert loss(Wf) <= loss(W0) + 1e-9 * scale, name
+        if ratio == 0.0 or merging != "perm_gradmask":
+            # no gradient mask constraints bite at ratio 0; for ratio 0.5 masked rows make `best` a lower bound
+            assert loss(Wf) >= best - 1e-6 * scale, name
+        if ratio == 0.0:
+            assert loss(Wf) <= best + 2e-3 * scale, name
