@@ -8,7 +8,10 @@ the group's model-B operands K-concatenated into one plane pair (the model-A pla
 packed once per group), ONE 3xTF32 tcgen05 GEMM with a fused split-K reduction, the GPU LAP
 kernel on the device-resident cost matrix, a device-side progress test, and gather kernels
 for the permutation — the only host round trip is one 4-byte progress flag per sweep.  The
-visit order replays ``torch.randperm`` on a seeded CPU generator exactly like the reference.
+visit order replays ``torch.randperm`` on a seeded CPU generator exactly like the reference;
+visits that do not share a tensor commute, so each sweep is scheduled by the levels of its
+conflict DAG and the visits of a level are solved in ONE batched LAP launch (the LAPs are 96 %
+of the time on a ResNet-50 pair) with results identical to the sequential order.
 """
 from collections.abc import Sequence
 from copy import copy, deepcopy
@@ -109,21 +112,53 @@ def weight_matching(
     flag = torch.zeros(1, dtype=torch.int32, device=device)
     gain = torch.zeros(1, dtype=torch.float64, device=device)
 
+    # Two visits of a sweep commute unless their groups touch a common tensor (the cost of one then
+    # depends on the permutation the other applies).  Scheduling a sweep by levels of that conflict
+    # DAG — a visit runs once every EARLIER conflicting visit has been applied — gives exactly the
+    # sequential result, and the visits of a level share one batched LAP launch.
+    touched = {p: {ax.key for ax in spec[p].state} for p in perm_names}
+
+    def levels(order):
+        lvl, out = [], []
+        for j, p in enumerate(order):
+            l = 0
+            for i in range(j):
+                if touched[order[i]] & touched[p]:
+                    l = max(l, lvl[i] + 1)
+            lvl.append(l)
+            while len(out) <= l:
+                out.append([])
+            out[l].append(p)
+        return out
+
+    def finish_visit(iteration, p, A, newP):
+        ops.wm_progress(A, newP, flag, gain)
+        if verbose:
+            print(f"{iteration}/{p.key}:{p.axis}: {gain.item()}")
+        perm[p] = ops.compose_perm(perm[p], newP)
+        all_costs[p] = A
+        for sb in state_bs:
+            apply_perm({p: newP}, spec, sb, inplace=True)
+
     with torch.no_grad():
         for iteration in range(max_iter):
             statuses = []
-            progress = False
-            for p_ix in torch.randperm(len(perm_names), generator=rng):
-                p = perm_names[p_ix]
-                pg = spec[p]
-                n = pg.size
-                if fused:
-                    if p not in plans:
-                        plans[p] = _GroupPlan(pg, p, state_as, state_bs, skip_suffixes, skip_missing, device)
-                    A = plans[p].build_cost(state_bs)
-                    (newP,), _, status = ops.lap_solve_batched([A], True)
+            order = [perm_names[i] for i in torch.randperm(len(perm_names), generator=rng)]
+            if fused:
+                for wave in levels(order):
+                    mats = []
+                    for p in wave:
+                        if p not in plans:
+                            plans[p] = _GroupPlan(spec[p], p, state_as, state_bs, skip_suffixes, skip_missing, device)
+                        mats.append(plans[p].build_cost(state_bs))
+                    newPs, _, status = ops.lap_solve_batched(mats, True)
                     statuses.append(status)
-                else:
+                    for p, A, newP in zip(wave, mats, newPs):
+                        finish_visit(iteration, p, A, newP)
+            else:
+                for p in order:
+                    pg = spec[p]
+                    n = pg.size
                     A = torch.zeros(n, n, device=device)
                     for ax in pg.state:
                         if ax.key.endswith(tuple(skip_suffixes)):
@@ -134,13 +169,7 @@ def weight_matching(
                             A.add_(cross_weights(sa[ax.key], sb[ax.key], ax.axis))
                     assert A.norm() > 0
                     newP = lsa_solver(A).to(device=device, dtype=torch.int64)
-                ops.wm_progress(A, newP, flag, gain)
-                if verbose:
-                    print(f"{iteration}/{p.key}:{p.axis}: {gain.item()}")
-                perm[p] = ops.compose_perm(perm[p], newP)
-                all_costs[p] = A
-                for sb in state_bs:
-                    apply_perm({p: newP}, spec, sb, inplace=True)
+                    finish_visit(iteration, p, A, newP)
             if statuses:
                 ops.raise_on_lap_status(torch.cat(statuses))
             progress = bool(flag.item())
