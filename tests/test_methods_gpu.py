@@ -453,3 +453,33 @@ def test_closed_form_alternative_targets(merging, ratio):
             assert loss(Wf) >= best - 1e-6 * scale, name
         if ratio == 0.0:
             assert loss(Wf) <= best + 2e-3 * scale, name
+
+
+def test_full_size_properties_rn50():
+    """BASELINE config-2 sizes (ResNet-50, batches of 32x3x224x224), where the CPU oracle is too
+    slow: (1) a model matched against a permuted copy of itself recovers the planted permutation in
+    every one of the 37 groups; (2) accumulate="sum" is linear over batches; (3) accumulate=
+    "reference" equals the last batch alone."""
+    import torchvision
+
+    P = _pkg()
+    torch.manual_seed(0)
+    m1 = torchvision.models.resnet50().eval()
+    spec = P.get_permutation_spec(m1, ((1, 3, 224, 224),))
+    planted = P.make_random_perm(spec, generator=torch.Generator().manual_seed(3))
+    m2 = copy.deepcopy(m1)
+    P.apply_perm(planted, spec, m2, inplace=True)
+    m1, m2 = m1.cuda(), m2.cuda()
+    g = torch.Generator().manual_seed(4)
+    loader = [(torch.randn(32, 3, 224, 224, generator=g), 0) for _ in range(3)]
+    perm, c_all = P.activation_matching(spec, m1, m2, loader, 3, output_costs=True, accumulate="sum")
+    inv = P.invert_perm(planted)
+    for k in spec:
+        assert torch.equal(perm[k], inv[k]), k
+    parts = [P.activation_matching(spec, m1, m2, [b], 1, output_costs=True, accumulate="sum")[1] for b in loader]
+    _, c_ref = P.activation_matching(spec, m1, m2, loader, 3, output_costs=True)  # reference semantics
+    for k in spec:
+        total = parts[0][k] + parts[1][k] + parts[2][k]
+        scale = float(total.abs().max())
+        assert float((c_all[k] - total).abs().max()) <= 2e-6 * scale, k
+        assert float((c_ref[k] - parts[2][k]).abs().max()) <= 2e-6 * float(parts[2][k].abs().max()), k
