@@ -271,8 +271,14 @@ def run_b200(args):
         acc.overlap = overlap_was
         timer, ops.GEMM_TIMER = ops.GEMM_TIMER, None
         launches = launches_per_step * K
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in timer)
-    gemm_flops = sum(f for _, _, f, _ in timer)
+    gemm_ms = sum(t[0].elapsed_time(t[1]) for t in timer)
+    gemm_flops = sum(t[2] for t in timer)
+    by_class = {}  # tensor-bound launches (one large tap each) vs the grouped small-tap launches, per tile width
+    for a, b, f, bn, nprob in timer:
+        c = by_class.setdefault(f"bn{bn}_" + ("single" if nprob == 1 else "grouped"), [0.0, 0.0, 0])
+        c[0] += a.elapsed_time(b)
+        c[1] += f
+        c[2] += 1
     t = torch.tensor([ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -305,7 +311,13 @@ def run_b200(args):
                 f"CUDA-graph region); peak = {pk['source']} sustained bf16 "
                 f"{pk['bf16_tflops_sustained']} TFLOP/s / 2 (TF32 dense rate)",
         "algorithmic_tflops": gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0,
-        "kernel_ms_per_step": gemm_ms / min(K, 5), "kernel_share_of_step": (gemm_ms / min(K, 5)) / (ms / K)}
+        "kernel_ms_per_step": gemm_ms / min(K, 5), "kernel_share_of_step": (gemm_ms / min(K, 5)) / (ms / K),
+        # launches split by class: "single" = one tap (>= 3 GFLOP, tensor-bound) per launch, "grouped" = the
+        # small taps of a batch in one persistent launch per tile width (HBM/latency-bound: C/4 flop/B)
+        "by_class": {k: {"launches": v[2], "ms_per_step": v[0] / min(K, 5),
+                         "algorithmic_tflops": v[1] / (v[0] / 1e3) / 1e12 if v[0] > 0 else 0.0,
+                         "tensor_frac": 3.0 * v[1] / (v[0] / 1e3) / 1e12 / tf32_peak if v[0] > 0 else 0.0}
+                     for k, v in sorted(by_class.items())}}
     out["clocks"] = clocks
 
     # ---- e2e through the public API with pinned host batches (H2D + LAP + D2H of the perms inside)
@@ -327,13 +339,23 @@ def run_b200(args):
                   "note": "activation_matching(spec, m1, m2, pinned host loader, K, accumulate='sum'): H2D of "
                           "every batch, all taps, batched GPU LAP, D2H of the permutations"}
 
-    if rank != 0:  # the remaining legs are single-GPU; rank 0 reports
-        dist.destroy_process_group()
-        return
-
-    # ---- the whole merge once: activation matching -> partial_merge -> PLeaS closed form
-    if not args.no_merge and world == 1:
+    # ---- the whole merge once: activation matching -> partial_merge -> PLeaS closed form.
+    # Multi-GPU runs time the SAME fixed job (strong scaling): the 100 + 401 batches are dealt to the
+    # ranks, cost matrices are all-reduced, normal equations reduced onto the layers' owner ranks,
+    # solves run layer-parallel and the fitted weights are all-reduced.
+    if not args.no_merge:
         ps = args.pleas_steps if args.pleas_steps is not None else (400 if K >= 100 else 4 * K)
+        dist_on = world > 1
+        t_am = dt
+        if dist_on:
+            aloader = [host[i % n_dev] for i in range(Ke)]
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            perm, costs = P.activation_matching(spec, m1, m2, aloader, Ke, output_costs=True, accumulate="sum",
+                                                distributed=True)
+            torch.cuda.synchronize()
+            t_am = time.perf_counter() - t0
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         model3 = P.partial_merge(spec, m1, m2, perm, costs, 0.0)
@@ -343,15 +365,23 @@ def run_b200(args):
         t0 = time.perf_counter()
         tstats = {}
         P.train(ploader, m1, m2, model3, spec, perm, costs, 0.0, False, ps, None,
-                num_classes=num_classes_of(args.model), model_type="rn50", stats=tstats)
+                num_classes=num_classes_of(args.model), model_type="rn50", stats=tstats, distributed=dist_on)
         torch.cuda.synchronize()
         t_train = time.perf_counter() - t0
-        out["merge"] = {"activation_matching_s": dt, "am_batches": Ke, "partial_merge_s": t_merge,
+        walls = torch.tensor([t_am, t_merge, t_train], dtype=torch.float64, device=device)
+        if dist_on:
+            dist.all_reduce(walls, op=dist.ReduceOp.MAX)
+        t_am, t_merge, t_train = walls.tolist()
+        out["merge"] = {"activation_matching_s": t_am, "am_batches": Ke, "partial_merge_s": t_merge,
                         "pleas_train_s": t_train, "pleas_batches": ps + 1,
-                        "merge_wall_s": dt + t_merge + t_train,
+                        "merge_wall_s": t_am + t_merge + t_train, "scaling": "strong" if dist_on else None,
                         "pleas_samples_per_s": (ps + 1) * BATCH / t_train, "pleas_timing": tstats.get("_timing")}
 
-    if not args.no_cpu_baseline:
+    if rank != 0:  # rank 0 reports
+        dist.destroy_process_group()
+        return
+
+    if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         out["cpu_baseline"] = cpu_baseline(args, spec)
     print(json.dumps(out))
     if world > 1:

@@ -30,7 +30,8 @@ import torch
 from .. import ops
 from ..core.utils import Axis, get_attr
 from ..graphs import GraphedStep
-from ..parallel import BatchSharder, allreduce_sum_, device_prefetch
+from ..parallel import (BatchSharder, allreduce_sum_, assign_owners, device_prefetch, reduce_to_owners_,
+                        world)
 from .partial_matching import get_blocks
 
 
@@ -325,8 +326,8 @@ class LstsqRunner:
     per-batch pipeline is replayed as a CUDA graph."""
 
     def __init__(self, model1, model2, model3, perm_blocks, num_classes, separate_classifier, model_type,
-                 use_cuda_graph=True, merging="perm_gradmask"):
-        self.merging = merging
+                 use_cuda_graph=True, merging="perm_gradmask", world_size=1):
+        self.merging, self.world_size = merging, world_size
         self.device = next(iter(model1.parameters())).device
         if self.device.type != "cuda":
             raise RuntimeError("pleas_merging_b200 runs on a CUDA device: move the models to cuda first")
@@ -357,15 +358,26 @@ class LstsqRunner:
                                    self.separate_classifier, self.model_type)
             self.accs[name] = _LayerLS(name, layer, bi, bo, tuple(self.acts1[name][0].shape), self.device,
                                        self.merging, self.acts1[name][1].shape[1])
-        # one flat fp64 accumulator for every layer's [G | R]: a single all-reduce in multi-GPU runs
-        total = sum(a.K * (a.K + a.cout) for a in self.accs.values())
+        # one flat fp64 accumulator for every layer's [G | R].  Multi-GPU runs solve layer-parallel:
+        # each layer has an owner rank (balanced by solve cost) and the buffer is laid out owner by
+        # owner, so summing the normal equations is one reduce per owner instead of an all-reduce.
+        accs = list(self.accs.values())
+        owners = assign_owners([a.K ** 3 / 3.0 + float(a.K) ** 2 * a.cout for a in accs], self.world_size)
+        total = sum(a.K * (a.K + a.cout) for a in accs)
         self.flat = torch.zeros(total, dtype=torch.float64, device=self.device)
         off = 0
-        for a in self.accs.values():
-            a.G = self.flat[off:off + a.K * a.K].view(a.K, a.K)
-            off += a.K * a.K
-            a.R = self.flat[off:off + a.K * a.cout].view(a.K, a.cout)
-            off += a.K * a.cout
+        self.segments, self.segment_owners = [], []
+        for r in range(self.world_size):
+            for a, o in zip(accs, owners):
+                if o != r:
+                    continue
+                a.owner, start = r, off
+                a.G = self.flat[off:off + a.K * a.K].view(a.K, a.K)
+                off += a.K * a.K
+                a.R = self.flat[off:off + a.K * a.cout].view(a.K, a.cout)
+                off += a.K * a.cout
+                self.segments.append((start, off - start))
+                self.segment_owners.append(r)
 
     def _bind_all(self):
         """Sizes the shared workspace for this batch shape and binds every layer's plans to it."""
@@ -405,43 +417,86 @@ def layer_objective(W, G, R, yy_plus=0.0):
     return float(((W @ G) * W).sum() - 2 * (W * R.T).sum()) + yy_plus
 
 
+def _write_back(layer, acc, W):
+    """Stores a fitted flattened [Co, K] weight (bias in the last column) into the layer."""
+    kw = acc.K - int(acc.has_bias)
+    layer.weight.data.copy_(W[:, :kw].reshape(layer.weight.shape).to(layer.weight.dtype))
+    if acc.has_bias:
+        layer.bias.data.copy_(W[:, kw].to(layer.bias.dtype))
+
+
 def _train_lstsq(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, separate_classifier, num_classes,
                  model_type, ridge, verbose, stats, distributed=False, use_cuda_graph=True,
                  merging="perm_gradmask"):
     model1.eval()
     model2.eval()
+    rank, wsize = world() if distributed else (0, 1)
     runner = LstsqRunner(model1, model2, model3, perm_blocks, num_classes, separate_classifier, model_type,
-                         use_cuda_graph, merging)
+                         use_cuda_graph, merging, wsize)
     t_start = time.perf_counter()
     try:
         # the reference's loop breaks when idx > MAX_STEPS, i.e. it consumes MAX_STEPS + 1 batches
-        sharder = BatchSharder(((b[0], 0) for b in dataloader), MAX_STEPS + 1, *(() if distributed else (0, 1)))
+        sharder = BatchSharder(((b[0], 0) for b in dataloader), MAX_STEPS + 1, rank, wsize)
         with torch.no_grad():
             for _, x in device_prefetch(sharder, runner.device):
                 runner.run(x)
+            if wsize > 1:  # collective decision: a rank without a batch has no layer shapes to reduce into
+                have = torch.tensor([int(runner.accs is not None)], device=runner.device)
+                torch.distributed.all_reduce(have, op=torch.distributed.ReduceOp.MIN)
+                if int(have.item()) == 0:
+                    raise RuntimeError(f"distributed PLeaS needs at least one batch per rank "
+                                       f"({sharder.total} batches for {wsize} ranks)")
             if runner.accs is None:
                 return model3
-            allreduce_sum_(runner.flat) if distributed else None
+            if wsize > 1:  # every owner receives the sum of its layers' [G | R]
+                reduce_to_owners_(runner.flat, runner.segments, runner.segment_owners)
             if stats is not None:
                 torch.cuda.synchronize()
                 stats["_timing"] = {"accumulate_s": time.perf_counter() - t_start}
                 t_solve = time.perf_counter()
+            # fitted weights travel in one flat fp64 buffer ([Co, K] per layer): a rank fills the layers
+            # it owns, the rest stays zero, and one all-reduce hands every rank every layer
+            sizes = {n: a.cout * a.K for n, a in runner.accs.items()}
+            wflat = torch.zeros(sum(sizes.values()), dtype=torch.float64, device=runner.device) if wsize > 1 else None
+            woff, off = {}, 0
+            for n in runner.accs:
+                woff[n], off = off, off + sizes[n]
+            local_stats = {}
             for name, acc in runner.accs.items():
+                if acc.owner != rank:
+                    continue
                 layer = runner.layers3[name]
                 W, W0 = acc.solve(layer, ridge)
                 if stats is not None:
-                    stats[name] = {"objective_init": layer_objective(W0, acc.G, acc.R),
-                                   "objective_fit": layer_objective(W, acc.G, acc.R),
-                                   "rows": acc.count, "cout": acc.cout, "K": acc.K,
-                                   "ridge_rel": getattr(acc, "ridge_used", 0.0)
-                                   / max(float(acc.G.diagonal().mean()), 1e-300)}
+                    local_stats[name] = {"objective_init": layer_objective(W0, acc.G, acc.R),
+                                         "objective_fit": layer_objective(W, acc.G, acc.R),
+                                         "rows": acc.count, "cout": acc.cout, "K": acc.K, "owner": rank,
+                                         "ridge_rel": getattr(acc, "ridge_used", 0.0)
+                                         / max(float(acc.G.diagonal().mean()), 1e-300)}
                 if verbose:
                     print(f"{name}: K={acc.K} Co={acc.cout} rows={acc.count}")
-                kw = acc.K - int(acc.has_bias)
-                layer.weight.data.copy_(W[:, :kw].reshape(layer.weight.shape).to(layer.weight.dtype))
-                if acc.has_bias:
-                    layer.bias.data.copy_(W[:, kw].to(layer.bias.dtype))
+                if wflat is not None:
+                    wflat[woff[name]:woff[name] + sizes[name]].copy_(W.reshape(-1))
+                else:
+                    _write_back(layer, acc, W)
+            if wflat is not None:
+                allreduce_sum_(wflat)
+                for name, acc in runner.accs.items():
+                    _write_back(runner.layers3[name], acc,
+                                wflat[woff[name]:woff[name] + sizes[name]].view(acc.cout, acc.K))
             if stats is not None:
+                if wsize > 1:
+                    gathered = [None] * wsize
+                    torch.distributed.all_gather_object(gathered, local_stats)
+                    for part in gathered:
+                        local_stats.update(part)
+                    rows = torch.tensor([a.count for a in runner.accs.values()], dtype=torch.int64,
+                                        device=runner.device)
+                    allreduce_sum_(rows)
+                    for n, r in zip(runner.accs, rows.tolist()):
+                        local_stats[n]["rows"] = r
+                for n in runner.accs:  # layer order, like the single-GPU run
+                    stats[n] = local_stats[n]
                 torch.cuda.synchronize()
                 stats["_timing"]["solve_s"] = time.perf_counter() - t_solve
     finally:
@@ -521,7 +576,8 @@ def train(dataloader, model1, model2, model3, spec, perm, costs, budget_ratios, 
     ``solver="adam"`` replays the reference optimiser.  ``ridge`` is relative to the mean
     diagonal of each layer's Gram matrix and is escalated tenfold when a pivot fails.  ``stats`` (dict) receives per-layer objectives.
     ``distributed=True`` (initialised torch.distributed job, same loader on every rank) deals the
-    batches round-robin and sums the normal equations with one all-reduce; every rank solves."""
+    batches round-robin, reduces every layer's normal equations onto the rank that owns the layer
+    (balanced by solve cost), solves layer-parallel and all-reduces the fitted weights."""
     blocks = get_blocks(spec, perm, costs, budget_ratios, False)
     perm_blocks = copy(blocks)
     for axis, pg in spec.items():

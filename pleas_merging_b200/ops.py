@@ -19,7 +19,7 @@ NUM_SMS = 148
 #   "simt"       SIMT fp32 FMA cross-check kernel on the same planes (debugging only; still CUDA)
 _GEMM_IMPL = os.environ.get("PLB_GEMM_IMPL", "tcgen05")
 assert _GEMM_IMPL in ("tcgen05", "tcgen05_v1", "simt")
-GEMM_TIMER = None  # set to a list by bench.py to collect (start, end, flops, bn) per GEMM launch
+GEMM_TIMER = None  # set to a list by bench.py to collect (start, end, flops, bn, n_problems) per GEMM launch
 
 
 def set_gemm_impl(name):
@@ -235,7 +235,7 @@ class GemmPlan:
             e0.record()
             self._launch(impl)
             e1.record()
-            GEMM_TIMER.append((e0, e1, self.alg_flops, self.bn))
+            GEMM_TIMER.append((e0, e1, self.alg_flops, self.bn, 1))
             return
         self._launch(impl)
 
@@ -283,7 +283,7 @@ class GroupedGemm:
                                          _impl_code(name), N.stream_ptr()), "plb_gemm_grouped")
         if GEMM_TIMER is not None:
             e1.record()
-            GEMM_TIMER.append((e0, e1, self.alg_flops, self.bn))
+            GEMM_TIMER.append((e0, e1, self.alg_flops, self.bn, len(self.plans)))
 
 
 def cross_statistic(x, y, axis, mode):

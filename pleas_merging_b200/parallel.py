@@ -5,7 +5,10 @@ The merge path shards only where the work splits naturally: cal
 batches are dealt round-robin at WHOLE-batch granularity (the -cdist statistic takes a sqrt per
 batch, so a batch is never split) and the additive accumulators — group cost matrices, PLeaS
 normal equations — are summed with ONE all-reduce at the end.  There is no collective inside
-the data path.
+the data path.  The per-layer least-squares solves are independent, so in a multi-GPU job they
+are dealt to owner ranks (``assign_owners``): every owner receives the sum of its layers'
+normal equations (``reduce_to_owners_``), solves them, and the fitted weights are exchanged with
+one more all-reduce of a flat weight buffer in which each rank filled only its own layers.
 """
 import torch
 import torch.distributed as dist
@@ -44,6 +47,37 @@ def allreduce_sum_(tensor):
     if world()[1] > 1:
         dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
     return tensor
+
+
+def assign_owners(costs, world_size):
+    """Deals independent work items (per-layer solves, weight ~ K^3/3 + K^2 Co) to ranks:
+    longest-processing-time-first greedy — heaviest item to the least-loaded rank, ties to the
+    lowest rank — so every rank computes the same assignment without communicating."""
+    load = [0.0] * world_size
+    owner = [0] * len(costs)
+    for i in sorted(range(len(costs)), key=lambda i: (-costs[i], i)):
+        r = min(range(world_size), key=lambda r: (load[r], r))
+        owner[i] = r
+        load[r] += costs[i]
+    return owner
+
+
+def reduce_to_owners_(flat, segments, owners):
+    """Sums each ``(offset, length)`` segment of the flat accumulator onto its owner rank
+    (runs of consecutive segments with one owner travel as one reduce).  On the other ranks the
+    segment's content is unspecified afterwards."""
+    if world()[1] == 1:
+        return flat
+    i = 0
+    while i < len(segments):
+        j = i
+        while j + 1 < len(segments) and owners[j + 1] == owners[i] and \
+                segments[j + 1][0] == segments[j][0] + segments[j][1]:
+            j += 1
+        lo, hi = segments[i][0], segments[j][0] + segments[j][1]
+        dist.reduce(flat[lo:hi], dst=owners[i], op=dist.ReduceOp.SUM)
+        i = j + 1
+    return flat
 
 
 def combine_costs_(flat, sharder, accumulate):

@@ -174,6 +174,25 @@ for mode in ("sum", "reference"):
     parallel.combine_costs_(flat, sh, mode)
     want = float(sum(range(5))) if mode == "sum" else 4.0
     assert torch.equal(flat, torch.full((4,), want)), (mode, flat)
+# layer-parallel solves: owners get the sum of their segments, then a flat all-reduce shares results
+costs = [5.0, 1.0, 4.0, 2.0, 2.0]
+owners = parallel.assign_owners(costs, world)
+assert owners == [0, 1, 1, 1, 0], owners            # LPT greedy: 5->r0, 4->r1, 2->r1, 2->r0, 1->r1
+lens = [3, 2, 4, 1, 2]
+order = [i for r in range(world) for i in range(5) if owners[i] == r]   # buffer laid out owner by owner
+segs, off = {}, 0
+for i in order:
+    segs[i] = (off, lens[i]); off += lens[i]
+flat = torch.arange(off, dtype=torch.float64) * (rank + 1)
+parallel.reduce_to_owners_(flat, [segs[i] for i in order], [owners[i] for i in order])
+out = torch.zeros(off, dtype=torch.float64)
+for i in order:
+    lo, n = segs[i]
+    if owners[i] == rank:
+        assert torch.equal(flat[lo:lo + n], torch.arange(lo, lo + n, dtype=torch.float64) * 3), (i, flat)
+        out[lo:lo + n] = flat[lo:lo + n] * 2            # the owner's "solve"
+parallel.allreduce_sum_(out)
+assert torch.equal(out, torch.arange(off, dtype=torch.float64) * 6), out
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)
@@ -193,6 +212,28 @@ def test_two_rank_sharding_and_allreduce_gloo(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"ok {r}" in o, o
+
+
+def test_assign_owners_balances_resnet50_solves():
+    """Layer-parallel PLeaS: the LPT deal keeps the heaviest rank within 10 % of the mean for
+    the ResNet-50 layer mix (K^3/3 + K^2 Co per layer) — or at the single heaviest layer (the
+    three K=4608 convolutions of layer4 are 23 % of the work each) once that exceeds the mean."""
+    from pleas_merging_b200.parallel import assign_owners
+
+    widths = [(64, 3), (128, 4), (256, 6), (512, 3)]
+    layers, cin = [(3 * 49, 64)], 64
+    for w, blocks in widths:
+        for b in range(blocks):
+            layers += [(cin, w), (w * 9, w), (w, 4 * w)] + ([(cin, 4 * w)] if b == 0 else [])
+            cin = 4 * w
+    layers.append((2049, 1000))
+    costs = [k ** 3 / 3.0 + k * k * co for k, co in layers]
+    assert len(costs) == 54
+    for world in (1, 2, 4, 8):
+        owners = assign_owners(costs, world)
+        load = [sum(c for c, o in zip(costs, owners) if o == r) for r in range(world)]
+        assert max(load) <= max(1.10 * sum(costs) / world, max(costs)), (world, load)
+        assert owners == assign_owners(costs, world)
 
 
 @pytest.mark.parametrize("name", ["tiny", "resnet18", "resnet50"])
