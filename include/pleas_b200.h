@@ -44,13 +44,14 @@ const char *plb_last_error_string(void);
  * the transposed copy.  plb_pack_split writes it as two fp32 planes hi = tf32(x) and
  * lo = tf32(x - hi) in the tcgen05 K-major no-swizzle core-matrix order
  *     plane[kb][g][j][r][e],  row = 8 g + r,  k = 16 kb + 4 j + e
- * with `row_groups` (a multiple of 16) groups of 8 rows per 16-wide k-block, so that any
- * (128·t rows x 16 k) operand tile is one contiguous run that a single cp.async.bulk can
- * land in shared memory ready for tcgen05.mma.  Rows >= rows and k >= K are written as 0.
+ * with `row_groups` (>= ceil(rows/8)) groups of 8 rows per 16-wide k-block, so that any
+ * (up to 128·t rows x 16 k) operand tile is one contiguous run that a single cp.async.bulk can
+ * land in shared memory ready for tcgen05.mma; the GEMM copies only the row groups that exist.
+ * Rows >= rows inside the last group and k >= K are written as 0.
  * --------------------------------------------------------------------------------------- */
 
 /* bytes of ONE plane for a [rows, K] operand; *row_groups / *k_blocks receive the padded
- * geometry (row_groups = 16*ceil(rows/128), k_blocks = ceil(K/16)).  Host-only helper. */
+ * geometry (row_groups = ceil(rows/8), k_blocks = ceil(K/16)).  Host-only helper. */
 int64_t plb_plane_bytes(int64_t rows, int64_t K, int32_t *row_groups, int32_t *k_blocks);
 
 /* Splits and packs one operand; optionally accumulates per-row sum of squares and sum into

@@ -361,13 +361,38 @@ def gen_budget(ref):
     print("budget_golden:", {k: v["flops"] for k, v in out.items()})
 
 
+def gen_eval(ref):
+    """get_fc_perm / permute_final_features (pleas/methods/pleas_merging.py:408-465) on the tiny
+    pair with the activation-matching result stored in tiny_golden.pt -> eval_golden.pt."""
+    m1, _ = tinynet.make_pair(12, 10)
+    spec = ref.compiler.get_permutation_spec(m1, ((1, 3, 16, 16),))
+    T = torch.load(os.path.join(GOLD, "tiny_golden.pt"))
+    perm = {k: T["am/cdist/sum/perm"][axis_key(k)] for k in spec}
+    costs = {k: T["am/cdist/sum/costs"][axis_key(k)] for k in spec}
+    keys = list(spec.keys())
+    cases = {"r0": 0.0, "r05": 0.5, "r1": 1.0, "mixed": {k: [0.3, 0.0, 0.7, 1.0][i % 4] for i, k in enumerate(keys)}}
+    G = {}
+    gen = torch.Generator().manual_seed(77)
+    for name, ratios in cases.items():
+        fc_perm = ref.pl.get_fc_perm(perm, spec, costs, ratios)
+        n, m = len(fc_perm[0]), len(fc_perm[2])
+        feats = torch.randn(5, n + 2 * m, generator=gen)
+        G[f"{name}/ratios"] = ratios if not isinstance(ratios, dict) else {axis_key(k): v for k, v in ratios.items()}
+        G[f"{name}/fc_perm"] = [t.clone() for t in fc_perm]
+        G[f"{name}/features"] = feats
+        G[f"{name}/out0"] = ref.pl.permute_final_features(feats, fc_perm, 0).clone()
+        G[f"{name}/out1"] = ref.pl.permute_final_features(feats, fc_perm, 1).clone()
+    torch.save(G, os.path.join(GOLD, "eval_golden.pt"))
+    print("eval_golden.pt written:", {k: [len(t) for t in v] for k, v in G.items() if k.endswith("fc_perm")})
+
+
 def main():
     if os.environ.get("PYTHONHASHSEED") != "0":
         sys.exit("run with PYTHONHASHSEED=0 (pins the reference's set iteration order)")
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     ref = load_reference()
-    which = sys.argv[1:] or ["lap", "specs", "tiny", "rn18", "budget"]
+    which = sys.argv[1:] or ["lap", "specs", "tiny", "rn18", "budget", "eval"]
     if "lap" in which:
         gen_lap()
     if "specs" in which:
@@ -378,6 +403,8 @@ def main():
         gen_rn18(ref)
     if "budget" in which:
         gen_budget(ref)
+    if "eval" in which:
+        gen_eval(ref)
 
 
 if __name__ == "__main__":

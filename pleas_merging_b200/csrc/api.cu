@@ -25,7 +25,7 @@ extern "C" int64_t plb_plane_bytes(int64_t rows, int64_t K, int32_t *row_groups,
     plb::set_error("plb_plane_bytes: rows and K must be positive");
     return PLB_EINVAL;
   }
-  int64_t g = plb::ceil_div(rows, 128) * 16;
+  int64_t g = plb::ceil_div(rows, 8);
   int64_t kb = plb::ceil_div(K, plb::kPackK);
   if (row_groups) *row_groups = (int32_t)g;
   if (k_blocks) *k_blocks = (int32_t)kb;

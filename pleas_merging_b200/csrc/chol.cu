@@ -7,12 +7,14 @@
 // fp64 because normal equations square the condition number; the work (n^3/3 + 2 n^2 nrhs,
 // n <= 4608) is a few ms per layer on B200's fp64 pipe and is L2/HBM-bound at this blocking
 // (panel width 32, 64x64 trailing tiles), so plain SIMT DFMA is the right tool — no tensor
-// cores here.
+// cores here.  Two-level blocking (inner steps of 32 inside outer panels of 128) keeps the
+// trailing matrix's read-modify-write traffic and the launch count down.
 #include "common.cuh"
 
 namespace plb {
 
-constexpr int NB = 32;
+constexpr int NB = 32;   // inner step: diagonal blocks live in shared memory / registers
+constexpr int OB = 128;  // outer panel: one trailing update per OB columns
 
 __global__ void add_ridge_kernel(double *G, int64_t n, double ridge) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -72,40 +74,49 @@ __global__ void __launch_bounds__(128) trsm_panel_kernel(double *G, int64_t n, i
     if (c < nb) row[c] = x[c];
 }
 
-// generic 64x64-tile rank-nb update  C[i, j] -= sum_c A(i, c) * B(c, j)
+// generic 64x64-tile rank-kdim update  C[i, j] -= sum_c A(i, c) * B(c, j),  c < kdim
 //   A(i, c) = A[i * ars + c * acs],  B(c, j) = B[c * brs + j * bcs],  C row-major ldc
-// lower_only skips tiles strictly above the diagonal (trailing SYRK update).
+// kdim is consumed in chunks of NB staged through shared memory (global loads walk the unit-stride
+// index of each operand fastest, so both the panel and its transpose are read coalesced); C is
+// read and written once per launch.  lower_only skips tiles strictly above the diagonal
+// (trailing SYRK update).
 __global__ void __launch_bounds__(256) rank_update_kernel(double *__restrict__ C, int64_t ldc, int64_t M, int64_t N,
                                                           const double *__restrict__ A, int64_t ars, int64_t acs,
                                                           const double *__restrict__ B, int64_t brs, int64_t bcs,
-                                                          int nb, int lower_only) {
+                                                          int kdim, int lower_only) {
   if (lower_only && blockIdx.x > blockIdx.y) return;
   __shared__ double sa[64][NB + 1];
   __shared__ double sb[NB][64 + 1];
   const int64_t i0 = (int64_t)blockIdx.y * 64, j0 = (int64_t)blockIdx.x * 64;
   const int tid = threadIdx.x;
-  for (int e = tid; e < 64 * NB; e += 256) {
-    const int r = e / NB, c = e % NB;
-    sa[r][c] = (i0 + r < M && c < nb) ? A[(i0 + r) * ars + (int64_t)c * acs] : 0.0;
-  }
-  for (int e = tid; e < NB * 64; e += 256) {
-    const int c = e / 64, j = e % 64;
-    sb[c][j] = (j0 + j < N && c < nb) ? B[(int64_t)c * brs + (j0 + j) * bcs] : 0.0;
-  }
-  __syncthreads();
   const int tr = (tid / 16) * 4, tc = (tid % 16) * 4;
   double acc[4][4] = {};
+  for (int c0 = 0; c0 < kdim; c0 += NB) {
+    const int nb = min(NB, kdim - c0);
+    if (c0) __syncthreads();
+    for (int e = tid; e < 64 * NB; e += 256) {
+      int r, c;
+      if (acs == 1) { r = e / NB; c = e % NB; } else { c = e / 64; r = e % 64; }
+      sa[r][c] = (i0 + r < M && c < nb) ? A[(i0 + r) * ars + (int64_t)(c0 + c) * acs] : 0.0;
+    }
+    for (int e = tid; e < NB * 64; e += 256) {
+      int c, j;
+      if (brs == 1) { j = e / NB; c = e % NB; } else { c = e / 64; j = e % 64; }
+      sb[c][j] = (j0 + j < N && c < nb) ? B[(int64_t)(c0 + c) * brs + (j0 + j) * bcs] : 0.0;
+    }
+    __syncthreads();
 #pragma unroll 8
-  for (int c = 0; c < NB; ++c) {
-    double av[4], bv[4];
+    for (int c = 0; c < NB; ++c) {
+      double av[4], bv[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) av[r] = sa[tr + r][c];
+      for (int r = 0; r < 4; ++r) av[r] = sa[tr + r][c];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) bv[q] = sb[c][tc + q];
+      for (int q = 0; q < 4; ++q) bv[q] = sb[c][tc + q];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+      for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc[r][q] = fma(av[r], bv[q], acc[r][q]);
+        for (int q = 0; q < 4; ++q) acc[r][q] = fma(av[r], bv[q], acc[r][q]);
+    }
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r)
@@ -174,37 +185,57 @@ extern "C" int plb_chol_solve(double *G, int64_t n, double *B, int64_t nrhs, dou
     return (int)e;
   }
   if (ridge != 0.0) add_ridge_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, s>>>(G, n, ridge);
-  // ---- factor G = L L^T (lower, in place)
-  for (int64_t j0 = 0; j0 < n; j0 += NB) {
-    const int nb = (int)((n - j0 < NB) ? (n - j0) : NB);
-    potrf_diag_kernel<<<1, dim3(NB, NB), 0, s>>>(G, n, (int)j0, nb, info);
-    const int64_t m = n - j0 - nb;
-    if (m > 0) {
-      trsm_panel_kernel<<<(unsigned)ceil_div(m, 128), 128, 0, s>>>(G, n, (int)j0, nb);
-      double *panel = G + (j0 + nb) * n + j0;
-      const unsigned t = (unsigned)ceil_div(m, 64);
-      // trailing[i, k] -= sum_c panel[i, c] * panel[k, c]
-      rank_update_kernel<<<dim3(t, t), 256, 0, s>>>(G + (j0 + nb) * n + (j0 + nb), n, m, m, panel, n, 1, panel, 1, n,
-                                                    nb, 1);
+  auto update = [&](double *C, int64_t ldc, int64_t M, int64_t N, const double *A, int64_t ars, int64_t acs,
+                    const double *B, int64_t brs, int64_t bcs, int kdim, int lower_only) {
+    if (M > 0 && N > 0 && kdim > 0)
+      rank_update_kernel<<<dim3((unsigned)ceil_div(N, 64), (unsigned)ceil_div(M, 64)), 256, 0, s>>>(
+          C, ldc, M, N, A, ars, acs, B, brs, bcs, kdim, lower_only);
+  };
+  // Two-level blocking: NB-wide steps (diagonal factor / triangular solve in shared memory) only
+  // update the columns of their own OB-wide outer panel; the trailing matrix is updated once per outer
+  // panel with k = OB, which cuts its read-modify-write traffic and launch count by OB / NB.
+  // ---- factor G = L L^T (lower, in place; entries above the diagonal are scratch)
+  for (int64_t J0 = 0; J0 < n; J0 += OB) {
+    const int64_t W = (n - J0 < OB) ? (n - J0) : OB;
+    for (int64_t j0 = J0; j0 < J0 + W; j0 += NB) {
+      const int nb = (int)((J0 + W - j0 < NB) ? (J0 + W - j0) : NB);
+      potrf_diag_kernel<<<1, dim3(NB, NB), 0, s>>>(G, n, (int)j0, nb, info);
+      const int64_t m = n - j0 - nb;
+      if (m > 0) {
+        trsm_panel_kernel<<<(unsigned)ceil_div(m, 128), 128, 0, s>>>(G, n, (int)j0, nb);
+        // columns j0+nb .. J0+W of the rows below: G[i, k] -= sum_c panel[i, c] * panel[k, c]
+        double *panel = G + (j0 + nb) * n + j0;
+        update(G + (j0 + nb) * n + (j0 + nb), n, m, J0 + W - j0 - nb, panel, n, 1, panel, 1, n, nb, 0);
+      }
     }
+    const int64_t m = n - J0 - W;
+    double *panel = G + (J0 + W) * n + J0;
+    update(G + (J0 + W) * n + (J0 + W), n, m, m, panel, n, 1, panel, 1, n, (int)W, 1);
   }
   if (nrhs > 0) {
     // ---- forward: L Z = B
-    for (int64_t j0 = 0; j0 < n; j0 += NB) {
-      const int nb = (int)((n - j0 < NB) ? (n - j0) : NB);
-      trsv_block_kernel<<<(unsigned)ceil_div(nrhs, 128), 128, 0, s>>>(G, n, (int)j0, nb, B, nrhs, 0);
-      const int64_t m = n - j0 - nb;
-      if (m > 0)
-        rank_update_kernel<<<dim3((unsigned)ceil_div(nrhs, 64), (unsigned)ceil_div(m, 64)), 256, 0, s>>>(
-            B + (j0 + nb) * nrhs, nrhs, m, nrhs, G + (j0 + nb) * n + j0, n, 1, B + j0 * nrhs, nrhs, 1, nb, 0);
+    for (int64_t J0 = 0; J0 < n; J0 += OB) {
+      const int64_t W = (n - J0 < OB) ? (n - J0) : OB;
+      for (int64_t j0 = J0; j0 < J0 + W; j0 += NB) {
+        const int nb = (int)((J0 + W - j0 < NB) ? (J0 + W - j0) : NB);
+        trsv_block_kernel<<<(unsigned)ceil_div(nrhs, 128), 128, 0, s>>>(G, n, (int)j0, nb, B, nrhs, 0);
+        update(B + (j0 + nb) * nrhs, nrhs, J0 + W - j0 - nb, nrhs, G + (j0 + nb) * n + j0, n, 1, B + j0 * nrhs, nrhs, 1,
+               nb, 0);
+      }
+      update(B + (J0 + W) * nrhs, nrhs, n - J0 - W, nrhs, G + (J0 + W) * n + J0, n, 1, B + J0 * nrhs, nrhs, 1, (int)W,
+             0);
     }
     // ---- backward: L^T X = Z
-    for (int64_t j0 = ((n - 1) / NB) * NB; j0 >= 0; j0 -= NB) {
-      const int nb = (int)((n - j0 < NB) ? (n - j0) : NB);
-      trsv_block_kernel<<<(unsigned)ceil_div(nrhs, 128), 128, 0, s>>>(G, n, (int)j0, nb, B, nrhs, 1);
-      if (j0 > 0)  // rows above: B[i, :] -= sum_c L[j0 + c, i] * X[j0 + c, :]
-        rank_update_kernel<<<dim3((unsigned)ceil_div(nrhs, 64), (unsigned)ceil_div(j0, 64)), 256, 0, s>>>(
-            B, nrhs, j0, nrhs, G + j0 * n, 1, n, B + j0 * nrhs, nrhs, 1, nb, 0);
+    for (int64_t J0 = ((n - 1) / OB) * OB; J0 >= 0; J0 -= OB) {
+      const int64_t W = (n - J0 < OB) ? (n - J0) : OB;
+      for (int64_t j0 = J0 + ((W - 1) / NB) * NB; j0 >= J0; j0 -= NB) {
+        const int nb = (int)((J0 + W - j0 < NB) ? (J0 + W - j0) : NB);
+        trsv_block_kernel<<<(unsigned)ceil_div(nrhs, 128), 128, 0, s>>>(G, n, (int)j0, nb, B, nrhs, 1);
+        // rows J0 .. j0 of this outer block: B[i, :] -= sum_c L[j0 + c, i] * X[j0 + c, :]
+        update(B + J0 * nrhs, nrhs, j0 - J0, nrhs, G + j0 * n + J0, 1, n, B + j0 * nrhs, nrhs, 1, nb, 0);
+      }
+      // rows above the outer block
+      update(B, nrhs, J0, nrhs, G + J0 * n, 1, n, B + J0 * nrhs, nrhs, 1, (int)W, 0);
     }
   }
   return launch_status("plb_chol_solve");

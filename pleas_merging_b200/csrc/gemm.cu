@@ -113,16 +113,17 @@ __global__ void __launch_bounds__(192, 2) gemm3xtf32_kernel(const PlbGemmProblem
       const int g0b = w.n_tile * (BN / 8);
       const int gcb = min(BN / 8, gb - g0b);
       const uint32_t b_bytes = (uint32_t)gcb * kPanelFloats * 4;
+      const uint32_t a_bytes = (uint32_t)min(16, ga - g0a) * kPanelFloats * 4;
       for (int i = 0; i < w.nkb; ++i) {
         const int s = i % Cfg::kStages;
         const uint32_t phase = (uint32_t)(i / Cfg::kStages) & 1u;
         mbar_wait(&bar_empty[s], phase ^ 1u);
         uint8_t *st = smem + (size_t)s * Cfg::kStageBytes;
-        mbar_arrive_expect_tx(&bar_full[s], 2u * Cfg::kATileBytes + 2u * b_bytes);
+        mbar_arrive_expect_tx(&bar_full[s], 2u * a_bytes + 2u * b_bytes);
         const int64_t kb = w.kb0 + i;
         const int64_t oa = panel_offset(kb, g0a, ga), ob = panel_offset(kb, g0b, gb);
-        bulk_g2s(st, p->a_hi + oa, Cfg::kATileBytes, &bar_full[s]);
-        bulk_g2s(st + Cfg::kATileBytes, p->a_lo + oa, Cfg::kATileBytes, &bar_full[s]);
+        bulk_g2s(st, p->a_hi + oa, a_bytes, &bar_full[s]);
+        bulk_g2s(st + Cfg::kATileBytes, p->a_lo + oa, a_bytes, &bar_full[s]);
         bulk_g2s(st + 2 * Cfg::kATileBytes, p->b_hi + ob, b_bytes, &bar_full[s]);
         bulk_g2s(st + 2 * Cfg::kATileBytes + Cfg::kBTileBytes, p->b_lo + ob, b_bytes, &bar_full[s]);
       }
@@ -250,15 +251,19 @@ __global__ void __launch_bounds__(320, 1) gemm3xtf32_v2_kernel(const PlbGemmProb
         const int ga = p->a_row_groups, gb = p->b_row_groups;
         const int g0a = w.m_tile * 16, g0b = w.n_tile * (BN / 8);
         const uint32_t b_bytes = (uint32_t)min(BN / 8, gb - g0b) * kPanelFloats * 4;
+        // only the row groups the operand has: rows past them keep stale shared memory and feed
+        // output rows nobody reads (a fixed 16-group copy would re-read the next k-block's panel
+        // from DRAM: +50 % traffic on the HBM-bound C=64 taps, ncu profiles/gemm_c64_r01_raw.csv)
+        const uint32_t a_bytes = (uint32_t)min(16, ga - g0a) * kPanelFloats * 4;
         for (int i = 0; i < w.nkb; ++i, ++it) {
           const int s = it % Cfg::kStages;
           mbar_wait(&bar_empty[s], ((it / Cfg::kStages) & 1u) ^ 1u);
           uint8_t *st = smem + (size_t)s * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&bar_full[s], 2u * Cfg::kATileBytes + 2u * b_bytes);
+          mbar_arrive_expect_tx(&bar_full[s], 2u * a_bytes + 2u * b_bytes);
           const int64_t kb = w.kb0 + i;
           const int64_t oa = panel_offset(kb, g0a, ga), ob = panel_offset(kb, g0b, gb);
-          bulk_g2s(st, p->a_hi + oa, Cfg::kATileBytes, &bar_full[s]);
-          bulk_g2s(st + Cfg::kATileBytes, p->a_lo + oa, Cfg::kATileBytes, &bar_full[s]);
+          bulk_g2s(st, p->a_hi + oa, a_bytes, &bar_full[s]);
+          bulk_g2s(st + Cfg::kATileBytes, p->a_lo + oa, a_bytes, &bar_full[s]);
           bulk_g2s(st + 2 * Cfg::kATileBytes, p->b_hi + ob, b_bytes, &bar_full[s]);
           bulk_g2s(st + 2 * Cfg::kATileBytes + Cfg::kBTileBytes, p->b_lo + ob, b_bytes, &bar_full[s]);
         }
@@ -361,8 +366,12 @@ __global__ void __launch_bounds__(256) gemm_simt_ref_kernel(const PlbGemmProblem
     const int64_t kb = w.kb0 + i;
     for (int idx = tid; idx < 128 * kPackK; idx += 256) {
       int r = idx & 127, k = idx >> 7;
-      int64_t off = panel_offset(kb, g0a + (r >> 3), p->a_row_groups) + ((k >> 2) * 8 + (r & 7)) * 4 + (k & 3);
-      sa[k][r] = p->a_hi[off] + p->a_lo[off];
+      float v = 0.f;
+      if (g0a + (r >> 3) < p->a_row_groups) {
+        int64_t off = panel_offset(kb, g0a + (r >> 3), p->a_row_groups) + ((k >> 2) * 8 + (r & 7)) * 4 + (k & 3);
+        v = p->a_hi[off] + p->a_lo[off];
+      }
+      sa[k][r] = v;
     }
     for (int idx = tid; idx < BN * kPackK; idx += 256) {
       int r = idx % BN, k = idx / BN;

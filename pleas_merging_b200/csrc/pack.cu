@@ -183,8 +183,8 @@ extern "C" int plb_pack_split(const float *x, int64_t outer, int64_t src_rows, i
   PLB_REQUIRE(row_index != nullptr || rows <= src_rows, PLB_EINVAL, "plb_pack_split: rows > src_rows without index");
   const int64_t K = outer * inner;
   PLB_REQUIRE(K < (int64_t)1 << 31 && inner < (int64_t)1 << 31, PLB_ESIZE, "plb_pack_split: K too large");
-  PLB_REQUIRE(row_groups % 16 == 0 && (int64_t)row_groups * 8 >= rows, PLB_EINVAL,
-              "plb_pack_split: row_groups must be a multiple of 16 covering rows");
+  PLB_REQUIRE(row_groups > 0 && (int64_t)row_groups * 8 >= rows, PLB_EINVAL,
+              "plb_pack_split: row_groups must cover rows");
   PLB_REQUIRE(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0, PLB_EALIGN, "plb_pack_split: planes unaligned");
   const int k_blocks = (int)ceil_div(K, kPackK);
   dim3 grid((unsigned)ceil_div(k_blocks, kKbPerBlock), (unsigned)ceil_div(rows, 8));
@@ -214,8 +214,8 @@ extern "C" int plb_pack_im2col(const float *x1, const float *x2, int64_t N, int6
   const int64_t rows = cmerged * kh * kw + (ones_row ? 1 : 0);
   const int64_t K = N * Ho * Wo;
   PLB_REQUIRE(K < (int64_t)1 << 31, PLB_ESIZE, "plb_pack_im2col: K too large");
-  PLB_REQUIRE(row_groups % 16 == 0 && (int64_t)row_groups * 8 >= rows, PLB_EINVAL,
-              "plb_pack_im2col: row_groups must be a multiple of 16 covering rows");
+  PLB_REQUIRE(row_groups > 0 && (int64_t)row_groups * 8 >= rows, PLB_EINVAL,
+              "plb_pack_im2col: row_groups must cover rows");
   Im2colGeom gm{N, cin_src, H, W, Ho, Wo, cmerged, kh, kw, stride_h, stride_w, pad_h, pad_w, dil_h, dil_w, ones_row};
   const int k_blocks = (int)ceil_div(K, kPackK);
   dim3 grid((unsigned)ceil_div(k_blocks, kKbPerBlock), (unsigned)ceil_div(rows, 8));

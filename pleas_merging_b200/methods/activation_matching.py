@@ -297,7 +297,7 @@ class CrossAccumulator:
 
     def _bind(self, st):
         """(Re)creates the tap's GEMM problem entry against the current arena."""
-        rga, rgb = 16 * ((st.ra + 127) // 128), 16 * ((st.rb + 127) // 128)
+        rga, rgb = ops.row_groups_of(st.ra), ops.row_groups_of(st.rb)
         bn = ops.choose_bn(st.rb)
         m_tiles, n_tiles = (st.ra + 127) // 128, (st.rb + bn - 1) // bn
         splits = ops.choose_splits(m_tiles * n_tiles, st.kb, 128, bn)

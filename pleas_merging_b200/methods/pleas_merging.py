@@ -215,7 +215,7 @@ class _LayerLS:
     def requirements(self, L):
         """(U-plane floats, Y-plane floats, partial floats) for a batch with L output positions."""
         kb = (L + 15) // 16
-        rgu, rgy = 16 * ((self.K + 127) // 128), 16 * ((self.cout + 127) // 128)
+        rgu, rgy = ops.row_groups_of(self.K), ops.row_groups_of(self.cout)
         need = 0
         for n_cols, sym in ((self.K, True), (self.cout, False)):
             bn, m_tiles, n_tiles, splits = self._geometry(n_cols, sym, kb)
@@ -226,7 +226,7 @@ class _LayerLS:
         from .activation_matching import _View
 
         kb = (L + 15) // 16
-        rgu, rgy = 16 * ((self.K + 127) // 128), 16 * ((self.cout + 127) // 128)
+        rgu, rgy = ops.row_groups_of(self.K), ops.row_groups_of(self.cout)
         pu = _View(ws.buf["u_hi"], ws.buf["u_lo"], self.K, rgu, kb)
         py = _View(ws.buf["y_hi"], ws.buf["y_lo"], self.cout, rgy, kb)
         plan_g = ops.GemmPlan(pu, pu, self.K, self.K, kb, symmetric=True, partial=ws.buf["partial"],
@@ -272,6 +272,39 @@ class _LayerLS:
             mask = torch.cat([mask, torch.ones(wshape[0], 1)], 1)
         return mask > 0
 
+    def mask_classes(self, wshape):
+        """The distinct rows of ``mask2d`` without materialising it: (patterns [P, K] bool, class id
+        per output row [Co]).  The reference's mask (:52-59, index order kept) zeroes two
+        row ranges against two ranges of dim 1, so there are at most three kinds of rows."""
+        ni, mi, no, mo = len(self.bi[0]), len(self.bi[2]), len(self.bo[0]), len(self.bo[2])
+        co = wshape[0]
+        row_class = torch.zeros(co, dtype=torch.int64)
+        if len(wshape) >= 2:
+            for cls, (lo, hi) in enumerate(((ni, ni + mi), (ni + mi, ni + 2 * mi)), start=1):
+                lo, hi = min(lo, co), min(hi, co)
+                if hi > lo:
+                    row_class[lo:hi] = cls
+        pats, remap = [], {}
+        per = 1
+        for d in wshape[2:]:
+            per *= d
+        for cls in sorted(set(row_class.tolist())):
+            m = torch.ones(wshape[1] if len(wshape) >= 2 else 1, per)
+            if cls == 1:
+                m[no + mo:no + 2 * mo] = 0.0
+            elif cls == 2:
+                m[no:no + mo] = 0.0
+            m = m.reshape(-1)
+            if self.has_bias:
+                m = torch.cat([m, torch.ones(1)])
+            m = m > 0
+            same = [i for i, q in enumerate(pats) if torch.equal(q, m)]
+            remap[cls] = same[0] if same else len(pats)
+            if not same:
+                pats.append(m)
+        inverse = torch.tensor([remap[c] for c in row_class.tolist()], dtype=torch.int64)
+        return torch.stack(pats), inverse
+
     def solve(self, layer, ridge_rel):
         """Returns the fitted flattened weight [Co, K] (fp64, CUDA) and the init it started from."""
         dev = self.G.device
@@ -285,9 +318,8 @@ class _LayerLS:
         assert W0.shape == (self.cout, self.K), f"{self.name}: merged layer shape {tuple(W0.shape)} != {(self.cout, self.K)}"
         grad = self.R - self.G @ W0.T  # [K, Co] residual of the normal equations at the init
         ridge = ridge_rel * float(self.G.diagonal().mean())
-        mask = self.mask2d(tuple(layer.weight.shape))
         W = W0.clone()
-        patterns, inverse = torch.unique(mask, dim=0, return_inverse=True)
+        patterns, inverse = self.mask_classes(tuple(layer.weight.shape))
         for pi in range(patterns.shape[0]):
             free = patterns[pi].to(dev)
             rows = (inverse == pi).nonzero().flatten().to(dev)

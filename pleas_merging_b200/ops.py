@@ -38,9 +38,15 @@ def _require_cuda_f32(t, what):
                         f"{type(t).__name__} {getattr(t, 'dtype', None)} on {getattr(t, 'device', None)}")
 
 
+def row_groups_of(rows):
+    """8-row groups of a packed operand.  Tight (no padding to the 128-row MMA tile): the GEMM
+    producer copies only the groups that exist, so narrow operands (C = 64) cost their own bytes."""
+    return (rows + 7) // 8
+
+
 def plane_geometry(rows, K):
     """(row_groups, k_blocks, floats per plane) of the packed layout."""
-    rg = 16 * ((rows + 127) // 128)
+    rg = row_groups_of(rows)
     kb = (K + 15) // 16
     return rg, kb, rg * kb * 128
 
@@ -117,7 +123,7 @@ class Planes:
 
     def __init__(self, rows, k_blocks, device, pool=None):
         self.rows = rows
-        self.row_groups = 16 * ((rows + 127) // 128)
+        self.row_groups = row_groups_of(rows)
         self.k_blocks = k_blocks
         n = self.row_groups * k_blocks * 128
         # no zero-fill needed: pad row groups only feed output rows/cols nobody reads, and the

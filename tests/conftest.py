@@ -55,6 +55,13 @@ def rn18_golden():
 
 
 @pytest.fixture(scope="session")
+def eval_golden():
+    import torch
+
+    return torch.load(os.path.join(GOLDEN, "eval_golden.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="session")
 def lap_golden():
     import numpy as np
 

@@ -31,8 +31,8 @@ def test_cabi_library_exports_every_declared_symbol():
     lib.plb_plane_bytes.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_int32),
                                     ctypes.POINTER(ctypes.c_int32)]
     rg, kb = ctypes.c_int32(), ctypes.c_int32()
-    assert lib.plb_plane_bytes(200, 1000, ctypes.byref(rg), ctypes.byref(kb)) == 32 * 63 * 512
-    assert (rg.value, kb.value) == (32, 63)
+    assert lib.plb_plane_bytes(200, 1000, ctypes.byref(rg), ctypes.byref(kb)) == 25 * 63 * 512
+    assert (rg.value, kb.value) == (25, 63)  # ceil(200/8) row groups, ceil(1000/16) k-blocks, 512-B panels
     assert lib.plb_plane_bytes(0, 5, None, None) < 0  # invalid argument, no crash
 
 
@@ -278,3 +278,35 @@ def test_zip_ratios_rule():
         assert v == want, k
     r2 = get_zip_ratios(spec, 2.0, base)
     assert all((v == 1.0) == k.key.startswith("layer") for k, v in r2.items())
+
+
+def test_mask_classes_equal_unique_rows_of_the_reference_mask():
+    """_LayerLS.mask_classes (analytic row classes) == torch.unique over the materialised gradient
+    mask (reference index order, pleas_merging.py:52-59) for merged / partially merged layers."""
+    import importlib
+
+    PM = importlib.import_module("pleas_merging_b200.methods.pleas_merging")
+    e = lambda n: torch.zeros(n, dtype=torch.int64)
+    cases = [((12, 8, 3, 3), (8, 0), (12, 0), False), ((14, 10, 3, 3), (6, 2), (8, 3), False),
+             ((10, 9), (5, 2), (6, 2), True), ((9, 20, 1, 1), (8, 6), (5, 2), True),
+             ((16, 12, 1, 1), (6, 3), (16, 0), False), ((7, 3, 7, 7), (3, 0), (5, 1), False)]
+    for wshape, (ni, mi), (no, mo), bias in cases:
+        a = object.__new__(PM._LayerLS)
+        a.bi, a.bo, a.has_bias = (e(ni), e(ni), e(mi), e(mi)), (e(no), e(no), e(mo), e(mo)), bias
+        mask = a.mask2d(wshape)
+        pats, inv = a.mask_classes(wshape)
+        assert pats.shape[1] == mask.shape[1] and inv.shape[0] == mask.shape[0]
+        assert torch.equal(pats[inv], mask), (wshape, ni, mi, no, mo)
+        assert pats.shape[0] == torch.unique(mask, dim=0).shape[0]
+
+
+@pytest.mark.parametrize("name", ["r0", "r05", "r1", "mixed"])
+def test_permute_final_features_equals_reference(eval_golden, name):
+    """permute_final_features is device-agnostic: on the reference's own fc blocks and features it
+    returns the reference's tensors bit for bit (pleas_merging.py:436-465)."""
+    from pleas_merging_b200.methods.evaluation import permute_final_features
+
+    fc_perm, feats = eval_golden[f"{name}/fc_perm"], eval_golden[f"{name}/features"]
+    for idx in (0, 1):
+        out = permute_final_features(feats, fc_perm, idx)
+        assert torch.equal(out, eval_golden[f"{name}/out{idx}"])

@@ -257,7 +257,8 @@ def test_gather_compose_progress():
     assert gain.item() == pytest.approx(float(A.double()[torch.arange(50), col].sum() - A.double().diag().sum()))
 
 
-@pytest.mark.parametrize("n,nrhs", [(1, 1), (5, 3), (33, 7), (100, 130), (300, 64), (1000, 257)])
+@pytest.mark.parametrize("n,nrhs", [(1, 1), (5, 3), (33, 7), (100, 130), (128, 1), (129, 33), (257, 2), (300, 64),
+                                    (1000, 257)])
 def test_chol_solve_vs_numpy(n, nrhs):
     ops = _ops()
     rng = np.random.default_rng(n)

@@ -483,3 +483,52 @@ def test_full_size_properties_rn50():
         scale = float(total.abs().max())
         assert float((c_all[k] - total).abs().max()) <= 2e-6 * scale, k
         assert float((c_ref[k] - parts[2][k]).abs().max()) <= 2e-6 * float(parts[2][k].abs().max()), k
+
+
+@pytest.mark.parametrize("name", ["r0", "r05", "r1", "mixed"])
+def test_get_fc_perm_equals_reference(tiny_golden, eval_golden, name):
+    """the classifier group's blocks (pleas_merging.py:408-433) equal the reference's."""
+    P = _pkg()
+    from pleas_merging_b200.methods.evaluation import get_fc_perm, permute_final_features
+
+    _, _, spec = _tiny(P)
+    perm = {k: tiny_golden["am/cdist/sum/perm"][key_str(k)] for k in spec}
+    costs = {k: tiny_golden["am/cdist/sum/costs"][key_str(k)].cuda() for k in spec}
+    r = eval_golden[f"{name}/ratios"]
+    ratios = {k: r[key_str(k)] for k in spec} if isinstance(r, dict) else r
+    fc_perm = get_fc_perm(perm, spec, costs, ratios)
+    for mine, gold in zip(fc_perm, eval_golden[f"{name}/fc_perm"]):
+        assert torch.equal(mine.cpu(), gold)
+    feats = eval_golden[f"{name}/features"].cuda()
+    for idx in (0, 1):
+        assert torch.equal(permute_final_features(feats, fc_perm, idx).cpu(), eval_golden[f"{name}/out{idx}"])
+
+
+@pytest.mark.parametrize("ratio", [0.0, 0.5])
+def test_eval_perm_model_recovers_source_predictions(ratio):
+    """Merging a network with a hidden-unit-permuted copy of itself is lossless, so the merged
+    backbone (fc removed) + either source classifier must score exactly what that source model
+    scores on its own labels — checks get_fc_perm / permute_final_features / eval_perm_model /
+    eval_whole_model end to end (pleas_merging.py:408-496, 574-585)."""
+    P = _pkg()
+    from pleas_merging_b200.methods import evaluation as E
+
+    m1, _ = tinynet.make_pair(12, 10)
+    spec = P.get_permutation_spec(m1, ((1, 3, 16, 16),))
+    planted = P.make_random_perm(spec, torch.Generator().manual_seed(3))
+    m2 = copy.deepcopy(m1)
+    m2.load_state_dict(P.apply_perm(planted, spec, m1.state_dict()))
+    m1, m2 = m1.cuda(), m2.cuda()
+    loader = tinynet.make_loader(3, 8, 16)
+    perm, costs = P.activation_matching(spec, m1, m2, loader, 3, output_costs=True, accumulate="sum")
+    model3 = P.partial_merge(spec, m1, m2, perm, costs, ratio).cuda()
+    fc_perm = E.get_fc_perm(perm, spec, costs, ratio)
+    # labels = model 1's own predictions -> accuracy of model 1 is 1.0 by construction
+    with torch.no_grad():
+        data = [(x, m1(x.cuda()).argmax(1).cpu()) for x, _ in tinynet.make_loader(4, 8, 16, seed=9)]
+    assert float(E.eval_whole_model(m1, data, 10)) == 1.0
+    backbone = copy.deepcopy(model3)
+    backbone.fc = torch.nn.Identity()
+    for idx, src in enumerate((m1, m2)):
+        acc = E.eval_perm_model(backbone, src.fc, data, 10, fc_perm, idx)
+        assert float(acc) == 1.0, (ratio, idx, float(acc))
