@@ -21,37 +21,63 @@ __global__ void add_ridge_kernel(double *G, int64_t n, double ridge) {
   if (i < n) G[i * n + i] += ridge;
 }
 
-// factor the nb x nb diagonal block at j0 (lower) in shared memory
+// Factor the nb x nb diagonal block at j0 (lower, in place) and store the strictly-lower part of
+// inv(L_jj) transposed into the block's strictly-upper triangle (scratch space nobody reads; the
+// inverse's diagonal is 1 / L_ii).  The panel and right-hand-side solves then become small
+// matrix products without dependent chains or divisions.
+// 32 x 32 threads, thread (i, j) owns entry [i][j]; one barrier per step:
+//   factor:  step k applies the rank-1 update a[i][j] -= a[i][k] a[j][k] / a[k][k] to the trailing
+//            entries directly from the UNSCALED column k, and stores L[i][k] = a[i][k] / sqrt(a[k][k])
+//            on the side (column k is never touched again);
+//   inverse: step k finalises row k of X = inv(L) (X[k][j] = (I - S)[k][j] / L[k][k]) and pushes
+//            it into the running sums S[i][j] += L[i][k] X[k][j] of the rows below.
 __global__ void __launch_bounds__(1024) potrf_diag_kernel(double *G, int64_t n, int j0, int nb, int32_t *info) {
   __shared__ double a[NB][NB + 1];
-  const int tx = threadIdx.x, ty = threadIdx.y;  // a[tx][ty]: row tx, col ty
-  if (tx < nb && ty < nb) a[tx][ty] = (ty <= tx) ? G[(int64_t)(j0 + tx) * n + j0 + ty] : 0.0;
+  __shared__ double l[NB][NB + 1];
+  __shared__ double x[NB][NB + 1];
+  const int i = threadIdx.y, j = threadIdx.x;
+  a[i][j] = (i < nb && j <= i) ? G[(int64_t)(j0 + i) * n + j0 + j] : (i == j ? 1.0 : 0.0);  // identity padding
+  l[i][j] = 0.0;
   __syncthreads();
-  for (int k = 0; k < nb; ++k) {
-    if (tx == k && ty == k) {
-      double piv = a[k][k];
-      if (!(piv > 0.0)) {
-        atomicCAS(info, 0, j0 + k + 1);
-        piv = 1.0;
-      }
-      a[k][k] = sqrt(piv);
+  for (int k = 0; k < NB; ++k) {
+    double piv = a[k][k];
+    if (!(piv > 0.0)) {
+      if (i == 0 && j == 0 && k < nb) atomicCAS(info, 0, j0 + k + 1);
+      piv = 1.0;
     }
-    __syncthreads();
-    if (ty == k && tx > k && tx < nb) a[tx][k] /= a[k][k];
-    __syncthreads();
-    if (tx > k && ty > k && ty <= tx && tx < nb) a[tx][ty] -= a[tx][k] * a[ty][k];
+    const double aik = a[i][k], ajk = a[j][k];
+    if (j == k && i >= k) l[i][k] = aik / sqrt(piv);
+    if (i > k && j > k && j <= i) a[i][j] -= aik * ajk / piv;  // never touches column k: no barrier before
     __syncthreads();
   }
-  if (tx < nb && ty <= tx) G[(int64_t)(j0 + tx) * n + j0 + ty] = a[tx][ty];
+  double s = 0.0;  // S[i][j]
+  for (int k = 0; k < NB; ++k) {
+    if (i == k) x[k][j] = (j <= k) ? (((j == k) ? 1.0 : 0.0) - s) / l[k][k] : 0.0;
+    __syncthreads();
+    if (i > k) s = fma(l[i][k], x[k][j], s);
+  }
+  __syncthreads();
+  if (i < nb && j < nb) G[(int64_t)(j0 + i) * n + j0 + j] = (j <= i) ? l[i][j] : x[j][i];  // upper: inv(L)^T
 }
 
-// rows below the diagonal block: A[i, j0:j0+nb] <- A[i, j0:j0+nb] * L_jj^{-T}
-__global__ void __launch_bounds__(128) trsm_panel_kernel(double *G, int64_t n, int j0, int nb) {
-  __shared__ double l[NB][NB + 1];
-  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
-    const int r = e / nb, c = e % nb;
-    l[r][c] = G[(int64_t)(j0 + r) * n + j0 + c];
+// loads inv(L_jj) (lower triangular incl. diagonal) from the layout potrf_diag_kernel left behind
+__device__ __forceinline__ void load_inverse_block(double (*li)[NB + 1], const double *G, int64_t n, int j0, int nb) {
+  for (int e = threadIdx.x; e < NB * NB; e += blockDim.x) {
+    const int r = e / NB, c = e % NB;
+    double v = 0.0;
+    if (r < nb && c < nb) {
+      if (c < r) v = G[(int64_t)(j0 + c) * n + j0 + r];
+      else if (c == r) v = 1.0 / G[(int64_t)(j0 + r) * n + j0 + r];
+    }
+    li[r][c] = v;
   }
+}
+
+// rows below the diagonal block: A[i, j0:j0+nb] <- A[i, j0:j0+nb] * inv(L_jj)^T
+// (thread = one row; out[c] = sum_{k <= c} x[k] * inv[c][k]: independent dot products)
+__global__ void __launch_bounds__(128) trsm_panel_kernel(double *G, int64_t n, int j0, int nb) {
+  __shared__ double li[NB][NB + 1];
+  load_inverse_block(li, G, n, j0, nb);
   __syncthreads();
   const int64_t i = (int64_t)j0 + nb + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -61,17 +87,14 @@ __global__ void __launch_bounds__(128) trsm_panel_kernel(double *G, int64_t n, i
   for (int c = 0; c < NB; ++c) x[c] = (c < nb) ? row[c] : 0.0;
 #pragma unroll
   for (int c = 0; c < NB; ++c) {
-    if (c < nb) {
-      double s = x[c];
+    double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-      for (int k = 0; k < NB; ++k)
-        if (k < c) s -= x[k] * l[c][k];
-      x[c] = s / l[c][c];
+    for (int k = 0; k < NB; k += 2) {
+      if (k <= c) s0 = fma(x[k], li[c][k], s0);
+      if (k + 1 <= c) s1 = fma(x[k + 1], li[c][k + 1], s1);
     }
+    if (c < nb) row[c] = s0 + s1;
   }
-#pragma unroll
-  for (int c = 0; c < NB; ++c)
-    if (c < nb) row[c] = x[c];
 }
 
 // generic 64x64-tile rank-kdim update  C[i, j] -= sum_c A(i, c) * B(c, j),  c < kdim
@@ -89,7 +112,11 @@ __global__ void __launch_bounds__(256) rank_update_kernel(double *__restrict__ C
   __shared__ double sb[NB][64 + 1];
   const int64_t i0 = (int64_t)blockIdx.y * 64, j0 = (int64_t)blockIdx.x * 64;
   const int tid = threadIdx.x;
-  const int tr = (tid / 16) * 4, tc = (tid % 16) * 4;
+  // thread micro-tile: rows tr..tr+3, columns tx + 16 q — the 16 lanes of a half-warp read 16
+  // consecutive doubles of sb (conflict-free) and both half-warps share them; sa reads broadcast
+  // (measured: 12.7 -> 9.6 ms of updates in a K = 4608 solve; a 128x64 / 8x4 register-prefetch
+  // variant was slower — fewer resident warps to hide the fp64 latency)
+  const int tr = (tid / 16) * 4, tx = tid % 16;
   double acc[4][4] = {};
   for (int c0 = 0; c0 < kdim; c0 += NB) {
     const int nb = min(NB, kdim - c0);
@@ -111,7 +138,7 @@ __global__ void __launch_bounds__(256) rank_update_kernel(double *__restrict__ C
 #pragma unroll
       for (int r = 0; r < 4; ++r) av[r] = sa[tr + r][c];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) bv[q] = sb[c][tc + q];
+      for (int q = 0; q < 4; ++q) bv[q] = sb[c][tx + 16 * q];
 #pragma unroll
       for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -122,52 +149,42 @@ __global__ void __launch_bounds__(256) rank_update_kernel(double *__restrict__ C
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const int64_t i = i0 + tr + r, j = j0 + tc + q;
+      const int64_t i = i0 + tr + r, j = j0 + tx + 16 * q;
       if (i < M && j < N) C[i * ldc + j] -= acc[r][q];
     }
 }
 
-// diagonal-block triangular solve on the right-hand sides: one thread per rhs column
-__global__ void __launch_bounds__(128) trsv_block_kernel(const double *__restrict__ G, int64_t n, int j0, int nb,
+// diagonal-block triangular solve on the right-hand sides as a product with the stored inverse:
+//   forward  X = inv(L_jj) B_blk,   backward  X = inv(L_jj)^T B_blk.
+// block = 32 rhs columns x 8 row-quads: thread (tx, ty) produces rows 4 ty .. 4 ty + 3 of column tx
+__global__ void __launch_bounds__(256) trsv_block_kernel(const double *__restrict__ G, int64_t n, int j0, int nb,
                                                          double *__restrict__ B, int64_t nrhs, int transposed) {
-  __shared__ double l[NB][NB + 1];
-  for (int e = threadIdx.x; e < nb * nb; e += blockDim.x) {
-    const int r = e / nb, c = e % nb;
-    l[r][c] = G[(int64_t)(j0 + r) * n + j0 + c];
+  __shared__ double li[NB][NB + 1];
+  __shared__ double xb[NB][32 + 1];
+  load_inverse_block(li, G, n, j0, nb);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t j = (int64_t)blockIdx.x * 32 + tx;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int r = ty * 4 + q;
+    xb[r][tx] = (r < nb && j < nrhs) ? B[(int64_t)(j0 + r) * nrhs + j] : 0.0;
   }
   __syncthreads();
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nrhs) return;
-  double x[NB];
+  double out[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 8
+  for (int k = 0; k < NB; ++k) {
+    const double xv = xb[k][tx];
 #pragma unroll
-  for (int r = 0; r < NB; ++r) x[r] = (r < nb) ? B[(int64_t)(j0 + r) * nrhs + j] : 0.0;
-  if (!transposed) {
-#pragma unroll
-    for (int r = 0; r < NB; ++r) {
-      if (r < nb) {
-        double s = x[r];
-#pragma unroll
-        for (int k = 0; k < NB; ++k)
-          if (k < r) s -= l[r][k] * x[k];
-        x[r] = s / l[r][r];
-      }
-    }
-  } else {
-#pragma unroll
-    for (int rr = 0; rr < NB; ++rr) {
-      const int r = NB - 1 - rr;
-      if (r < nb) {
-        double s = x[r];
-#pragma unroll
-        for (int k = 0; k < NB; ++k)
-          if (k > r && k < nb) s -= l[k][r] * x[k];
-        x[r] = s / l[r][r];
-      }
+    for (int q = 0; q < 4; ++q) {
+      const int r = ty * 4 + q;
+      out[q] = fma(transposed ? li[k][r] : li[r][k], xv, out[q]);
     }
   }
 #pragma unroll
-  for (int r = 0; r < NB; ++r)
-    if (r < nb) B[(int64_t)(j0 + r) * nrhs + j] = x[r];
+  for (int q = 0; q < 4; ++q) {
+    const int r = ty * 4 + q;
+    if (r < nb && j < nrhs) B[(int64_t)(j0 + r) * nrhs + j] = out[q];
+  }
 }
 
 }  // namespace plb
@@ -218,7 +235,7 @@ extern "C" int plb_chol_solve(double *G, int64_t n, double *B, int64_t nrhs, dou
       const int64_t W = (n - J0 < OB) ? (n - J0) : OB;
       for (int64_t j0 = J0; j0 < J0 + W; j0 += NB) {
         const int nb = (int)((J0 + W - j0 < NB) ? (J0 + W - j0) : NB);
-        trsv_block_kernel<<<(unsigned)ceil_div(nrhs, 128), 128, 0, s>>>(G, n, (int)j0, nb, B, nrhs, 0);
+        trsv_block_kernel<<<(unsigned)ceil_div(nrhs, 32), 256, 0, s>>>(G, n, (int)j0, nb, B, nrhs, 0);
         update(B + (j0 + nb) * nrhs, nrhs, J0 + W - j0 - nb, nrhs, G + (j0 + nb) * n + j0, n, 1, B + j0 * nrhs, nrhs, 1,
                nb, 0);
       }
@@ -230,7 +247,7 @@ extern "C" int plb_chol_solve(double *G, int64_t n, double *B, int64_t nrhs, dou
       const int64_t W = (n - J0 < OB) ? (n - J0) : OB;
       for (int64_t j0 = J0 + ((W - 1) / NB) * NB; j0 >= J0; j0 -= NB) {
         const int nb = (int)((J0 + W - j0 < NB) ? (J0 + W - j0) : NB);
-        trsv_block_kernel<<<(unsigned)ceil_div(nrhs, 128), 128, 0, s>>>(G, n, (int)j0, nb, B, nrhs, 1);
+        trsv_block_kernel<<<(unsigned)ceil_div(nrhs, 32), 256, 0, s>>>(G, n, (int)j0, nb, B, nrhs, 1);
         // rows J0 .. j0 of this outer block: B[i, :] -= sum_c L[j0 + c, i] * X[j0 + c, :]
         update(B + J0 * nrhs, nrhs, j0 - J0, nrhs, G + j0 * n + J0, 1, n, B + j0 * nrhs, nrhs, 1, nb, 0);
       }
