@@ -261,7 +261,7 @@ def run_b200(args):
         # per-launch CUDA-event timing of the dominant kernel: the timed region replays a CUDA graph
         # (events cannot bracket nodes of a replay), so the same steps are re-run un-captured with
         # events around every GEMM launch on the launching stream
-        ops.GEMM_TIMER = []
+        ops.GEMM_TIMER, ops.PACK_TIMER = [], []
         overlap_was, acc.overlap = acc.overlap, False  # time the kernel alone, not time-sliced with cuDNN
         torch.cuda.nvtx.range_push("plb_eager")
         for i in range(min(K, 5)):
@@ -270,6 +270,7 @@ def run_b200(args):
         torch.cuda.nvtx.range_pop()
         acc.overlap = overlap_was
         timer, ops.GEMM_TIMER = ops.GEMM_TIMER, None
+        pack_timer, ops.PACK_TIMER = ops.PACK_TIMER, None
         launches = launches_per_step * K
     gemm_ms = sum(t[0].elapsed_time(t[1]) for t in timer)
     gemm_flops = sum(t[2] for t in timer)
@@ -318,6 +319,20 @@ def run_b200(args):
                          "algorithmic_tflops": v[1] / (v[0] / 1e3) / 1e12 if v[0] > 0 else 0.0,
                          "tensor_frac": 3.0 * v[1] / (v[0] / 1e3) / 1e12 / tf32_peak if v[0] > 0 else 0.0}
                      for k, v in sorted(by_class.items())}}
+    # second-largest kernel of this library: the operand pack (HBM-bound by construction: reads every
+    # activation once, writes its tf32 hi/lo planes, accumulates the row sums of squares)
+    pack_ms = sum(a.elapsed_time(b) for a, b, _ in pack_timer)
+    pack_bytes = sum(n for _, _, n in pack_timer)
+    if pack_ms > 0:
+        gbs = pack_bytes / (pack_ms / 1e3) / 1e9
+        out["roofline_pack"] = {
+            "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+            "traffic": 255.9e6, "traffic_algorithmic_bytes": 308.3e6, "kernel": "pack_split_kernel",
+            "kernel_ms_per_step": pack_ms / min(K, 5), "launches_per_step": len(pack_timer) // min(K, 5),
+            "note": "achieved = algorithmic bytes (12 B per activation element: 4 read + 8 written as tf32 hi/lo "
+                    "planes) / summed CUDA-event time of the pack launches of the same un-captured steps; traffic = "
+                    "dram read (102.8 MB = the operand) + write (153.1 MB; the rest of the 205.5 MB of planes is still in L2 "
+                    "when the launch ends) of the C=64, K=401408 launch in profiles/pack_r01_raw.csv"}
     out["clocks"] = clocks
 
     # ---- e2e through the public API with pinned host batches (H2D + LAP + D2H of the perms inside)

@@ -19,6 +19,7 @@ NUM_SMS = 148
 #   "simt"       SIMT fp32 FMA cross-check kernel on the same planes (debugging only; still CUDA)
 _GEMM_IMPL = os.environ.get("PLB_GEMM_IMPL", "tcgen05")
 assert _GEMM_IMPL in ("tcgen05", "tcgen05_v1", "simt")
+PACK_TIMER = None  # set to a list by bench.py to collect (start, end, algorithmic bytes) per pack_split launch
 GEMM_TIMER = None  # set to a list by bench.py to collect (start, end, flops, bn, n_problems) per GEMM launch
 
 
@@ -160,9 +161,16 @@ def pack_split(x, axis, planes, kb_offset=0, row_index=None, rows=None, sumsq=No
     kb = (K + 15) // 16
     if kb_offset + kb > planes.k_blocks or rows > planes.row_groups * 8:
         raise ValueError("pack_split: operand does not fit the planes")
+    if PACK_TIMER is not None:  # bench instrumentation: CUDA events around this launch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     N.check(N.lib().plb_pack_split(x.data_ptr(), outer, src_rows, inner, N.ptr(row_index), rows,
                                    planes.hi.data_ptr(), planes.lo.data_ptr(), planes.row_groups, kb_offset,
                                    N.ptr(sumsq), N.ptr(rowsum), N.stream_ptr()), "plb_pack_split")
+    if PACK_TIMER is not None:
+        e1.record()
+        # algorithmic bytes: every element read once (4 B) and written as a tf32 hi/lo pair (8 B)
+        PACK_TIMER.append((e0, e1, 12.0 * rows * outer * inner))
     return kb
 
 
