@@ -238,6 +238,267 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel(const float *const *__rest
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// v2: the same algorithm (same selection rules, same fp64 association order => the same
+// assignment, ties included) with a shorter critical path per Dijkstra step.  The solve is a
+// chain of ~60 n dependent steps on the hard instances of the merge path (ResNet-50, n = 2048:
+// 125 k steps), so the step LATENCY is the whole cost.  Measured on the v1 kernel: 0.9 us per
+// step with 8-16 warps, 2.1 us with 32.  Changes:
+//   * CPT columns per thread, compile-time, processed in phases (all list reads, then all cost
+//     loads, then all relaxations) so the loads of a thread overlap: few warps, no 32-warp
+//     barrier, no 32-way second reduction stage;
+//   * arg-min by redux.sync on an order-preserving integer image of (distance, rank): three
+//     single-instruction reductions instead of a 5-level 3-register shuffle tree;
+//   * one barrier per step: warp winners (with their column) go to a double-buffered shared
+//     slot, every thread reduces them redundantly and tracks (row, list length, minimum,
+//     seen counts) in registers; the owner of the winning list slot compacts the list, so no
+//     thread ever reads a slot another thread is rewriting.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t order_key(double d) {
+  const uint64_t b = (uint64_t)__double_as_longlong(d);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_value(uint64_t k) {
+  const uint64_t b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+struct Win {
+  uint64_t key;
+  uint32_t rank;
+  bool mine;  // this lane holds the winning candidate
+};
+// lexicographic min of (key, rank) over the lanes of a warp; rank is unique per candidate
+__device__ __forceinline__ Win warp_argmin(uint64_t key, uint32_t rank) {
+  const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+  const uint32_t mhi = __reduce_min_sync(0xffffffffu, hi);
+  const uint32_t mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+  const bool tie = hi == mhi && lo == mlo;
+  const uint32_t mrk = __reduce_min_sync(0xffffffffu, tie ? rank : 0xffffffffu);
+  Win w;
+  w.key = ((uint64_t)mhi << 32) | mlo;
+  w.rank = mrk;
+  w.mine = tie && rank == mrk;
+  return w;
+}
+
+template <int CPT>
+__global__ void __launch_bounds__(1024, 1) lap_kernel_v2(const float *const *__restrict__ costs,
+                                                        const int32_t *__restrict__ ns,
+                                                        const int32_t *__restrict__ lds,
+                                                        int64_t *const *__restrict__ outs,
+                                                        double *__restrict__ objective, int32_t *__restrict__ status,
+                                                        int maximize) {
+  extern __shared__ __align__(16) uint8_t lap_smem[];
+  __shared__ uint64_t w_key[2][32];
+  __shared__ uint32_t w_rank[2][32];
+  __shared__ int w_col[2][32];
+  __shared__ double red[32];
+  __shared__ int sh_bad;
+
+  const int prob = blockIdx.x;
+  const int n = ns[prob];
+  const int64_t ld = lds[prob];
+  const float *__restrict__ C = costs[prob];
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = nthr >> 5;
+  const double sgn = maximize ? -1.0 : 1.0;
+  LapSmem s = carve(lap_smem, n);
+
+  if (tid == 0) sh_bad = 0;
+  for (int k = tid; k < n; k += nthr) {
+    s.u[k] = 0.0;
+    s.v[k] = 0.0;
+    s.pred[k] = -1;
+    s.row4col[k] = -1;
+    s.col4row[k] = -1;
+  }
+  __syncthreads();
+  {  // NaN / -inf screen (SciPy returns an error for those)
+    int bad = 0;
+    for (int i = 0; i < n; ++i) {
+      const float *__restrict__ crow = C + (int64_t)i * ld;
+      for (int j = tid; j < n; j += nthr) {
+        const double x = sgn * (double)__ldg(crow + j);
+        if (x != x || x == -INFINITY) bad = 1;
+      }
+    }
+    if (bad) sh_bad = 1;
+  }
+  __syncthreads();
+  if (sh_bad) {
+    if (tid == 0) {
+      status[prob] = 2;
+      objective[prob] = 0.0;
+    }
+    return;
+  }
+
+  int result = 0;
+  uint32_t step = 0;  // parity selects the warp-winner buffer
+  for (int cur = 0; cur < n; ++cur) {
+    for (int k = tid; k < n; k += nthr) {
+      s.dist[k] = INFINITY;
+      s.todo[k] = n - 1 - k;
+    }
+    __syncthreads();
+    int row = cur, ntodo = n, nrows = 0, ncols = 0, sink = -1;
+    double min_val = 0.0;
+
+    while (true) {
+      const double u_row = s.u[row];
+      const float *__restrict__ crow = C + (int64_t)row * ld;
+      int jj[CPT];
+      float cf[CPT];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        const int t = tid + c * nthr;
+        jj[c] = (t < ntodo) ? s.todo[t] : -1;
+      }
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) cf[c] = (jj[c] >= 0) ? __ldg(crow + jj[c]) : 0.f;
+      uint64_t bkey = 0xffffffffffffffffull;
+      uint32_t brank = 0xffffffffu;
+      int bcol = -1;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        if (jj[c] >= 0) {
+          const int j = jj[c], t = tid + c * nthr;
+          const double cst = sgn * (double)cf[c];
+          const double r = __dsub_rn(__dsub_rn(__dadd_rn(min_val, cst), u_row), s.v[j]);
+          double dj = s.dist[j];
+          if (r < dj) {
+            s.pred[j] = row;
+            s.dist[j] = r;
+            dj = r;
+          }
+          const uint64_t key = order_key(dj);
+          const uint32_t rank = (s.row4col[j] < 0) ? (uint32_t)(n - 1 - t) : (uint32_t)(n + t);
+          if (key < bkey || (key == bkey && rank < brank)) {
+            bkey = key;
+            brank = rank;
+            bcol = j;
+          }
+        }
+      }
+      const uint32_t buf = step & 1u;
+      ++step;
+      {
+        const Win w = warp_argmin(bkey, brank);
+        if (w.mine && brank != 0xffffffffu) {
+          w_key[buf][warp] = w.key;
+          w_rank[buf][warp] = w.rank;
+          w_col[buf][warp] = bcol;
+        } else if (lane == 0 && w.rank == 0xffffffffu) {  // no candidate in this warp
+          w_key[buf][warp] = 0xffffffffffffffffull;
+          w_rank[buf][warp] = 0xffffffffu;
+          w_col[buf][warp] = -1;
+        }
+      }
+      __syncthreads();
+      const bool have = lane < nwarps;
+      const Win g = warp_argmin(have ? w_key[buf][lane] : 0xffffffffffffffffull, have ? w_rank[buf][lane] : 0xffffffffu);
+      if (g.rank == 0xffffffffu || key_value(g.key) == INFINITY) {
+        sink = -2;  // infeasible
+        break;
+      }
+      const int wsrc = __ffs(__ballot_sync(0xffffffffu, g.mine)) - 1;
+      const int j = w_col[buf][wsrc];
+      const int t = (g.rank < (uint32_t)n) ? (n - 1 - (int)g.rank) : ((int)g.rank - n);
+      min_val = key_value(g.key);
+      if (tid == 0) {
+        s.rows_seen[nrows] = row;
+        s.cols_seen[ncols] = j;
+      }
+      ++nrows;
+      ++ncols;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)  // the slot's own reader compacts it
+        if (tid + c * nthr == t) s.todo[t] = s.todo[ntodo - 1];
+      --ntodo;
+      const int r4c = s.row4col[j];
+      if (r4c < 0) {
+        sink = j;
+        break;
+      }
+      row = r4c;
+    }
+    __syncthreads();  // rows_seen / cols_seen / dist / pred of the last step are visible
+    if (sink == -2) {
+      result = 1;
+      break;
+    }
+
+    // dual update (rows_seen[0] == cur; row k>0 was reached through column cols_seen[k-1])
+    for (int k = tid; k < nrows; k += nthr) {
+      const int i = s.rows_seen[k];
+      if (k == 0) s.u[i] = __dadd_rn(s.u[i], min_val);
+      else s.u[i] = __dadd_rn(s.u[i], __dsub_rn(min_val, s.dist[s.col4row[i]]));
+    }
+    for (int k = tid; k < ncols; k += nthr) {
+      const int j = s.cols_seen[k];
+      s.v[j] = __dsub_rn(s.v[j], __dsub_rn(min_val, s.dist[j]));
+    }
+    __syncthreads();
+    if (tid == 0) {  // flip the augmenting path
+      int j = sink;
+      while (true) {
+        const int i = s.pred[j];
+        s.row4col[j] = i;
+        const int prev = s.col4row[i];
+        s.col4row[i] = j;
+        j = prev;
+        if (i == cur) break;
+      }
+    }
+    __syncthreads();
+  }
+
+  if (result != 0) {
+    if (tid == 0) {
+      status[prob] = result;
+      objective[prob] = 0.0;
+    }
+    return;
+  }
+  int64_t *out = outs[prob];
+  double part = 0.0;
+  for (int i = tid; i < n; i += nthr) {
+    const int j = s.col4row[i];
+    out[i] = (int64_t)j;
+    part += (double)C[(int64_t)i * ld + j];
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+  if (lane == 0) red[warp] = part;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int wq = 0; wq < nwarps; ++wq) tot += red[wq];
+    objective[prob] = tot;
+    status[prob] = 0;
+  }
+}
+
+template <int CPT>
+static int launch_lap_v2(const float *const *cost, const int32_t *n, const int32_t *ld, int64_t *const *col4row,
+                         double *objective, int32_t *status, int n_problems, int max_n, int maximize, size_t smem,
+                         cudaStream_t stream) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(lap_kernel_v2<CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(lap_kernel_v2<%d>, %zu): %s", CPT, smem, cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = smem;
+  }
+  int threads = (int)(ceil_div(max_n, 32 * CPT) * 32);
+  threads = threads < 32 ? 32 : threads;  // <= 1024 by the caller's choice of CPT
+  lap_kernel_v2<CPT><<<n_problems, threads, smem, stream>>>(cost, n, ld, col4row, objective, status, maximize);
+  return launch_status("lap_kernel_v2");
+}
+
 }  // namespace plb
 
 extern "C" int plb_lap_solve_batched(const float *const *cost, const int32_t *n, const int32_t *ld,
@@ -257,15 +518,30 @@ extern "C" int plb_lap_solve_batched(const float *const *cost, const int32_t *n,
     }
     configured = smem;
   }
-  // columns per thread (PLB_LAP_COLS_PER_THREAD, default 1): measured on B200, one column per
-  // thread wins up to the 1024-thread cap (n=256: 2.3 ms vs 2.7 / 3.7 / 5.5 ms at 2 / 4 / 8 columns) —
-  // the per-column fp64 relaxation costs more than the wider block-wide reduction
-  static int cols_per_thread = 0;
-  if (cols_per_thread == 0) {
-    const char *e = getenv("PLB_LAP_COLS_PER_THREAD");
-    cols_per_thread = e ? atoi(e) : 1;
-    if (cols_per_thread < 1) cols_per_thread = 1;
+  // PLB_LAP_IMPL=v1 selects the first kernel (one column per thread, two barriers per step) for A/B
+  // runs; PLB_LAP_COLS_PER_THREAD overrides the columns per thread of either kernel.
+  static int impl = 0, cols_override = -1;
+  if (impl == 0) {
+    const char *e = getenv("PLB_LAP_IMPL");
+    impl = (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
+    const char *c = getenv("PLB_LAP_COLS_PER_THREAD");
+    cols_override = c ? atoi(c) : 0;
   }
+  if (impl == 2) {
+    // columns per thread, measured on B200 (profiles/experiments/lap_cpt_sweep.py, N(0,1) costs, ms at
+    // 1 / 2 / 4 / 8 columns): n=256 1.7 / 2.0 / 2.7 / 4.2, n=512 5.1 / 5.5 / 6.9 / 11.3, n=1024 14.9 / 13.7 /
+    // 15.6 / 24.6, n=2048 - / 52.2 / 51.2 / 71.5, n=4096 - / - / 202 / 233 (v1 kernel: 3.2, 9.2, 22.6, 74.4, 263)
+    int cpt = cols_override > 0 ? cols_override : (max_n <= 512 ? 1 : (max_n <= 2048 ? 2 : 4));
+    while (cpt < 8 && (int64_t)cpt * 1024 < max_n) cpt *= 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (cpt) {
+      case 1: return launch_lap_v2<1>(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, smem, st);
+      case 2: return launch_lap_v2<2>(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, smem, st);
+      case 4: return launch_lap_v2<4>(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, smem, st);
+      default: return launch_lap_v2<8>(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, smem, st);
+    }
+  }
+  const int cols_per_thread = cols_override > 0 ? cols_override : 1;
   int threads = (int)(ceil_div(max_n, 32 * cols_per_thread) * 32);
   threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
   lap_kernel<<<n_problems, threads, smem, (cudaStream_t)stream>>>(cost, n, ld, col4row, objective, status, maximize);
