@@ -65,6 +65,13 @@ int plb_pack_split(const float *x, int64_t outer, int64_t src_rows, int64_t inne
                    float *hi, float *lo, int32_t row_groups, int32_t kb_offset,
                    double *row_sumsq, double *row_sum, void *stream);
 
+/* Both operands of one activation tap (the same tap of the two models: equal [outer][rows][inner]
+ * geometry, all rows, no gather) in one launch — the form activation matching uses for every tap
+ * (activation_matching.py:87-92 inserts one cross_features call per tapped node pair). */
+int plb_pack_split_pair(const float *xa, const float *xb, int64_t outer, int64_t src_rows, int64_t inner,
+                        float *hi_a, float *lo_a, float *hi_b, float *lo_b, int32_t row_groups,
+                        int32_t kb_offset, double *sumsq_a, double *sumsq_b, void *stream);
+
 /* Two-source gather-average + im2col pack for the PLeaS normal equations
  * (pleas_merging.py:116-123, 146-147: X-bar = cat[(x1[bi1]+x2[bi2])/2, x1[bi1c], x2[bi2c]]).
  * Packed row f = (c, dy, dx) of the merged layer input, k = (n, ho, wo).  chan1/chan2 give,

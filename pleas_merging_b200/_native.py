@@ -28,6 +28,8 @@ _SIGNATURES = {
     "plb_plane_bytes": (c_i64, [c_i64, c_i64, ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
     "plb_pack_split": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i64, c_ptr, c_ptr, c_i32, c_i32,
                                       c_ptr, c_ptr, c_ptr]),
+    "plb_pack_split_pair": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32,
+                                           c_ptr, c_ptr, c_ptr]),
     "plb_pack_im2col": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
                                        c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_i64, c_i32,
                                        c_ptr, c_ptr, c_i32, c_i32, c_ptr]),

@@ -51,11 +51,11 @@ __device__ __forceinline__ void reduce_row_stats(float s2, float s1, int row, in
 }
 
 template <bool VEC4>
-__global__ void __launch_bounds__(256) pack_split_kernel(const float *__restrict__ x, int64_t src_rows, uint32_t inner,
-                                                         uint32_t K, const int64_t *__restrict__ row_index, int rows,
-                                                         float *__restrict__ hi, float *__restrict__ lo,
-                                                         int row_groups, int kb_offset, int k_blocks,
-                                                         double *__restrict__ sumsq, double *__restrict__ sum) {
+__device__ __forceinline__ void pack_split_body(const float *__restrict__ x, int64_t src_rows, uint32_t inner,
+                                                uint32_t K, const int64_t *__restrict__ row_index, int rows,
+                                                float *__restrict__ hi, float *__restrict__ lo, int row_groups,
+                                                int kb_offset, int k_blocks, double *__restrict__ sumsq,
+                                                double *__restrict__ sum) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = lane & 7, jj = lane >> 3;
   const int g = blockIdx.y;
@@ -94,6 +94,34 @@ __global__ void __launch_bounds__(256) pack_split_kernel(const float *__restrict
     split_store(v, hi, lo, panel_offset(kb_offset + kb, g, row_groups) + (jj * 8 + r) * 4);
   }
   if (sumsq || sum) reduce_row_stats(s2, s1, g * 8 + (int)threadIdx.x, rows, sumsq, sum);
+}
+
+template <bool VEC4>
+__global__ void __launch_bounds__(256) pack_split_kernel(const float *__restrict__ x, int64_t src_rows, uint32_t inner,
+                                                         uint32_t K, const int64_t *__restrict__ row_index, int rows,
+                                                         float *__restrict__ hi, float *__restrict__ lo,
+                                                         int row_groups, int kb_offset, int k_blocks,
+                                                         double *__restrict__ sumsq, double *__restrict__ sum) {
+  pack_split_body<VEC4>(x, src_rows, inner, K, row_index, rows, hi, lo, row_groups, kb_offset, k_blocks, sumsq, sum);
+}
+
+// Both operands of one tap (same geometry) in ONE launch: blockIdx.z selects the operand.  Half the
+// launches and twice the CTAs per launch for the many small taps (C = 256..2048 at 14x14 / 7x7), whose
+// single-operand packs are ~10 us launches that never fill the machine (ncu: 1.3-3.7 TB/s vs 5.4-6.5
+// TB/s for the large ones, profiles/launches_r01c.csv.gz).
+struct PackPair {
+  const float *x[2];
+  float *hi[2], *lo[2];
+  double *sumsq[2];
+};
+
+template <bool VEC4>
+__global__ void __launch_bounds__(256) pack_split_pair_kernel(PackPair pp, int64_t src_rows, uint32_t inner,
+                                                              uint32_t K, int rows, int row_groups, int kb_offset,
+                                                              int k_blocks) {
+  const int z = blockIdx.z;
+  pack_split_body<VEC4>(pp.x[z], src_rows, inner, K, nullptr, rows, pp.hi[z], pp.lo[z], row_groups, kb_offset,
+                        k_blocks, pp.sumsq[z], nullptr);
 }
 
 struct Im2colGeom {
@@ -198,6 +226,35 @@ extern "C" int plb_pack_split(const float *x, int64_t outer, int64_t src_rows, i
     pack_split_kernel<false><<<grid, 256, 0, s>>>(x, src_rows, (uint32_t)inner, (uint32_t)K, row_index, (int)rows, hi,
                                                   lo, row_groups, kb_offset, k_blocks, row_sumsq, row_sum);
   return launch_status("pack_split_kernel");
+}
+
+extern "C" int plb_pack_split_pair(const float *xa, const float *xb, int64_t outer, int64_t src_rows, int64_t inner,
+                                   float *hi_a, float *lo_a, float *hi_b, float *lo_b, int32_t row_groups,
+                                   int32_t kb_offset, double *sumsq_a, double *sumsq_b, void *stream) {
+  using namespace plb;
+  PLB_REQUIRE(xa && xb && hi_a && lo_a && hi_b && lo_b, PLB_EINVAL, "plb_pack_split_pair: null pointer");
+  PLB_REQUIRE(outer > 0 && src_rows > 0 && inner > 0, PLB_EINVAL, "plb_pack_split_pair: empty operand");
+  PLB_REQUIRE((sumsq_a == nullptr) == (sumsq_b == nullptr), PLB_EINVAL,
+              "plb_pack_split_pair: row statistics must be requested for both operands or neither");
+  const int64_t K = outer * inner, rows = src_rows;
+  PLB_REQUIRE(K < (int64_t)1 << 31 && inner < (int64_t)1 << 31, PLB_ESIZE, "plb_pack_split_pair: K too large");
+  PLB_REQUIRE(row_groups > 0 && (int64_t)row_groups * 8 >= rows, PLB_EINVAL,
+              "plb_pack_split_pair: row_groups must cover rows");
+  PLB_REQUIRE((((uintptr_t)hi_a | (uintptr_t)lo_a | (uintptr_t)hi_b | (uintptr_t)lo_b) & 15) == 0, PLB_EALIGN,
+              "plb_pack_split_pair: planes unaligned");
+  const int k_blocks = (int)ceil_div(K, kPackK);
+  dim3 grid((unsigned)ceil_div(k_blocks, kKbPerBlock), (unsigned)ceil_div(rows, 8), 2);
+  PLB_REQUIRE(grid.y <= 65535, PLB_ESIZE, "plb_pack_split_pair: too many rows");
+  cudaStream_t s = (cudaStream_t)stream;
+  PackPair pp{{xa, xb}, {hi_a, hi_b}, {lo_a, lo_b}, {sumsq_a, sumsq_b}};
+  const bool vec4 = (inner % 4 == 0) && ((((uintptr_t)xa | (uintptr_t)xb) & 15) == 0);
+  if (vec4)
+    pack_split_pair_kernel<true><<<grid, 256, 0, s>>>(pp, src_rows, (uint32_t)inner, (uint32_t)K, (int)rows,
+                                                      row_groups, kb_offset, k_blocks);
+  else
+    pack_split_pair_kernel<false><<<grid, 256, 0, s>>>(pp, src_rows, (uint32_t)inner, (uint32_t)K, (int)rows,
+                                                       row_groups, kb_offset, k_blocks);
+  return launch_status("pack_split_pair_kernel");
 }
 
 extern "C" int plb_pack_im2col(const float *x1, const float *x2, int64_t N, int64_t cin_src, int64_t H, int64_t W,

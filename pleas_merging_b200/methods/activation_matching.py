@@ -341,8 +341,7 @@ class CrossAccumulator:
         if xb.dtype != torch.float32:
             xb = xb.float()
         qa, qb = (st.q[:st.ra], st.q[st.ra:]) if st.q is not None else (None, None)
-        ops.pack_split(xa, t.axis, st.pa, sumsq=qa)
-        ops.pack_split(xb, t.axis, st.pb, sumsq=qb)
+        ops.pack_split_pair(xa, xb, t.axis, st.pa, st.pb, qa, qb)
 
     def _multiply(self, st):
         qa, qb = (st.q[:st.ra], st.q[st.ra:]) if st.q is not None else (None, None)

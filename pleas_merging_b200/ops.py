@@ -174,6 +174,34 @@ def pack_split(x, axis, planes, kb_offset=0, row_index=None, rows=None, sumsq=No
     return kb
 
 
+def pack_split_pair(xa, xb, axis, pa, pb, sumsq_a=None, sumsq_b=None):
+    """Packs the two operands of one tap (same shape, all rows) with ONE launch; falls back to two
+    ``pack_split`` calls when the geometries differ."""
+    _require_cuda_f32(xa, "pack_split_pair")
+    _require_cuda_f32(xb, "pack_split_pair")
+    if xa.shape != xb.shape or pa.row_groups != pb.row_groups or (sumsq_a is None) != (sumsq_b is None):
+        pack_split(xa, axis, pa, sumsq=sumsq_a)
+        pack_split(xb, axis, pb, sumsq=sumsq_b)
+        return
+    if not xa.is_contiguous():
+        xa = xa.contiguous()
+    if not xb.is_contiguous():
+        xb = xb.contiguous()
+    outer, rows, inner = as_rows_view(xa, axis)
+    kb = (outer * inner + 15) // 16
+    if kb > min(pa.k_blocks, pb.k_blocks) or rows > pa.row_groups * 8:
+        raise ValueError("pack_split_pair: operands do not fit the planes")
+    if PACK_TIMER is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    N.check(N.lib().plb_pack_split_pair(xa.data_ptr(), xb.data_ptr(), outer, rows, inner, pa.hi.data_ptr(),
+                                        pa.lo.data_ptr(), pb.hi.data_ptr(), pb.lo.data_ptr(), pa.row_groups, 0,
+                                        N.ptr(sumsq_a), N.ptr(sumsq_b), N.stream_ptr()), "plb_pack_split_pair")
+    if PACK_TIMER is not None:
+        e1.record()
+        PACK_TIMER.append((e0, e1, 2 * 12.0 * rows * outer * inner))
+
+
 def choose_bn(n_rows):
     return 64 if n_rows <= 64 else (128 if n_rows <= 128 else 256)
 
@@ -315,8 +343,7 @@ def cross_statistic(x, y, axis, mode):
     need_q = mode == MODE_NEG_CDIST
     q = torch.zeros(ra + rb, dtype=torch.float64, device=dev) if need_q else None
     qa, qb = (q[:ra], q[ra:]) if need_q else (None, None)
-    pack_split(x, axis, pa, sumsq=qa)
-    pack_split(y, axis, pb, sumsq=qb)
+    pack_split_pair(x, y, axis, pa, pb, qa, qb)
     plan = GemmPlan(pa, pb, ra, rb, kb)
     plan.run()
     out = torch.empty(ra, rb, dtype=torch.float32, device=dev)

@@ -56,6 +56,29 @@ def test_pack_split_layout_and_stats(shape, axis):
     np.testing.assert_allclose(q[1].cpu().numpy(), ref.astype(np.float64).sum(1), rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("shape,axis", [((3, 20, 5, 4), 1), ((2, 130, 7, 7), 1), ((5, 24), 1), ((32, 64, 16, 16), 1)])
+def test_pack_split_pair_equals_two_single_packs(shape, axis):
+    """One launch for both operands of a tap == two plb_pack_split launches, bit for bit."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    xa, xb = torch.randn(*shape, generator=g).cuda(), torch.randn(*shape, generator=g).cuda()
+    outer, rows, inner = ops.as_rows_view(xa, axis)
+    kb = (outer * inner + 15) // 16
+    single = [ops.Planes(rows, kb, xa.device) for _ in range(2)]
+    pair = [ops.Planes(rows, kb, xa.device) for _ in range(2)]
+    for p in single + pair:
+        p.hi.zero_()
+        p.lo.zero_()
+    q1 = torch.zeros(2, rows, dtype=torch.float64, device=xa.device)
+    q2 = torch.zeros(2, rows, dtype=torch.float64, device=xa.device)
+    ops.pack_split(xa, axis, single[0], sumsq=q1[0])
+    ops.pack_split(xb, axis, single[1], sumsq=q1[1])
+    ops.pack_split_pair(xa, xb, axis, pair[0], pair[1], q2[0], q2[1])
+    for a, b in zip(single, pair):
+        assert torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo)
+    torch.testing.assert_close(q1, q2, rtol=1e-12, atol=0)
+
+
 def test_pack_split_row_gather():
     ops = _ops()
     x = torch.randn(4, 10, 6, generator=torch.Generator().manual_seed(1))
