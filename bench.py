@@ -261,7 +261,7 @@ def run_b200(args):
         # per-launch CUDA-event timing of the dominant kernel: the timed region replays a CUDA graph
         # (events cannot bracket nodes of a replay), so the same steps are re-run un-captured with
         # events around every GEMM launch on the launching stream
-        ops.GEMM_TIMER, ops.PACK_TIMER = [], []
+        ops.GEMM_TIMER, ops.PACK_TIMER, ops.DIRECT_TIMER = [], [], []
         overlap_was, acc.overlap = acc.overlap, False  # time the kernel alone, not time-sliced with cuDNN
         torch.cuda.nvtx.range_push("plb_eager")
         for i in range(min(K, 5)):
@@ -271,6 +271,7 @@ def run_b200(args):
         acc.overlap = overlap_was
         timer, ops.GEMM_TIMER = ops.GEMM_TIMER, None
         pack_timer, ops.PACK_TIMER = ops.PACK_TIMER, None
+        direct_timer, ops.DIRECT_TIMER = ops.DIRECT_TIMER, None
         launches = launches_per_step * K
     gemm_ms = sum(t[0].elapsed_time(t[1]) for t in timer)
     gemm_flops = sum(t[2] for t in timer)
@@ -333,6 +334,18 @@ def run_b200(args):
                     "planes) / summed CUDA-event time of the pack launches of the same un-captured steps; traffic = "
                     "dram read (102.8 MB = the operand) + write (153.1 MB; the rest of the 205.5 MB of planes is still in L2 "
                     "when the launch ends) of the C=64, K=401408 launch in profiles/pack_r01_raw.csv"}
+    # fused narrow-tap kernel (C <= 128): HBM-bound, reads each fp32 activation once
+    d_ms = sum(a.elapsed_time(b) for a, b, _, _ in direct_timer)
+    if d_ms > 0:
+        d_bytes = sum(n for _, _, n, _ in direct_timer)
+        gbs = d_bytes / (d_ms / 1e3) / 1e9
+        out["roofline_narrow_taps"] = {
+            "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+            "traffic": None, "kernel": "gram_direct_kernel", "kernel_ms_per_step": d_ms / min(K, 5),
+            "launches_per_step": len(direct_timer) // min(K, 5),
+            "algorithmic_tflops": sum(f for _, _, _, f in direct_timer) / (d_ms / 1e3) / 1e12,
+            "note": "achieved = algorithmic bytes (both fp32 activations of the tap, read once: 2*C*K*4) / summed "
+                    "CUDA-event time of the launches of the same un-captured steps"}
     out["clocks"] = clocks
 
     # ---- e2e through the public API with pinned host batches (H2D + LAP + D2H of the perms inside)

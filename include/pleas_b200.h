@@ -85,6 +85,19 @@ int plb_pack_im2col(const float *x1, const float *x2, int64_t N, int64_t cin_src
                     int32_t ones_row, float *hi, float *lo, int32_t row_groups, int32_t kb_offset,
                     void *stream);
 
+/* Fused cross-Gram of one NARROW tap (C <= 128 channels, C % 8 == 0, inner % 16 == 0): reads the
+ * two fp32 activations x, y [outer][C][inner] directly (no packed planes: 4 instead of 20 bytes
+ * of HBM traffic per element), splits to tf32 hi/lo on the way into shared memory and contracts
+ * with the 3xTF32 tcgen05 pipeline.  Writes partial[s] = X[:, Ks] Y[:, Ks]^T for `splits` K ranges
+ * as [splits][128][bn] fp32 with bn = 64 (C <= 64) or 128, to be reduced by plb_cross_finalize
+ * (ld_m = 128, ld_n = bn), and adds the rows' sums of squares to the fp64 vectors (atomics: zero
+ * them first; both or neither).  chain_kb = k-blocks per tensor-core accumulation chain (4).
+ * Replaces cross_features_inner_product / cross_features_cdist (activation_matching.py:14-46)
+ * for the HBM-bound taps. */
+int plb_gram_direct(const float *x, const float *y, int64_t outer, int64_t C, int64_t inner,
+                    float *partial, int32_t splits, int32_t chain_kb, double *row_sumsq_x,
+                    double *row_sumsq_y, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * 3xTF32 tcgen05 GEMM over packed planes:  partial[s] = A[:, Ks] B[:, Ks]^T per K split s.
  * One table entry per problem; problems sharing a tile width are launched together

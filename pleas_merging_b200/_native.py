@@ -30,6 +30,7 @@ _SIGNATURES = {
                                       c_ptr, c_ptr, c_ptr]),
     "plb_pack_split_pair": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32,
                                            c_ptr, c_ptr, c_ptr]),
+    "plb_gram_direct": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
     "plb_pack_im2col": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
                                        c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_i64, c_i32,
                                        c_ptr, c_ptr, c_i32, c_i32, c_ptr]),

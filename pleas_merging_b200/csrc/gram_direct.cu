@@ -1,0 +1,304 @@
+// Fused cross-Gram for NARROW taps (C <= 128): reads the two fp32 activations straight from
+// their [outer][C][inner] layout — no packed planes — splits every value into tf32 hi + lo on the
+// way into shared memory and contracts with the same 3xTF32 tcgen05 pipeline as gemm.cu.
+//
+// Why a second kernel: a tap with C channels has arithmetic intensity C/4 flop per activation
+// byte (activation_matching.py:26-28, 44-46: X Y^T over K = batch x spatial positions), so the
+// C = 64 / 128 taps of a ResNet (46 of the 174 taps of a ResNet-50 pair, K up to 401 408) are
+// HBM-bound.  Through packed planes they move 20 B per element (4 read + 8 written by pack.cu, 8
+// read by gemm.cu); here they move 4.  The converter stage costs shared-memory bandwidth (write
+// hi/lo: 2 x 4 B per element on top of the MMA's operand reads), which is why the WIDE taps keep
+// the packed-plane kernel: at BN = 256 that stage would make the tensor-bound kernel smem-bound.
+//
+// One output tile (128 x BN accumulator, rows/cols >= C unused), K split over the CTAs.
+// Warp roles (512 threads, 1 CTA/SM): warp 0 = TMEM owner + MMA issuer, warps 1-8 = promotion /
+// epilogue (as gemm3xtf32_v2_kernel), warps 9-15 = converters: lane 8 jj + r of a converter warp
+// owns row r and the jj-th 16-byte k-chunk of one (8 rows x 16 k) panel, loads it with one
+// LDG.128, writes one STS.128 per plane in the K-major no-swizzle core-matrix order, and keeps
+// the row's running sum of squares for the -cdist epilogue.  The raw fp32 k-blocks reach shared
+// memory by cp.async (no registers held while in flight; ~50 KB of raw slots per SM), are re-read
+// by the lane that requested them, split, and written into the MMA operand stages.  Converter
+// teams own whole k-blocks (and one stage each), so their latency chains overlap.
+#include "common.cuh"
+
+namespace plb {
+
+struct DirectProblem {
+  const float *x, *y;   // [outer][C][inner] fp32, 16-byte aligned, inner % 16 == 0
+  float *partial;       // [splits][128][BN]
+  double *qa, *qb;      // row sums of squares (fp64 atomics) or nullptr
+  int C, inner, k_blocks, splits;
+};
+
+template <int BN>
+struct DirectCfg {
+  static constexpr int kPlaneBytes = BN * kPackK * 4;      // one operand plane of one k-block (BN rows)
+  static constexpr int kStageBytes = 4 * kPlaneBytes;      // [A_hi][A_lo][B_hi][B_lo]
+  static constexpr int kRawBytes = 2 * kPlaneBytes;        // one k-block of both fp32 operands
+  static constexpr int kRawSlots = 2;                      // raw k-blocks in flight per team
+  static constexpr int kConvWarps = 7;                     // 16 warps in all: 128 registers per thread
+  static constexpr int kTeam = BN == 128 ? 2 : 1;          // converter warps per k-block
+  static constexpr int kTeams = kConvWarps / kTeam;        // == MMA stages == raw slots: team t owns stage t
+  static constexpr int kStages = kTeams;
+  static constexpr int kSmemBytes = kStages * (kStageBytes + kRawSlots * kRawBytes) + 1024;  // 225 KB / 193 KB
+  static constexpr int kThreads = 512;
+  static constexpr int kEpiWarps = 8;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(512, 1) gram_direct_kernel(DirectProblem p, int chain_kb) {
+  using Cfg = DirectCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[Cfg::kStages];
+  __shared__ uint64_t bar_empty[Cfg::kStages];
+  __shared__ uint64_t bar_acc_full[2];
+  __shared__ uint64_t bar_acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x;
+  const int kb0 = (int)((int64_t)p.k_blocks * split / p.splits);
+  const int nkb = (int)((int64_t)p.k_blocks * (split + 1) / p.splits) - kb0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < Cfg::kStages; ++s) {
+        mbar_init(&bar_full[s], Cfg::kTeam);
+        mbar_init(&bar_empty[s], 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&bar_acc_full[b], 1);
+        mbar_init(&bar_acc_empty[b], Cfg::kEpiWarps);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_base_s, 2 * BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp >= 9) {
+    // ------------------------------------------------------------------ converters
+    // Team t (kTeam warps) owns MMA stage t and raw slot t and handles the k-blocks kb = t (mod kTeams),
+    // so the per-k-block latency chain (cp.async wait -> split -> proxy fence -> barrier) of one team
+    // overlaps the other teams' instead of gating every k-block.
+    constexpr int P = 16;                       // panels per warp per k-block (2 * BN / 8 / kTeam)
+    const int cw = warp - 9;
+    const int team = cw / Cfg::kTeam, tw = cw % Cfg::kTeam;
+    const bool idle = team >= Cfg::kTeams;      // BN = 128: the seventh converter warp has no partner
+    const int r = lane & 7, jj = lane >> 3;
+    const int groups = p.C >> 3;                // 8-row groups per operand
+    const int64_t img = (int64_t)p.C * p.inner; // floats per outer index
+    const int64_t gstride = (int64_t)8 * p.inner;
+    uint8_t *st = smem + (size_t)team * Cfg::kStageBytes;
+    uint8_t *raw0 = smem + (size_t)Cfg::kStages * Cfg::kStageBytes + (size_t)team * Cfg::kRawSlots * Cfg::kRawBytes;
+    float s2[P];
+#pragma unroll
+    for (int q = 0; q < P; ++q) s2[q] = 0.f;
+    // panel q of this warp: pidx = tw + kTeam * q over [x groups | y groups]
+    auto request = [&](int kb, uint8_t *raw) {  // this lane's 16-byte pieces of k-block kb -> raw slot (cp.async)
+      const int64_t k0 = (int64_t)(kb0 + kb) * kPackK;
+      const int64_t o = k0 / p.inner;
+      const int64_t base = o * img + (k0 - o * p.inner) + (int64_t)r * p.inner + jj * 4;
+#pragma unroll
+      for (int q = 0; q < P; ++q) {
+        const int pidx = tw + Cfg::kTeam * q;
+        if (pidx < 2 * groups) {
+          const int opnd = pidx >= groups ? 1 : 0;
+          const int g = pidx - opnd * groups;
+          cp_async16(raw + (uint32_t)pidx * 512u + (uint32_t)lane * 16u, (opnd ? p.y : p.x) + base + g * gstride);
+        }
+      }
+      cp_async_commit();
+    };
+    auto convert = [&](const float4 &v, int q) {
+      const int pidx = tw + Cfg::kTeam * q;
+      const int opnd = pidx >= groups ? 1 : 0;
+      const int g = pidx - opnd * groups;
+      uint8_t *dst = st + (opnd ? 2 * Cfg::kPlaneBytes : 0) + (uint32_t)g * 512u + (uint32_t)(jj * 8 + r) * 16u;
+      float4 h, l;
+      h.x = to_tf32(v.x); l.x = to_tf32(v.x - h.x);
+      h.y = to_tf32(v.y); l.y = to_tf32(v.y - h.y);
+      h.z = to_tf32(v.z); l.z = to_tf32(v.z - h.z);
+      h.w = to_tf32(v.w); l.w = to_tf32(v.w - h.w);
+      *reinterpret_cast<float4 *>(dst) = h;
+      *reinterpret_cast<float4 *>(dst + Cfg::kPlaneBytes) = l;
+      s2[q] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2[q]))));
+    };
+    if (!idle) {  // two k-blocks in flight per team; always one commit group per slot
+      if (team < nkb) request(team, raw0); else cp_async_commit();
+      if (team + Cfg::kTeams < nkb) request(team + Cfg::kTeams, raw0 + Cfg::kRawBytes); else cp_async_commit();
+    }
+    uint32_t round = 0;
+    for (int kb = idle ? nkb : team; kb < nkb; kb += Cfg::kTeams, ++round) {
+      uint8_t *raw = raw0 + (round & 1u) * Cfg::kRawBytes;
+      cp_async_wait<1>();                                   // all but the newest group: k-block kb has landed
+      mbar_wait(&bar_empty[team], (round & 1u) ^ 1u);       // the MMAs of the stage's previous k-block retired
+      float4 v[P / 2];
+#pragma unroll
+      for (int q = 0; q < P / 2; ++q)
+        if (tw + Cfg::kTeam * q < 2 * groups)
+          v[q] = *reinterpret_cast<const float4 *>(raw + (uint32_t)(tw + Cfg::kTeam * q) * 512u + (uint32_t)lane * 16u);
+#pragma unroll
+      for (int q = 0; q < P / 2; ++q)
+        if (tw + Cfg::kTeam * q < 2 * groups) convert(v[q], q);
+#pragma unroll
+      for (int q = P / 2; q < P; ++q)
+        if (tw + Cfg::kTeam * q < 2 * groups)
+          v[q - P / 2] = *reinterpret_cast<const float4 *>(raw + (uint32_t)(tw + Cfg::kTeam * q) * 512u + (uint32_t)lane * 16u);
+#pragma unroll
+      for (int q = P / 2; q < P; ++q)
+        if (tw + Cfg::kTeam * q < 2 * groups) convert(v[q - P / 2], q);
+      // generic-proxy stores -> visible to tcgen05.mma (async proxy).  The fence compiles to
+      // MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and the MEMBAR also waits for this thread's outstanding
+      // cp.async, so the next request is issued AFTER it (ncu: with the request in front, every
+      // k-block paid a full memory round trip before its barrier arrive).
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_full[team]);
+      // this raw slot is consumed: the team's k-block after next streams into it
+      if (kb + 2 * Cfg::kTeams < nkb) request(kb + 2 * Cfg::kTeams, raw); else cp_async_commit();
+    }
+    // row sums of squares: the 4 jj lanes of a row, then one fp64 atomic per row
+    if (p.qa != nullptr && !idle) {
+#pragma unroll
+      for (int q = 0; q < P; ++q) {
+        float v = s2[q];
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        const int pidx = tw + Cfg::kTeam * q;
+        if (pidx < 2 * groups && lane < 8) {
+          const int opnd = pidx >= groups ? 1 : 0;
+          const int g = pidx - opnd * groups;
+          atomicAdd((opnd ? p.qb : p.qa) + g * 8 + lane, (double)v);
+        }
+      }
+    }
+  } else if (warp == 0) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
+    uint32_t it = 0, chain = 0;
+    for (int i0 = 0; i0 < nkb; i0 += chain_kb, ++chain) {
+      const uint32_t buf = chain & 1u;
+      mbar_wait(&bar_acc_empty[buf], ((chain >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * BN;
+      const int i1 = min(nkb, i0 + chain_kb);
+      for (int i = i0; i < i1; ++i, ++it) {
+        const int s = it % Cfg::kStages;
+        mbar_wait(&bar_full[s], (it / Cfg::kStages) & 1u);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = smem_u32(smem + (size_t)s * Cfg::kStageBytes);
+#pragma unroll
+          for (int ks = 0; ks < kPackK / 8; ++ks) {
+            const uint32_t koff = ks * 256;
+            // A descriptors span 128 rows (8 KB): with BN = 64 rows 64..127 alias the next plane — they
+            // only feed accumulator rows nobody reads
+            const uint64_t a_hi = umma_desc_kmajor(st + koff, 128, 512);
+            const uint64_t a_lo = umma_desc_kmajor(st + Cfg::kPlaneBytes + koff, 128, 512);
+            const uint64_t b_hi = umma_desc_kmajor(st + 2 * Cfg::kPlaneBytes + koff, 128, 512);
+            const uint64_t b_lo = umma_desc_kmajor(st + 3 * Cfg::kPlaneBytes + koff, 128, 512);
+            umma_tf32(d_tmem, a_lo, b_hi, idesc, (i > i0 || ks > 0) ? 1u : 0u);
+            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+            umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+          }
+          umma_commit(&bar_empty[s]);
+          if (i == i1 - 1) umma_commit(&bar_acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ promotion / epilogue
+    constexpr int COLS = BN / 2;
+    const int q = warp & 3;
+    const int half = (warp - 1) >> 2;
+    uint32_t chain = 0;
+    float acc[COLS];
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) acc[c] = 0.f;
+    for (int i0 = 0; i0 < nkb; i0 += chain_kb, ++chain) {
+      const uint32_t buf = chain & 1u;
+      mbar_wait(&bar_acc_full[buf], (chain >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * COLS;
+#pragma unroll
+      for (int c = 0; c < COLS / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t0 + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[c * 32 + e] += __uint_as_float(v[e]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_acc_empty[buf]);
+    }
+    const int64_t row = q * 32 + lane;
+    float4 *d4 = reinterpret_cast<float4 *>(p.partial + ((int64_t)split * 128 + row) * BN + half * COLS);
+#pragma unroll
+    for (int e = 0; e < COLS / 4; ++e) d4[e] = make_float4(acc[4 * e], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+template <int BN>
+static int launch_direct(const DirectProblem &p, int chain_kb, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gram_direct_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         DirectCfg<BN>::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(gram_direct_kernel<%d>): %s", BN, cudaGetErrorString(e));
+      return (int)e;
+    }
+    configured = true;
+  }
+  gram_direct_kernel<BN><<<p.splits, DirectCfg<BN>::kThreads, DirectCfg<BN>::kSmemBytes, stream>>>(p, chain_kb);
+  return launch_status("gram_direct_kernel");
+}
+
+}  // namespace plb
+
+extern "C" int plb_gram_direct(const float *x, const float *y, int64_t outer, int64_t C, int64_t inner,
+                               float *partial, int32_t splits, int32_t chain_kb, double *row_sumsq_x,
+                               double *row_sumsq_y, void *stream) {
+  using namespace plb;
+  PLB_REQUIRE(x && y && partial, PLB_EINVAL, "plb_gram_direct: null pointer");
+  PLB_REQUIRE(outer > 0 && inner > 0 && C > 0, PLB_EINVAL, "plb_gram_direct: empty operand");
+  PLB_REQUIRE(C <= 128 && C % 8 == 0, PLB_ESIZE, "plb_gram_direct: C must be a multiple of 8, at most 128");
+  PLB_REQUIRE(inner % 16 == 0, PLB_ESIZE, "plb_gram_direct: inner must be a multiple of 16 (use the packed path)");
+  PLB_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)partial) & 15) == 0, PLB_EALIGN,
+              "plb_gram_direct: pointers must be 16-byte aligned");
+  PLB_REQUIRE((row_sumsq_x == nullptr) == (row_sumsq_y == nullptr), PLB_EINVAL,
+              "plb_gram_direct: row statistics for both operands or neither");
+  const int64_t kb = outer * inner / kPackK;
+  PLB_REQUIRE(kb < ((int64_t)1 << 31), PLB_ESIZE, "plb_gram_direct: K too large");
+  PLB_REQUIRE(splits > 0 && splits <= kb && chain_kb > 0, PLB_EINVAL, "plb_gram_direct: bad splits / chain");
+  DirectProblem p{x, y, partial, row_sumsq_x, row_sumsq_y, (int)C, (int)inner, (int)kb, splits};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (C <= 64) return launch_direct<64>(p, chain_kb, s);
+  return launch_direct<128>(p, chain_kb, s);
+}

@@ -196,7 +196,7 @@ DEFER_FLOPS = float(os.environ.get("PLB_DEFER_FLOPS", "3e9"))
 
 class _TapState:
     """Geometry, row-norm buffer and GEMM plan of one tap for one pair of activation shapes."""
-    __slots__ = ("ra", "rb", "kb", "K", "q", "plan", "version", "pa", "pb", "deferred", "group", "slot")
+    __slots__ = ("ra", "rb", "kb", "K", "q", "plan", "version", "pa", "pb", "deferred", "group", "slot", "direct")
 
 
 class _Tap:
@@ -283,6 +283,14 @@ class CrossAccumulator:
         st.q = self.pool.empty(2 * (ra + rb)).view(torch.float64).zero_() \
             if self.mode == ops.MODE_NEG_CDIST else None
         st.plan, st.version, st.group, st.slot = None, -1, t.group, None
+        # narrow taps (C <= 128) are HBM-bound: the fused kernel reads the activations once, in place,
+        # right behind their producer — no planes, nothing deferred
+        st.direct = (not self.overlap) and xa.dtype == torch.float32 and xb.dtype == torch.float32 and \
+            ops.direct_gram_eligible(xa, xb, t.axis)
+        if st.direct:
+            st.deferred, st.pa, st.pb, st.version = False, None, None, None
+            st.plan = ops.DirectGramPlan(ra, st.K, self.device, pool=self.pool)
+            return st
         st.deferred = 2.0 * ra * rb * st.K < DEFER_FLOPS
         if st.deferred:  # own planes and partial tiles: they must survive until the end of the batch
             bn = ops.choose_bn(rb)
@@ -318,7 +326,7 @@ class CrossAccumulator:
         """Binds every tap state against the final arena (outside any graph capture)."""
         for t in self.taps:
             for st in t.states.values():
-                if not st.deferred and st.version != self.arena.version:
+                if not st.deferred and not st.direct and st.version != self.arena.version:
                     self._bind(st)
 
     def _state(self, idx, xa, xb):
@@ -328,7 +336,7 @@ class CrossAccumulator:
         if st is None:
             with _timed("prepare"):
                 st = t.states[key] = self._prepare(t, xa, xb)
-        if not st.deferred:
+        if not st.deferred and not st.direct:
             if st.version != self.arena.version:
                 with _timed("bind"):
                     self._bind(st)
@@ -350,6 +358,13 @@ class CrossAccumulator:
 
     def tap(self, idx, xa, xb):
         t, st = self._state(idx, xa, xb)
+        if st.direct:
+            qa, qb = (st.q[:st.ra], st.q[st.ra:]) if st.q is not None else (None, None)
+            if not xa.is_contiguous() or not xb.is_contiguous():  # same shape as a contiguous earlier batch
+                xa, xb = xa.contiguous(), xb.contiguous()
+            st.plan.run(xa, xb, t.axis, qa, qb)
+            st.plan.finalize(self.costs[st.group], self.mode, qa, qb, accumulate=True)
+            return
         if not self.overlap:
             self._pack(t, st, xa, xb)
             if st.deferred:

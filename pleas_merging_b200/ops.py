@@ -19,6 +19,7 @@ NUM_SMS = 148
 #   "simt"       SIMT fp32 FMA cross-check kernel on the same planes (debugging only; still CUDA)
 _GEMM_IMPL = os.environ.get("PLB_GEMM_IMPL", "tcgen05")
 assert _GEMM_IMPL in ("tcgen05", "tcgen05_v1", "simt")
+DIRECT_TIMER = None  # (start, end, algorithmic bytes, flops) per fused narrow-tap launch
 PACK_TIMER = None  # set to a list by bench.py to collect (start, end, algorithmic bytes) per pack_split launch
 GEMM_TIMER = None  # set to a list by bench.py to collect (start, end, flops, bn, n_problems) per GEMM launch
 
@@ -298,6 +299,50 @@ class GemmPlan:
                 "plb_cross_finalize")
 
 
+DIRECT_MAX_ROWS = int(os.environ.get("PLB_DIRECT_MAX_ROWS", "128"))  # 0 disables the fused narrow-tap kernel
+
+
+def direct_gram_eligible(x, y, axis):
+    """True when a tap can use the fused narrow-tap kernel (plb_gram_direct): both operands fp32,
+    contiguous, the same [outer][C][inner] geometry, C <= 128 a multiple of 8, inner a multiple of 16."""
+    if DIRECT_MAX_ROWS <= 0 or x.shape != y.shape or x.dtype != torch.float32 or y.dtype != torch.float32:
+        return False
+    if not (x.is_contiguous() and y.is_contiguous()):
+        return False
+    outer, rows, inner = as_rows_view(x, axis)
+    return rows <= min(DIRECT_MAX_ROWS, 128) and rows % 8 == 0 and inner % 16 == 0 and outer * inner >= 256
+
+
+class DirectGramPlan:
+    """Fused cross-Gram of one narrow tap: partial tiles [splits][128][bn] + the finalize geometry."""
+
+    def __init__(self, rows, K, device, pool=None):
+        self.M = self.N = rows
+        self.bn = 64 if rows <= 64 else 128
+        self.ld_m, self.ld_n = 128, self.bn
+        kb = K // 16
+        self.splits = max(1, min(NUM_SMS, kb // 16))
+        need = self.splits * self.ld_m * self.ld_n
+        self.partial = pool.empty(need) if pool is not None else torch.empty(need, dtype=torch.float32, device=device)
+        self.alg_flops = 2.0 * rows * rows * K
+        self.alg_bytes = 2.0 * rows * K * 4
+        self.symmetric = False
+
+    def run(self, x, y, axis, qa=None, qb=None):
+        outer, rows, inner = as_rows_view(x, axis)
+        if DIRECT_TIMER is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        N.check(N.lib().plb_gram_direct(x.data_ptr(), y.data_ptr(), outer, rows, inner, self.partial.data_ptr(),
+                                        self.splits, MAX_CHAIN_KB, N.ptr(qa), N.ptr(qb), N.stream_ptr()),
+                "plb_gram_direct")
+        if DIRECT_TIMER is not None:
+            e1.record()
+            DIRECT_TIMER.append((e0, e1, self.alg_bytes, self.alg_flops))
+
+    finalize = GemmPlan.finalize
+
+
 class GroupedGemm:
     """Several small problems of one tile width in ONE persistent launch (their CTAs share the
     148 SMs), e.g. the ~100 small taps of a ResNet-50 calibration batch."""
@@ -339,14 +384,19 @@ def cross_statistic(x, y, axis, mode):
         raise ValueError(f"cross_statistic: contraction sizes differ ({oa * ia} vs {ob * ib})")
     kb = (oa * ia + 15) // 16
     dev = x.device
-    pa, pb = Planes(ra, kb, dev), Planes(rb, kb, dev)
     need_q = mode == MODE_NEG_CDIST
     q = torch.zeros(ra + rb, dtype=torch.float64, device=dev) if need_q else None
     qa, qb = (q[:ra], q[ra:]) if need_q else (None, None)
+    out = torch.empty(ra, rb, dtype=torch.float32, device=dev)
+    if direct_gram_eligible(x, y, axis):  # narrow tap: fused kernel, no packed planes
+        plan = DirectGramPlan(ra, oa * ia, dev)
+        plan.run(x, y, axis, qa, qb)
+        plan.finalize(out, mode, qa, qb, accumulate=False)
+        return out
+    pa, pb = Planes(ra, kb, dev), Planes(rb, kb, dev)
     pack_split_pair(x, y, axis, pa, pb, qa, qb)
     plan = GemmPlan(pa, pb, ra, rb, kb)
     plan.run()
-    out = torch.empty(ra, rb, dtype=torch.float32, device=dev)
     plan.finalize(out, mode, qa, qb, accumulate=False)
     return out
 

@@ -98,8 +98,9 @@ GEMM_CASES = [((2, 12, 5, 5), 1), ((4, 64, 16, 16), 1), ((3, 200, 9, 10), 1), ((
 
 @pytest.mark.parametrize("impl", ["simt", "tcgen05_v1", "tcgen05"])
 @pytest.mark.parametrize("shape,axis", GEMM_CASES)
-def test_cross_statistic_inner_and_cdist(shape, axis, impl):
+def test_cross_statistic_inner_and_cdist(shape, axis, impl, monkeypatch):
     ops = _ops()
+    monkeypatch.setattr(ops, "DIRECT_MAX_ROWS", 0)  # the packed-plane path (pack + GEMM); fused path below
     g = torch.Generator().manual_seed(3)
     x = torch.relu(torch.randn(*shape, generator=g)) + 0.1 * torch.randn(*shape, generator=g)
     y = torch.relu(torch.randn(*shape, generator=g))
@@ -118,6 +119,40 @@ def test_cross_statistic_inner_and_cdist(shape, axis, impl):
     assert np.abs(D - Dref).max() <= 1e-4 * np.abs(Dref).max()
     # and against the fp32 oracle restatement of the reference operator
     assert np.abs(D - O.cross_neg_cdist(x.numpy(), y.numpy(), axis)).max() <= 1e-4 * np.abs(Dref).max()
+
+
+DIRECT_CASES = [((4, 64, 16, 16), 1), ((1, 128, 64, 64), 1), ((6, 24, 4, 16), 1), ((2, 72, 16, 16), 1),
+                ((32, 64, 56, 56), 1), ((3, 8, 16, 16), 1), ((20, 128, 4, 4), 1), ((7, 40, 48), 1)]
+
+
+@pytest.mark.parametrize("shape,axis", DIRECT_CASES)
+def test_fused_narrow_tap_kernel(shape, axis):
+    """plb_gram_direct (no packed planes) == fp64 reference at 3xTF32 accuracy, == the packed path
+    to fp32 rounding, for both statistics; rows that are not a multiple of the tile and K ranges
+    that split unevenly included."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    x = (torch.relu(torch.randn(*shape, generator=g)) + 0.1 * torch.randn(*shape, generator=g)).cuda()
+    y = torch.relu(torch.randn(*shape, generator=g)).cuda()
+    assert ops.direct_gram_eligible(x, y, axis)
+    before = ops.N.LAUNCH_COUNTS["plb_gram_direct"]
+    G = ops.cross_statistic(x, y, axis, ops.MODE_INNER)
+    D = ops.cross_statistic(x, y, axis, ops.MODE_NEG_CDIST)
+    assert ops.N.LAUNCH_COUNTS["plb_gram_direct"] == before + 2
+    old, ops.DIRECT_MAX_ROWS = ops.DIRECT_MAX_ROWS, 0
+    try:
+        Gp = ops.cross_statistic(x, y, axis, ops.MODE_INNER)
+        Dp = ops.cross_statistic(x, y, axis, ops.MODE_NEG_CDIST)
+    finally:
+        ops.DIRECT_MAX_ROWS = old
+    X = O._rows(x.cpu().numpy(), axis).astype(np.float64)
+    Y = O._rows(y.cpu().numpy(), axis).astype(np.float64)
+    Gref = X @ Y.T
+    assert np.abs(G.cpu().numpy() - Gref).max() <= 2.5e-6 * np.abs(Gref).max()
+    Dref = -np.sqrt(np.maximum((X * X).sum(1)[:, None] + (Y * Y).sum(1)[None] - 2 * Gref, 0))
+    assert np.abs(D.cpu().numpy() - Dref).max() <= 1e-4 * np.abs(Dref).max()
+    assert (G - Gp).abs().max() <= 2e-6 * Gp.abs().max()
+    assert (D - Dp).abs().max() <= 1e-4 * Dp.abs().max()
 
 
 @pytest.mark.parametrize("impl", ["tcgen05", "tcgen05_v1"])
