@@ -11,14 +11,22 @@
 // the packed-plane kernel: at BN = 256 that stage would make the tensor-bound kernel smem-bound.
 //
 // One output tile (128 x BN accumulator, rows/cols >= C unused), K split over the CTAs.
-// Warp roles (512 threads, 1 CTA/SM): warp 0 = TMEM owner + MMA issuer, warps 1-8 = promotion /
-// epilogue (as gemm3xtf32_v2_kernel), warps 9-15 = converters: lane 8 jj + r of a converter warp
-// owns row r and the jj-th 16-byte k-chunk of one (8 rows x 16 k) panel, loads it with one
-// LDG.128, writes one STS.128 per plane in the K-major no-swizzle core-matrix order, and keeps
-// the row's running sum of squares for the -cdist epilogue.  The raw fp32 k-blocks reach shared
-// memory by cp.async (no registers held while in flight; ~50 KB of raw slots per SM), are re-read
-// by the lane that requested them, split, and written into the MMA operand stages.  Converter
-// teams own whole k-blocks (and one stage each), so their latency chains overlap.
+// Warp roles (512 threads, 1 CTA/SM):
+//   warp 0      TMEM owner + MMA issuer
+//   warps 1-8   promotion / epilogue (as gemm3xtf32_v2_kernel)
+//   warps 9-10  LOADERS (x / y): cp.async of the raw fp32 k-blocks straight into the MMA stages' hi planes in
+//               the K-major core-matrix order (lane 8 jj + r = row r, jj-th 16-byte k-chunk of an
+//               8-row panel), completion signalled per stage with cp.async.mbarrier.arrive — it runs
+//               up to kStages k-blocks (96+ KB per SM) ahead and never executes a fence;
+//   warps 11-15 CONVERTERS: read a landed hi plane, write lo = x - trunc_tf32(x) into the stage's lo
+//               plane, keep the rows' running sums of squares, proxy-fence, signal the MMA warp.
+// The hi operand is the RAW fp32 word: kind::tf32 ignores the 13 low mantissa bits, i.e. the tensor
+// core multiplies trunc_tf32(x), and lo is taken against exactly that value, so hi + lo = x.
+// Measured (ncu profiles/gram_direct_c64_r01_raw.csv, C = 64, K = 401 408): 96.5 us, DRAM read =
+// algorithmic bytes, 2.1 TB/s — limited by how many cp.async two loader warps can keep outstanding
+// (converters wait for data 46 % of the time; converters that issue their own cp.async are instead
+// gated by their proxy fence, whose MEMBAR.ALL.CTA waits for the thread's outstanding copies).
+// Next: TMA 2-D tensor-map loads (legal here because inner % 16 == 0) into 128B-swizzled stages.
 #include "common.cuh"
 
 namespace plb {
@@ -33,25 +41,23 @@ struct DirectProblem {
 template <int BN>
 struct DirectCfg {
   static constexpr int kPlaneBytes = BN * kPackK * 4;      // one operand plane of one k-block (BN rows)
-  static constexpr int kStageBytes = 4 * kPlaneBytes;      // [A_hi][A_lo][B_hi][B_lo]
-  static constexpr int kRawBytes = 2 * kPlaneBytes;        // one k-block of both fp32 operands
-  static constexpr int kRawSlots = 2;                      // raw k-blocks in flight per team
-  static constexpr int kConvWarps = 7;                     // 16 warps in all: 128 registers per thread
+  static constexpr int kStageBytes = 4 * kPlaneBytes;      // [X raw/hi][X lo][Y raw/hi][Y lo]
+  static constexpr int kConvWarps = 5;                     // warps 11-15 (BN = 128: two teams of two, one idle)
+  static constexpr int kStages = BN == 128 ? 6 : 10;       // 192 KB / 160 KB of operand stages
   static constexpr int kTeam = BN == 128 ? 2 : 1;          // converter warps per k-block
-  static constexpr int kTeams = kConvWarps / kTeam;        // == MMA stages == raw slots: team t owns stage t
-  static constexpr int kStages = kTeams;
-  static constexpr int kSmemBytes = kStages * (kStageBytes + kRawSlots * kRawBytes) + 1024;  // 225 KB / 193 KB
+  static constexpr int kTeams = kConvWarps / kTeam;        // k-block kb is converted by team kb % kTeams
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
   static constexpr int kThreads = 512;
   static constexpr int kEpiWarps = 8;
+  static_assert(kStages % kTeams == 0, "a stage is always converted by the same team");
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+// the mbarrier receives one arrival from this thread once all its prior cp.async have completed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -62,8 +68,9 @@ template <int BN>
 __global__ void __launch_bounds__(512, 1) gram_direct_kernel(DirectProblem p, int chain_kb) {
   using Cfg = DirectCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_full[Cfg::kStages];
-  __shared__ uint64_t bar_empty[Cfg::kStages];
+  __shared__ uint64_t bar_raw[Cfg::kStages];    // loader -> converters: the raw k-block has landed
+  __shared__ uint64_t bar_full[Cfg::kStages];   // converters -> MMA: lo planes written
+  __shared__ uint64_t bar_empty[Cfg::kStages];  // MMA -> loader: the stage's MMAs have retired
   __shared__ uint64_t bar_acc_full[2];
   __shared__ uint64_t bar_acc_empty[2];
   __shared__ uint32_t tmem_base_s;
@@ -77,6 +84,7 @@ __global__ void __launch_bounds__(512, 1) gram_direct_kernel(DirectProblem p, in
   if (warp == 0) {
     if (lane == 0) {
       for (int s = 0; s < Cfg::kStages; ++s) {
+        mbar_init(&bar_raw[s], 64);  // both loader warps, one arrival per lane
         mbar_init(&bar_full[s], Cfg::kTeam);
         mbar_init(&bar_empty[s], 1);
       }
@@ -95,87 +103,65 @@ __global__ void __launch_bounds__(512, 1) gram_direct_kernel(DirectProblem p, in
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp >= 9) {
-    // ------------------------------------------------------------------ converters
-    // Team t (kTeam warps) owns MMA stage t and raw slot t and handles the k-blocks kb = t (mod kTeams),
-    // so the per-k-block latency chain (cp.async wait -> split -> proxy fence -> barrier) of one team
-    // overlaps the other teams' instead of gating every k-block.
-    constexpr int P = 16;                       // panels per warp per k-block (2 * BN / 8 / kTeam)
-    const int cw = warp - 9;
-    const int team = cw / Cfg::kTeam, tw = cw % Cfg::kTeam;
-    const bool idle = team >= Cfg::kTeams;      // BN = 128: the seventh converter warp has no partner
+  if (warp == 9 || warp == 10) {
+    // ------------------------------------------------------------------ loaders (warp 9: x, warp 10: y)
     const int r = lane & 7, jj = lane >> 3;
-    const int groups = p.C >> 3;                // 8-row groups per operand
-    const int64_t img = (int64_t)p.C * p.inner; // floats per outer index
+    const int groups = p.C >> 3;                 // 8-row groups per operand
+    const int64_t img = (int64_t)p.C * p.inner;  // floats per outer index
     const int64_t gstride = (int64_t)8 * p.inner;
-    uint8_t *st = smem + (size_t)team * Cfg::kStageBytes;
-    uint8_t *raw0 = smem + (size_t)Cfg::kStages * Cfg::kStageBytes + (size_t)team * Cfg::kRawSlots * Cfg::kRawBytes;
+    const float *src0 = (warp == 9 ? p.x : p.y) + (int64_t)r * p.inner + jj * 4;
+    const uint32_t plane = warp == 9 ? 0u : 2u * Cfg::kPlaneBytes;
+    int64_t o = ((int64_t)kb0 * kPackK) / p.inner;
+    int64_t i = ((int64_t)kb0 * kPackK) - o * p.inner;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % Cfg::kStages;
+      mbar_wait(&bar_empty[s], ((uint32_t)(kb / Cfg::kStages) & 1u) ^ 1u);
+      uint8_t *dst = smem + (size_t)s * Cfg::kStageBytes + plane + (uint32_t)lane * 16u;  // (jj * 8 + r) * 16 == lane * 16
+      const float *src = src0 + o * img + i;
+#pragma unroll 4
+      for (int g = 0; g < groups; ++g) cp_async16(dst + (uint32_t)g * 512u, src + g * gstride);
+      cp_async_arrive_noinc(&bar_raw[s]);
+      i += kPackK;
+      if (i >= p.inner) {
+        i = 0;
+        ++o;
+      }
+    }
+  } else if (warp >= 11) {
+    // ------------------------------------------------------------------ converters
+    constexpr int P = 16;                        // panels per warp per k-block (2 * BN / 8 / kTeam)
+    const int cw = warp - 11;
+    const int team = cw / Cfg::kTeam, tw = cw % Cfg::kTeam;
+    const bool idle = team >= Cfg::kTeams;       // BN = 128: the fifth converter warp has no partner
+    const int groups = p.C >> 3;
     float s2[P];
 #pragma unroll
     for (int q = 0; q < P; ++q) s2[q] = 0.f;
     // panel q of this warp: pidx = tw + kTeam * q over [x groups | y groups]
-    auto request = [&](int kb, uint8_t *raw) {  // this lane's 16-byte pieces of k-block kb -> raw slot (cp.async)
-      const int64_t k0 = (int64_t)(kb0 + kb) * kPackK;
-      const int64_t o = k0 / p.inner;
-      const int64_t base = o * img + (k0 - o * p.inner) + (int64_t)r * p.inner + jj * 4;
+    for (int kb = idle ? nkb : team; kb < nkb; kb += Cfg::kTeams) {
+      const int s = kb % Cfg::kStages;
+      const uint32_t ph = (uint32_t)(kb / Cfg::kStages) & 1u;
+      mbar_wait(&bar_raw[s], ph);
+      uint8_t *st = smem + (size_t)s * Cfg::kStageBytes + (uint32_t)lane * 16u;
 #pragma unroll
       for (int q = 0; q < P; ++q) {
         const int pidx = tw + Cfg::kTeam * q;
         if (pidx < 2 * groups) {
           const int opnd = pidx >= groups ? 1 : 0;
-          const int g = pidx - opnd * groups;
-          cp_async16(raw + (uint32_t)pidx * 512u + (uint32_t)lane * 16u, (opnd ? p.y : p.x) + base + g * gstride);
+          uint8_t *hp = st + (opnd ? 2 * Cfg::kPlaneBytes : 0) + (uint32_t)(pidx - opnd * groups) * 512u;
+          const float4 v = *reinterpret_cast<const float4 *>(hp);
+          float4 l;  // x - trunc_tf32(x): exact, at most 13 significant bits
+          l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          *reinterpret_cast<float4 *>(hp + Cfg::kPlaneBytes) = l;
+          s2[q] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2[q]))));
         }
       }
-      cp_async_commit();
-    };
-    auto convert = [&](const float4 &v, int q) {
-      const int pidx = tw + Cfg::kTeam * q;
-      const int opnd = pidx >= groups ? 1 : 0;
-      const int g = pidx - opnd * groups;
-      uint8_t *dst = st + (opnd ? 2 * Cfg::kPlaneBytes : 0) + (uint32_t)g * 512u + (uint32_t)(jj * 8 + r) * 16u;
-      float4 h, l;
-      h.x = to_tf32(v.x); l.x = to_tf32(v.x - h.x);
-      h.y = to_tf32(v.y); l.y = to_tf32(v.y - h.y);
-      h.z = to_tf32(v.z); l.z = to_tf32(v.z - h.z);
-      h.w = to_tf32(v.w); l.w = to_tf32(v.w - h.w);
-      *reinterpret_cast<float4 *>(dst) = h;
-      *reinterpret_cast<float4 *>(dst + Cfg::kPlaneBytes) = l;
-      s2[q] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2[q]))));
-    };
-    if (!idle) {  // two k-blocks in flight per team; always one commit group per slot
-      if (team < nkb) request(team, raw0); else cp_async_commit();
-      if (team + Cfg::kTeams < nkb) request(team + Cfg::kTeams, raw0 + Cfg::kRawBytes); else cp_async_commit();
-    }
-    uint32_t round = 0;
-    for (int kb = idle ? nkb : team; kb < nkb; kb += Cfg::kTeams, ++round) {
-      uint8_t *raw = raw0 + (round & 1u) * Cfg::kRawBytes;
-      cp_async_wait<1>();                                   // all but the newest group: k-block kb has landed
-      mbar_wait(&bar_empty[team], (round & 1u) ^ 1u);       // the MMAs of the stage's previous k-block retired
-      float4 v[P / 2];
-#pragma unroll
-      for (int q = 0; q < P / 2; ++q)
-        if (tw + Cfg::kTeam * q < 2 * groups)
-          v[q] = *reinterpret_cast<const float4 *>(raw + (uint32_t)(tw + Cfg::kTeam * q) * 512u + (uint32_t)lane * 16u);
-#pragma unroll
-      for (int q = 0; q < P / 2; ++q)
-        if (tw + Cfg::kTeam * q < 2 * groups) convert(v[q], q);
-#pragma unroll
-      for (int q = P / 2; q < P; ++q)
-        if (tw + Cfg::kTeam * q < 2 * groups)
-          v[q - P / 2] = *reinterpret_cast<const float4 *>(raw + (uint32_t)(tw + Cfg::kTeam * q) * 512u + (uint32_t)lane * 16u);
-#pragma unroll
-      for (int q = P / 2; q < P; ++q)
-        if (tw + Cfg::kTeam * q < 2 * groups) convert(v[q - P / 2], q);
-      // generic-proxy stores -> visible to tcgen05.mma (async proxy).  The fence compiles to
-      // MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and the MEMBAR also waits for this thread's outstanding
-      // cp.async, so the next request is issued AFTER it (ncu: with the request in front, every
-      // k-block paid a full memory round trip before its barrier arrive).
-      fence_proxy_async_smem();
+      fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma (async proxy)
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_full[team]);
-      // this raw slot is consumed: the team's k-block after next streams into it
-      if (kb + 2 * Cfg::kTeams < nkb) request(kb + 2 * Cfg::kTeams, raw); else cp_async_commit();
+      if (lane == 0) mbar_arrive(&bar_full[s]);
     }
     // row sums of squares: the 4 jj lanes of a row, then one fp64 atomic per row
     if (p.qa != nullptr && !idle) {
@@ -187,8 +173,7 @@ __global__ void __launch_bounds__(512, 1) gram_direct_kernel(DirectProblem p, in
         const int pidx = tw + Cfg::kTeam * q;
         if (pidx < 2 * groups && lane < 8) {
           const int opnd = pidx >= groups ? 1 : 0;
-          const int g = pidx - opnd * groups;
-          atomicAdd((opnd ? p.qb : p.qa) + g * 8 + lane, (double)v);
+          atomicAdd((opnd ? p.qb : p.qa) + (pidx - opnd * groups) * 8 + lane, (double)v);
         }
       }
     }
