@@ -192,6 +192,21 @@ def cpu_baseline(args, spec):
 
 
 def run_b200(args):
+    # rank 0 prints ONE JSON line on stdout: anything else that writes to fd 1 (NCCL's version banner,
+    # library chatter) is sent to stderr for the duration of the run
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _run_b200(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if line is not None:
+        print(line, flush=True)
+
+
+def _run_b200(args):
     import torch
     import torch.distributed as dist
 
@@ -407,13 +422,13 @@ def run_b200(args):
 
     if rank != 0:  # rank 0 reports
         dist.destroy_process_group()
-        return
+        return None
 
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N=1 only
         out["cpu_baseline"] = cpu_baseline(args, spec)
-    print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    return json.dumps(out)
 
 
 if __name__ == "__main__":
