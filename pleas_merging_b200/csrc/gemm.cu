@@ -9,7 +9,11 @@
 // so the producer needs no tensor map: one cp.async.bulk per plane per stage lands a tile in
 // shared memory already in the K-major no-swizzle core-matrix order tcgen05.mma reads.
 //
-// Warp roles (192 threads, 2 CTAs/SM):  warp 0 = bulk-copy producer, warp 1 = TMEM owner +
+// Two kernels share this file.  gemm3xtf32_v2_kernel (further down) is the product path: persistent
+// CTAs, ping-pong TMEM accumulators, in-kernel promotion.  gemm3xtf32_kernel (v1, kept for A/B runs
+// and as the chain-length experiment's subject) is described first.
+//
+// v1 warp roles (192 threads, 2 CTAs/SM):  warp 0 = bulk-copy producer, warp 1 = TMEM owner +
 // single-thread MMA issuer (3 MMAs per 8-wide k-step: lo·hi, hi·lo, hi·hi, fp32 accumulate in
 // TMEM), warps 2-5 = epilogue (tcgen05.ld -> global partial tile).  smem ring of kStages
 // stages; mbarrier full/empty per stage; tcgen05.commit releases stages and publishes the
