@@ -386,13 +386,34 @@ def gen_eval(ref):
     print("eval_golden.pt written:", {k: [len(t) for t in v] for k, v in G.items() if k.endswith("fc_perm")})
 
 
+def gen_wmp(ref):
+    """weight_matching_partial (pleas/methods/partial_matching.py:337-463) on the tiny pair:
+    returned permutation and both rewritten state dicts (inplace=True) -> wmp_golden.pt."""
+    G = {}
+    m1, m2 = tinynet.make_pair(12, 10)
+    spec = ref.compiler.get_permutation_spec(m1, ((1, 3, 16, 16),))
+    keys = list(spec.keys())
+    cases = {"r05": {k: 0.5 for k in keys}, "r025": {k: 0.25 for k in keys},
+             "mixed": {k: [0.5, 1.0, 0.25, 0.75][i % 4] for i, k in enumerate(keys)}}
+    for name, ratios in cases.items():
+        sa = {k: v.clone() for k, v in m1.state_dict().items()}
+        sb = {k: v.clone() for k, v in m2.state_dict().items()}
+        perm = ref.pm.weight_matching_partial(spec, sa, sb, ratios, max_iter=20, inplace=True, verbose=False, seed=0)
+        G[f"{name}/ratios"] = {axis_key(k): v for k, v in ratios.items()}
+        G[f"{name}/perm"] = {axis_key(k): v.clone() for k, v in perm.items()}
+        G[f"{name}/state_a"] = {k: v.clone() for k, v in sa.items()}
+        G[f"{name}/state_b"] = {k: v.clone() for k, v in sb.items()}
+        print("wmp", name, {k: tuple(v.shape) for k, v in list(sa.items())[:2]})
+    torch.save(G, os.path.join(GOLD, "wmp_golden.pt"))
+
+
 def main():
     if os.environ.get("PYTHONHASHSEED") != "0":
         sys.exit("run with PYTHONHASHSEED=0 (pins the reference's set iteration order)")
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     ref = load_reference()
-    which = sys.argv[1:] or ["lap", "specs", "tiny", "rn18", "budget", "eval"]
+    which = sys.argv[1:] or ["lap", "specs", "tiny", "rn18", "budget", "eval", "wmp"]
     if "lap" in which:
         gen_lap()
     if "specs" in which:
@@ -405,6 +426,8 @@ def main():
         gen_budget(ref)
     if "eval" in which:
         gen_eval(ref)
+    if "wmp" in which:
+        gen_wmp(ref)
 
 
 if __name__ == "__main__":

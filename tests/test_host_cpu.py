@@ -351,3 +351,43 @@ def test_qp_ratios_feasible_and_near_optimal():
     # extremes
     assert all(v == 1.0 for v in qp_ratios(spec, terms, 2.5, {k: 1.0 for k in keys}).values())
     assert all(v == 0.0 for v in qp_ratios(spec, terms, 1.0, {k: 1.0 for k in keys}).values())
+
+
+@pytest.mark.parametrize("name", ["r05", "r025", "mixed"])
+def test_weight_matching_partial_equals_reference(name):
+    """weight_matching_partial / apply_perm_with_padding / remove_zero_block
+    (partial_matching.py:260-463) reproduce the reference's permutation and BOTH rewritten state
+    dicts on the tiny pair.  The host logic is device-agnostic, so it runs here with CPU plug-ins in
+    the two operator slots (the oracle's SciPy-identical LAP and a torch matmul); the product
+    defaults are the library's GPU LAP and tcgen05 Gram."""
+    import numpy as np
+
+    import pleas_merging_b200 as P
+    from oracle import ref_oracle as O
+    from oracle import tinynet
+    from pleas_merging_b200.methods.weight_matching_partial import weight_matching_partial
+
+    G = torch.load(os.path.join(ROOT, "tests", "golden", "wmp_golden.pt"), weights_only=False)
+
+    def cpu_lsa(A, maximize=True):
+        return torch.from_numpy(np.asarray(O.solve_lsa(A.numpy(), maximize)[0], dtype=np.int64))
+
+    def cpu_cross(x, y, a):
+        x = torch.movedim(x, a, 0).reshape(x.shape[a], -1)
+        y = torch.movedim(y, a, 0).reshape(y.shape[a], -1)
+        return x @ y.T
+
+    m1, m2 = tinynet.make_pair(12, 10)
+    spec = P.get_permutation_spec(m1, ((1, 3, 16, 16),))
+    ratios = {k: G[f"{name}/ratios"][f"{k.key}:{k.axis}"] for k in spec}
+    sa = {k: v.clone() for k, v in m1.state_dict().items()}
+    sb = {k: v.clone() for k, v in m2.state_dict().items()}
+    perm = weight_matching_partial(spec, sa, sb, ratios, max_iter=20, inplace=True, verbose=False, seed=0,
+                                   lsa_solver=cpu_lsa, cross_weights=cpu_cross)
+    for k in spec:
+        assert torch.equal(perm[k], G[f"{name}/perm"][f"{k.key}:{k.axis}"]), k
+    for tag, mine in (("state_a", sa), ("state_b", sb)):
+        gold = G[f"{name}/{tag}"]
+        assert set(mine) == set(gold)
+        for k, v in gold.items():
+            assert mine[k].shape == v.shape and torch.equal(mine[k], v), (tag, k)

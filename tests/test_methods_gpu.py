@@ -532,3 +532,27 @@ def test_eval_perm_model_recovers_source_predictions(ratio):
     for idx, src in enumerate((m1, m2)):
         acc = E.eval_perm_model(backbone, src.fc, data, 10, fc_perm, idx)
         assert float(acc) == 1.0, (ratio, idx, float(acc))
+
+
+@pytest.mark.parametrize("name", ["r05", "mixed"])
+def test_weight_matching_partial_gpu_equals_reference(name):
+    """weight_matching_partial with the product plug-ins (GPU LAP, tcgen05 Gram) on CUDA state dicts
+    reproduces the reference's permutation and expanded state dicts (tests/golden/wmp_golden.pt)."""
+    import os
+
+    from conftest import GOLDEN
+    from pleas_merging_b200.methods import weight_matching_partial
+
+    P = _pkg()
+    G = torch.load(os.path.join(GOLDEN, "wmp_golden.pt"), weights_only=False)
+    m1, m2 = tinynet.make_pair(12, 10)
+    spec = P.get_permutation_spec(m1, ((1, 3, 16, 16),))
+    ratios = {k: G[f"{name}/ratios"][key_str(k)] for k in spec}
+    sa = {k: v.clone().cuda() for k, v in m1.state_dict().items()}
+    sb = {k: v.clone().cuda() for k, v in m2.state_dict().items()}
+    perm = weight_matching_partial(spec, sa, sb, ratios, max_iter=20, inplace=True, verbose=False, seed=0)
+    for k in spec:
+        assert torch.equal(perm[k].cpu(), G[f"{name}/perm"][key_str(k)]), k
+    for tag, mine in (("state_a", sa), ("state_b", sb)):
+        for k, v in G[f"{name}/{tag}"].items():
+            assert torch.equal(mine[k].cpu(), v), (tag, k)  # gathers and zero blocks only: bit exact
