@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(192, 2) gemm3xtf32_kernel(const PlbGemmProblem
       const uint32_t phase = (uint32_t)(i / Cfg::kStages) & 1u;
       mbar_wait(&bar_full[s], phase);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {  // elect.sync: the compiler keeps descriptors in uniform registers (no per-MMA R2UR loop)
         const uint32_t st = smem_u32(smem + (size_t)s * Cfg::kStageBytes);
 #pragma unroll
         for (int ks = 0; ks < kPackK / 8; ++ks) {
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(320, 1) gemm3xtf32_v2_kernel(const PlbGemmProb
           const int s = it % Cfg::kStages;
           mbar_wait(&bar_full[s], (it / Cfg::kStages) & 1u);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {  // elect.sync: the compiler keeps descriptors in uniform registers (no per-MMA R2UR loop)
             const uint32_t st = smem_u32(smem + (size_t)s * Cfg::kStageBytes);
 #pragma unroll
             for (int ks = 0; ks < kPackK / 8; ++ks) {

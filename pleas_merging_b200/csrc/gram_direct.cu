@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(512, 1) gram_direct_kernel(DirectProblem p, in
         const int s = it % Cfg::kStages;
         mbar_wait(&bar_full[s], (it / Cfg::kStages) & 1u);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {  // elect.sync: the compiler keeps descriptors in uniform registers (no per-MMA R2UR loop)
           const uint32_t st = smem_u32(smem + (size_t)s * Cfg::kStageBytes);
 #pragma unroll
           for (int ks = 0; ks < kPackK / 8; ++ks) {
