@@ -412,3 +412,40 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def test_built_library_is_sm100a_native_sass():
+    """The in-tree library really is tcgen05 / TMA / redux code for sm_100a (cuobjdump -sass, no GPU
+    needed): UTCHMMA + LDTM (TMEM loads) + UBLKCP (bulk copies) in the GEMM, UTCHMMA + LDGSTS in the
+    fused narrow-tap kernel, REDUX in the LAP kernel — and the MMAs of a k-block are issued back to
+    back from uniform registers (no per-MMA ELECT/R2UR uniformisation loop)."""
+    import shutil
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    from pleas_merging_b200 import build
+
+    lib = build.build()
+    sass = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True, timeout=300).stdout
+    assert "sm_100a" in sass
+    funcs = {}
+    name = None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+            funcs[name] = []
+        elif name is not None:
+            funcs[name].append(line)
+
+    def body(sub):
+        hits = [n for n in funcs if sub in n]
+        assert hits, sub
+        return {n: "\n".join(funcs[n]) for n in hits}
+
+    for n, b in body("gemm3xtf32_v2_kernel").items():
+        assert "UTCHMMA" in b and "LDTM" in b and "UBLKCP" in b and "UTCBAR" in b, n
+        assert b.count("BRA.U.ANY") <= 6, (n, b.count("BRA.U.ANY"))  # was 24 with the lane == 0 guard
+    for n, b in body("gram_direct_kernel").items():
+        assert "UTCHMMA" in b and "LDTM" in b and "LDGSTS" in b, n
+    assert all("REDUX" in b for b in body("lap_kernel_v2").values())
