@@ -449,3 +449,23 @@ def test_built_library_is_sm100a_native_sass():
     for n, b in body("gram_direct_kernel").items():
         assert "UTCHMMA" in b and "LDTM" in b and "LDGSTS" in b, n
     assert all("REDUX" in b for b in body("lap_kernel_v2").values())
+
+
+def test_parallel_helpers_single_process_edges():
+    """No process group: the collectives are no-ops, every item belongs to rank 0, and a sharder
+    over an empty / short loader yields what exists."""
+    from pleas_merging_b200 import parallel
+
+    assert parallel.world() == (0, 1)
+    assert parallel.assign_owners([], 4) == []
+    assert parallel.assign_owners([3.0, 1.0, 2.0], 1) == [0, 0, 0]
+    assert parallel.assign_owners([1.0, 1.0, 1.0, 1.0], 4) == [0, 1, 2, 3]  # ties: lowest rank, input order
+    flat = torch.arange(6.0)
+    assert parallel.reduce_to_owners_(flat, [(0, 3), (3, 3)], [0, 0]) is flat and torch.equal(flat, torch.arange(6.0))
+    assert parallel.allreduce_sum_(flat) is flat
+    sh = parallel.BatchSharder([], 5)
+    assert list(sh) == [] and sh.total == 0 and not sh.owns_last()
+    sh = parallel.BatchSharder([(torch.zeros(1), 0)] * 2, 5)  # loader shorter than num_batches
+    assert [i for i, _ in sh] == [0, 1] and sh.total == 2 and sh.owns_last()
+    sh = parallel.BatchSharder([(torch.zeros(1), 0)] * 7, 5, rank=1, world_size=2)
+    assert [i for i, _ in sh] == [1, 3] and sh.total == 5 and not sh.owns_last()
