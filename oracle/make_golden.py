@@ -407,13 +407,54 @@ def gen_wmp(ref):
     torch.save(G, os.path.join(GOLD, "wmp_golden.pt"))
 
 
+def gen_api(ref):
+    """Positional parameter names and plain default values of the reference's public functions on the
+    path (the drop-in contract) -> api_signatures.json."""
+    import inspect
+
+    funcs = {
+        "get_permutation_spec": ref.compiler.get_permutation_spec,
+        "activation_matching": ref.am.activation_matching, "cross_features_cdist": ref.am.cross_features_cdist,
+        "cross_features_inner_product": ref.am.cross_features_inner_product,
+        "build_cross_module": ref.am.build_cross_module, "compute_matching_costs": ref.am.compute_matching_costs,
+        "weight_matching": ref.wm.weight_matching, "partial_merge": ref.pm.partial_merge,
+        "get_blocks": ref.pm.get_blocks, "expand_ratios": ref.pm.expand_ratios,
+        "build_partial_merge_model": ref.pm.build_partial_merge_model,
+        "partial_merge_flops": ref.pm.partial_merge_flops, "qp_ratios": ref.pm.qp_ratios,
+        "weight_matching_partial": ref.pm.weight_matching_partial,
+        "apply_perm_with_padding": ref.pm.apply_perm_with_padding, "remove_zero_block": ref.pm.remove_zero_block,
+        "train": ref.pl.train, "get_fc_perm": ref.pl.get_fc_perm,
+        "permute_final_features": ref.pl.permute_final_features, "eval_perm_model": ref.pl.eval_perm_model,
+        "eval_whole_model": ref.pl.eval_whole_model, "train_eval_linear_probe": ref.pl.train_eval_linear_probe,
+        "scipy_solve_lsa": ref.solvers.scipy_solve_lsa, "apply_perm": ref.utils.apply_perm,
+        "count_linear_flops": ref.utils.count_linear_flops,
+    }
+    out = {}
+    for name, fn in funcs.items():
+        params = []
+        for prm in inspect.signature(fn).parameters.values():
+            d = prm.default
+            if d is inspect.Parameter.empty:
+                params.append([prm.name, "<required>"])
+            elif isinstance(d, (int, float, str, bool, type(None))):
+                params.append([prm.name, d])
+            elif isinstance(d, tuple):
+                params.append([prm.name, list(d)])
+            else:
+                params.append([prm.name, "<callable>"])
+        out[name] = params
+    with open(os.path.join(GOLD, "api_signatures.json"), "w") as f:
+        json.dump(out, f, indent=0)
+    print("api_signatures:", len(out), "functions")
+
+
 def main():
     if os.environ.get("PYTHONHASHSEED") != "0":
         sys.exit("run with PYTHONHASHSEED=0 (pins the reference's set iteration order)")
     os.makedirs(GOLD, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
     ref = load_reference()
-    which = sys.argv[1:] or ["lap", "specs", "tiny", "rn18", "budget", "eval", "wmp"]
+    which = sys.argv[1:] or ["lap", "specs", "tiny", "rn18", "budget", "eval", "wmp", "api"]
     if "lap" in which:
         gen_lap()
     if "specs" in which:
@@ -428,6 +469,8 @@ def main():
         gen_eval(ref)
     if "wmp" in which:
         gen_wmp(ref)
+    if "api" in which:
+        gen_api(ref)
 
 
 if __name__ == "__main__":

@@ -17,6 +17,7 @@ import torch
 from torch.nn import Module
 
 from .. import ops
+from ..core.solvers import b200_solve_lsa
 from ..core.utils import Axis, Permutation, PermutationSpec, set_attr
 
 Ratios = Union[float, Dict[Axis, float]]
@@ -36,7 +37,7 @@ def _device_of(costs):
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def get_blocks(spec: PermutationSpec, perm: Permutation, costs, ratios: Ratios, lsa_solver=None):
+def get_blocks(spec: PermutationSpec, perm: Permutation, costs, ratios: Ratios, lsa_solver=b200_solve_lsa):
     """{group key: (Q[mask], P[mask], Q[~mask], P[~mask])} as int64 CUDA tensors (reference
     :47-89): ``mask = c >= torch.quantile(c, ratio)`` over the matched costs ``c_i = C[i, P_i]``;
     a ratio within 1e-3 of 1.0 forces the identity permutation."""

@@ -469,3 +469,35 @@ def test_parallel_helpers_single_process_edges():
     assert [i for i, _ in sh] == [0, 1] and sh.total == 2 and sh.owns_last()
     sh = parallel.BatchSharder([(torch.zeros(1), 0)] * 7, 5, rank=1, world_size=2)
     assert [i for i, _ in sh] == [1, 3] and sh.total == 5 and not sh.owns_last()
+
+
+def test_public_api_signatures_match_the_reference():
+    """Drop-in contract: every public function of the reference on the merge path exists here with
+    the same positional parameter names in the same order and the same plain default values
+    (tests/golden/api_signatures.json, generated from the unmodified reference); this package may
+    only ADD keyword parameters after them."""
+    import inspect
+    import json
+
+    import pleas_merging_b200 as P
+    from pleas_merging_b200 import methods as M
+    from pleas_merging_b200.core import solvers, utils
+
+    with open(os.path.join(ROOT, "tests", "golden", "api_signatures.json")) as f:
+        gold = json.load(f)
+    assert len(gold) >= 25
+    for name, params in gold.items():
+        fn = next((getattr(m, name) for m in (M, P, solvers, utils) if hasattr(m, name)), None)
+        assert fn is not None, f"{name} is missing"
+        mine = list(inspect.signature(fn).parameters.values())
+        assert [p.name for p in mine[:len(params)]] == [a for a, _ in params], name
+        for prm, (_, default) in zip(mine, params):
+            if default == "<required>":
+                assert prm.default is inspect.Parameter.empty, (name, prm.name)
+            elif default == "<callable>":
+                assert callable(prm.default), (name, prm.name)
+            else:
+                got = list(prm.default) if isinstance(prm.default, tuple) else prm.default
+                assert got == default, (name, prm.name, got, default)
+        for extra in mine[len(params):]:  # additions must not break positional calls written for the reference
+            assert extra.default is not inspect.Parameter.empty or extra.kind is extra.KEYWORD_ONLY, (name, extra.name)
