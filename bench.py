@@ -350,15 +350,15 @@ def _run_b200(args):
                     "dram read (102.8 MB = the operand) + write (153.1 MB; the rest of the 205.5 MB of planes is still in L2 "
                     "when the launch ends) of the C=64, K=401408 launch in profiles/pack_r01_raw.csv"}
     # fused narrow-tap kernel (C <= 128): HBM-bound, reads each fp32 activation once
-    d_ms = sum(a.elapsed_time(b) for a, b, _, _ in direct_timer)
+    d_ms = sum(t[0].elapsed_time(t[1]) for t in direct_timer)
     if d_ms > 0:
-        d_bytes = sum(n for _, _, n, _ in direct_timer)
+        d_bytes = sum(t[2] for t in direct_timer)
         gbs = d_bytes / (d_ms / 1e3) / 1e9
         out["roofline_narrow_taps"] = {
             "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
             "traffic": None, "kernel": "gram_direct_kernel", "kernel_ms_per_step": d_ms / min(K, 5),
             "launches_per_step": len(direct_timer) // min(K, 5),
-            "algorithmic_tflops": sum(f for _, _, _, f in direct_timer) / (d_ms / 1e3) / 1e12,
+            "algorithmic_tflops": sum(t[3] for t in direct_timer) / (d_ms / 1e3) / 1e12,
             "note": "achieved = algorithmic bytes (both fp32 activations of the tap, read once: 2*C*K*4) / summed "
                     "CUDA-event time of the launches of the same un-captured steps"}
     out["clocks"] = clocks

@@ -98,6 +98,26 @@ int plb_gram_direct(const float *x, const float *y, int64_t outer, int64_t C, in
                     float *partial, int32_t splits, int32_t chain_kb, double *row_sumsq_x,
                     double *row_sumsq_y, void *stream);
 
+/* TMA-fed fused cross-Gram of one tap of ANY width, straight from the two fp32 activations
+ * x, y [outer][C][inner] (inner % 4 == 0: the tensor is then a legal 3-D tensor map): no packed
+ * planes.  TMA boxes of (rows x 32 k) land in 128-byte-swizzled shared memory, converter warps
+ * derive the tf32 lo plane in place, the contraction is the 3xTF32 tcgen05 pipeline with in-kernel
+ * promotion.  C <= 128: one CTA per work item (tile 128 x 64 / 128 x 128); C > 128: a CTA PAIR
+ * (cluster of 2, tcgen05 cta_group::2) per 256 x 256 tile.  Writes partial[s] = X[:, Ks] Y[:, Ks]^T
+ * for `splits` K ranges as [splits][ld_m][ld_n] fp32 (geometry from plb_gram_tma_geometry), to be
+ * reduced by plb_cross_finalize, and adds the rows' sums of squares to the fp64 vectors (atomics:
+ * zero them first; both or neither).  chain_kb = 16-wide k-blocks per accumulation chain (4).
+ * Replaces cross_features_inner_product / cross_features_cdist (activation_matching.py:14-46)
+ * together with its movedim/reshape copy (:26-27, 44-45). */
+int plb_gram_tma(const float *x, const float *y, int64_t outer, int64_t C, int64_t inner,
+                 float *partial, int32_t splits, int32_t chain_kb, double *row_sumsq_x,
+                 double *row_sumsq_y, void *stream);
+
+/* Host-only: tiling plb_gram_tma uses for C rows: CTAs per work item (1 or 2), output tiles and the
+ * padded leading dimensions of the partial tiles. */
+int plb_gram_tma_geometry(int64_t C, int32_t *cta_group, int32_t *m_tiles, int32_t *n_tiles,
+                          int32_t *ld_m, int32_t *ld_n);
+
 /* ---------------------------------------------------------------------------------------
  * 3xTF32 tcgen05 GEMM over packed planes:  partial[s] = A[:, Ks] B[:, Ks]^T per K split s.
  * One table entry per problem; problems sharing a tile width are launched together
@@ -177,8 +197,9 @@ int plb_gather_axis(const float *in, float *out, int64_t outer, int64_t n, int64
 /* perm composition (weight_matching.py:85): out[i] = a[b[i]] on int64. */
 int plb_compose_perm(const int64_t *a, const int64_t *b, int64_t *out, int64_t n, void *stream);
 
-/* weight_matching's progress test (weight_matching.py:80-81): *flag |= (sum_i A[i,P_i] >
- * sum_i A[i,i] + 1e-12), sums in fp64 of the fp32 entries. */
+/* weight_matching's progress test (weight_matching.py:80-81): *flag |= (newL > oldL + 1e-12) with
+ * newL = sum_i A[i,P_i], oldL = sum_i A[i,i] compared as FLOAT32 values like the reference's torch
+ * sums (each sum is formed in fp64 and rounded once); *gain (optional) = newL - oldL in fp64. */
 int plb_wm_progress(const float *A, int64_t ld, const int64_t *P, int32_t n, int32_t *flag,
                     double *gain, void *stream);
 

@@ -31,6 +31,9 @@ _SIGNATURES = {
     "plb_pack_split_pair": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32,
                                            c_ptr, c_ptr, c_ptr]),
     "plb_gram_direct": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
+    "plb_gram_tma": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
+    "plb_gram_tma_geometry": (ctypes.c_int, [c_i64, ctypes.POINTER(c_i32), ctypes.POINTER(c_i32),
+                                             ctypes.POINTER(c_i32), ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
     "plb_pack_im2col": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
                                        c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_i64, c_i32,
                                        c_ptr, c_ptr, c_i32, c_i32, c_ptr]),
@@ -80,10 +83,39 @@ def check(rc, what):
         raise RuntimeError(f"pleas_merging_b200: {what} failed with status {rc}: {msg}")
 
 
-def stream_ptr():
+def call(name, device, *args):
+    """Invokes the entry point ``name`` for tensors living on ``device``: the launch happens with
+    that device current and on ITS current stream (the C ABI takes raw pointers, so nothing else
+    ties a launch to the tensors' device; a model on cuda:1 while cuda:0 is current must not run on
+    device 0's stream).  The stream handle is appended as the last argument."""
     import torch
 
-    return torch.cuda.current_stream().cuda_stream
+    fn = getattr(lib(), name)
+    if device.index is None or device.index == torch.cuda.current_device():
+        rc = fn(*args, torch.cuda.current_stream().cuda_stream)
+    else:
+        with torch.cuda.device(device):
+            rc = fn(*args, torch.cuda.current_stream(device).cuda_stream)
+    check(rc, name)
+
+
+def stream_ptr(device=None):
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+_SM_COUNT = {}
+
+
+def sm_count(device=None):
+    """Streaming multiprocessors of ``device`` (148 on a B200), cached per device ordinal."""
+    import torch
+
+    idx = torch.cuda.current_device() if device is None or getattr(device, "index", None) is None else device.index
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
 
 
 def ptr(t):

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpleas_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "gram_direct.cu", "pack.cu", "finalize.cu", "lap.cu", "blocks.cu", "chol.cu"]
+SOURCES = ["api.cu", "gemm.cu", "gram_direct.cu", "gram_tma.cu", "pack.cu", "finalize.cu", "lap.cu", "blocks.cu", "chol.cu"]
 
 
 def _stale():

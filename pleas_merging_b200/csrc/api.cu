@@ -3,6 +3,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace plb {
@@ -13,6 +17,45 @@ void set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// Function attributes and the SM count belong to a DEVICE: cached per (kernel, ordinal) so that a
+// process using several GPUs configures each of them (a single `static bool` would only set the
+// > 48 KB dynamic shared-memory limit on the first device used).
+int ensure_dynamic_smem(const void *func, int bytes, const char *name) {
+  static std::mutex mu;
+  static std::map<std::pair<const void *, int>, int> done;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDevice: %s", cudaGetErrorString(e));
+    return (int)e;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(func, dev);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return PLB_OK;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(%s, %d bytes of dynamic shared memory): %s", name, bytes, cudaGetErrorString(e));
+    return (int)e;
+  }
+  done[key] = bytes;
+  return PLB_OK;
+}
+
+int device_sm_count() {
+  static std::mutex mu;
+  static std::map<int, int> sms;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = sms.find(dev);
+  if (it != sms.end()) return it->second;
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  sms[dev] = n;
+  return n;
 }
 }  // namespace plb
 

@@ -11,6 +11,9 @@
 namespace plb {
 
 void set_error(const char *fmt, ...);  // api.cu
+// per (kernel, device) cudaFuncAttributeMaxDynamicSharedMemorySize; returns PLB_OK or the cudaError_t
+int ensure_dynamic_smem(const void *func, int bytes, const char *name);  // api.cu
+int device_sm_count();  // SMs of the current device, cached per ordinal (api.cu)
 
 #define PLB_REQUIRE(cond, code, ...)  \
   do {                                \

@@ -403,19 +403,10 @@ __global__ void __launch_bounds__(256) gemm_simt_ref_kernel(const PlbGemmProblem
 
 template <int BN>
 static int launch_gemm_v2(const PlbGemmProblem *probs, int nprob, int total_items, int chain_kb, cudaStream_t stream) {
-  static bool configured = false;
-  static int num_sms = 148;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm3xtf32_v2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg2<BN>::kSmemBytes);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(gemm3xtf32_v2_kernel<%d>): %s", BN, cudaGetErrorString(e));
-      return (int)e;
-    }
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
-  }
+  if (int rc = ensure_dynamic_smem((const void *)gemm3xtf32_v2_kernel<BN>, GemmCfg2<BN>::kSmemBytes,
+                                   "gemm3xtf32_v2_kernel"))
+    return rc;
+  const int num_sms = device_sm_count();
   const int grid = total_items < num_sms ? total_items : num_sms;
   gemm3xtf32_v2_kernel<BN><<<grid, GemmCfg2<BN>::kThreads, GemmCfg2<BN>::kSmemBytes, stream>>>(probs, nprob,
                                                                                               total_items, chain_kb);
@@ -429,16 +420,8 @@ static int launch_gemm(const PlbGemmProblem *probs, int nprob, int total_ctas, i
     gemm_simt_ref_kernel<BN><<<total_ctas, 256, 0, stream>>>(probs, nprob);
     return launch_status("gemm_simt_ref_kernel");
   }
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm3xtf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GemmCfg<BN>::kSmemBytes);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(gemm3xtf32_kernel<%d>): %s", BN, cudaGetErrorString(e));
-      return (int)e;
-    }
-    configured = true;
-  }
+  if (int rc = ensure_dynamic_smem((const void *)gemm3xtf32_kernel<BN>, GemmCfg<BN>::kSmemBytes, "gemm3xtf32_kernel"))
+    return rc;
   gemm3xtf32_kernel<BN><<<total_ctas, GemmCfg<BN>::kThreads, GemmCfg<BN>::kSmemBytes, stream>>>(probs, nprob);
   return launch_status("gemm3xtf32_kernel");
 }

@@ -251,16 +251,9 @@ __global__ void __launch_bounds__(512, 1) gram_direct_kernel(DirectProblem p, in
 
 template <int BN>
 static int launch_direct(const DirectProblem &p, int chain_kb, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gram_direct_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         DirectCfg<BN>::kSmemBytes);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(gram_direct_kernel<%d>): %s", BN, cudaGetErrorString(e));
-      return (int)e;
-    }
-    configured = true;
-  }
+  if (int rc = ensure_dynamic_smem((const void *)gram_direct_kernel<BN>, DirectCfg<BN>::kSmemBytes,
+                                   "gram_direct_kernel"))
+    return rc;
   gram_direct_kernel<BN><<<p.splits, DirectCfg<BN>::kThreads, DirectCfg<BN>::kSmemBytes, stream>>>(p, chain_kb);
   return launch_status("gram_direct_kernel");
 }

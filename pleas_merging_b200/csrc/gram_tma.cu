@@ -1,0 +1,531 @@
+// TMA-fed fused cross-Gram, straight from the fp32 activations:  partial[s] = X[:, Ks] Y[:, Ks]^T.
+//
+// The statistic behind cross_features_inner_product / cross_features_cdist
+// (pleas/methods/activation_matching.py:14-46) is a contraction of two [C, K] views of NCHW
+// activations over K = batch x spatial positions.  An [outer][C][inner] fp32 tensor whose inner
+// extent is a multiple of 4 elements is a legal 3-D tensor map (inner, C, outer), so the operands
+// need no packing pass at all: TMA lands (rows x 32 k) boxes in shared memory in the 128-byte
+// swizzled K-major layout tcgen05.mma reads, converter warps derive the tf32 "lo" plane in place
+// (4 bytes of HBM traffic per element instead of the 20 of pack + packed-plane GEMM), and the
+// contraction is the same 3xTF32 scheme as gemm.cu:
+//     x = hi + lo,  hi = trunc_tf32(x) (the tensor core ignores the 13 low mantissa bits of the raw
+//     fp32 word, so the raw tile IS the hi operand),  lo = rna_tf32(x - hi)  (exact difference,
+//     rounded to nearest so the core's truncation of lo is exact),
+//     X Y^T ~= lo_x hi_y^T + hi_x lo_y^T + hi_x hi_y^T      (fp32 accumulation in TMEM).
+// The tensor core's fp32 accumulator truncates (gemm.cu), so chains are short: the MMA warp
+// ping-pongs between two TMEM accumulators and eight promotion warps drain every finished chain
+// into fp32 registers with round-to-nearest adds.
+//
+// Two shapes of one kernel:
+//   CG = 1, tile 128 x {64,128}   narrow taps (C <= 128; HBM-bound, one output tile, K split
+//                                 over the SMs)
+//   CG = 2, tile 256 x 256        wide taps: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) owns a
+//                                 256 x 256 tile; each CTA stages 128 rows of X and 128 rows of Y,
+//                                 i.e. half the B operand per CTA — what keeps the in-kernel hi/lo
+//                                 split within the SM's shared-memory bandwidth.
+// Persistent: work items (tile, K split) are dealt round-robin to the clusters.
+//
+// Warp roles (384 threads, 1 CTA/SM):
+//   warp 0      TMA producer (one elected lane): two 3-D box loads per stage
+//   warp 1      TMEM owner; in the leader CTA the MMA issuer
+//   warps 2-3   converters: raw tile -> lo tile, row sums of squares, proxy fence, signal the
+//               LEADER's barrier (remote mbarrier arrive for the peer CTA)
+//   warps 4-11  promotion / epilogue (two per TMEM lane quadrant, half the columns each)
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace plb {
+
+// ----------------------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry-point query: no link-time dependency on
+// libcuda (the build box has no driver).
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+constexpr int kBoxK = 32;  // k per TMA box = one 128-byte swizzle row of fp32
+
+// [outer][C][inner] fp32 as a 3-D tensor map (inner, C, outer), boxes of (32 k, box_rows, 1), 128-byte swizzle;
+// out-of-range rows / k read as zeros.
+static int make_operand_map(CUtensorMap *m, const float *base, int64_t outer, int64_t C, int64_t inner,
+                            int box_rows) {
+  EncodeTiledFn enc = encode_tiled();
+  PLB_REQUIRE(enc != nullptr, PLB_EINVAL, "plb_gram_tma: cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)C, (cuuint64_t)outer};
+  cuuint64_t gstride[2] = {(cuuint64_t)inner * 4, (cuuint64_t)inner * (cuuint64_t)C * 4};
+  cuuint32_t box[3] = {(cuuint32_t)kBoxK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PLB_REQUIRE(r == CUDA_SUCCESS, PLB_EINVAL, "plb_gram_tma: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return PLB_OK;
+}
+
+// ----------------------------------------------------------------------------- PTX (cluster / cta_group::2 forms)
+template <int CG>
+__device__ __forceinline__ void tmem_alloc_cg(uint32_t *smem_result, uint32_t cols) {
+  if (CG == 1)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "r"(cols)
+                 : "memory");
+  else
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "r"(cols)
+                 : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tmem_relinquish_cg() {
+  if (CG == 1)
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  else
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc_cg(uint32_t taddr, uint32_t cols) {
+  if (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void umma_tf32_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  if (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier (same shared-memory offset in every CTA of the pair) when all MMAs issued so far retired
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint64_t *bar) {
+  if (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+  else
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Arrive on the barrier at this shared-memory offset in the cluster's rank-0 CTA (the MMA leader).  Default
+// semantics (release at CTA scope), as CUTLASS's cluster barriers: the data handed over is read by the tensor
+// core through the async proxy (fence.proxy.async / tcgen05.fence precede the arrive), not by the waiting
+// thread, so no cluster-scope release is needed — that form compiles to MEMBAR.ALL.GPU + ERRBAR per arrive
+// and its acquire counterpart to an L1 invalidate per wait, which made every stage hand-over cost ~1 us.
+template <int CG>
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t *bar) {
+  if (CG == 1) {
+    mbar_arrive(bar);
+  } else {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
+  }
+}
+// Watchdog waits: a broken handshake traps (the launch fails loudly) instead of hanging the GPU.
+constexpr long long kWatchdogClocks = 1ll << 32;  // ~2 s
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > kWatchdogClocks) __trap();
+}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2,
+                                            uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// K-major operand tile with 128-byte swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor): rows are 128 bytes,
+// 8-row groups 1024 bytes apart (SBO), LBO unused for a K extent inside one swizzle row, version 1,
+// layout_type 2 = SWIZZLE_128B.  The tile base is 1024-byte aligned; a k8 step advances the start by 32 bytes.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct TmaGramParams {
+  float *partial;    // [splits][ld_m][ld_n]
+  double *qa, *qb;   // row sums of squares (fp64 atomics) or nullptr
+  int C, inner, boxes_per_image, total_boxes;
+  int m_tiles, n_tiles, splits, total_items;
+  int ld_m, ld_n, chain_boxes;
+};
+
+template <int CG, int TM, int TN>
+struct TmaCfg {
+  static constexpr int kXBytes = TM * 128, kYBytes = TN * 128;
+  static constexpr int kRawBytes = kXBytes + kYBytes;   // what TMA lands per stage and CTA
+  static constexpr int kStageBytes = 2 * kRawBytes;     // [X raw = hi][Y raw = hi][X lo][Y lo]
+  static constexpr int kStages = (192 * 1024) / kStageBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr int kThreads = 384;
+  static constexpr int kConvWarps = 2, kEpiWarps = 8;
+  static constexpr int kMmaM = 128 * CG, kMmaN = TN * CG;
+  static constexpr int kTmemCols = 2 * kMmaN;
+  static constexpr int kCols = kMmaN / 2;               // accumulator columns per promotion warp
+  static constexpr int kChunks = (TM + TN) * 8;         // 16-byte chunks of the raw region
+  static constexpr int kPer = kChunks / (kConvWarps * 32);
+  static_assert(kStages >= 2 && kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "geometry");
+  static_assert(kChunks % (kConvWarps * 32) == 0, "converter mapping");
+};
+
+template <int CG, int TM, int TN>
+__global__ void __launch_bounds__(384, 1) gram_tma_kernel(const __grid_constant__ CUtensorMap tmx,
+                                                          const __grid_constant__ CUtensorMap tmy, TmaGramParams p) {
+  using Cfg = TmaCfg<CG, TM, TN>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_raw[Cfg::kStages];    // TMA -> converters (this CTA)
+  __shared__ uint64_t bar_conv[Cfg::kStages];   // converters of both CTAs -> MMA issuer (leader's copy is used)
+  __shared__ uint64_t bar_empty[Cfg::kStages];  // MMA -> producer (multicast to both CTAs)
+  __shared__ uint64_t bar_acc_full[2];          // MMA -> promotion warps (multicast)
+  __shared__ uint64_t bar_acc_empty[2];         // promotion warps of both CTAs -> MMA issuer (leader's copy)
+  __shared__ uint32_t tmem_base_s;
+
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int cluster_id = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_clusters = (int)gridDim.x / CG;
+  const int tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&bar_raw[s], 1);
+      mbar_init(&bar_conv[s], CG * Cfg::kConvWarps);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bar_acc_full[b], 1);
+      mbar_init(&bar_acc_empty[b], CG * Cfg::kEpiWarps);
+    }
+    fence_mbar_init();
+  } else if (warp == 1) {
+    tmem_alloc_cg<CG>(&tmem_base_s, Cfg::kTmemCols);
+    tmem_relinquish_cg<CG>();
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    uint32_t s = 0, ph = 0;
+    for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+      const int tile = item % tiles, split = item / tiles;
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int box0 = (int)((int64_t)p.total_boxes * split / p.splits);
+      const int nbox = (int)((int64_t)p.total_boxes * (split + 1) / p.splits) - box0;
+      const int row_x = mt * (TM * CG) + (int)rank * TM, row_y = nt * (TN * CG) + (int)rank * TN;
+      int img = box0 / p.boxes_per_image, kb = box0 - img * p.boxes_per_image;
+      for (int i = 0; i < nbox; ++i) {
+        mbar_wait_wd(&bar_empty[s], ph ^ 1u);
+        if (elect_one()) {
+          uint8_t *st = smem + (size_t)s * Cfg::kStageBytes;
+          mbar_arrive_expect_tx(&bar_raw[s], Cfg::kRawBytes);
+          tma_load_3d(st, &tmx, kb * kBoxK, row_x, img, &bar_raw[s]);
+          tma_load_3d(st + Cfg::kXBytes, &tmy, kb * kBoxK, row_y, img, &bar_raw[s]);
+        }
+        __syncwarp();
+        if (++kb == p.boxes_per_image) {
+          kb = 0;
+          ++img;
+        }
+        if (++s == Cfg::kStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(Cfg::kMmaM, Cfg::kMmaN);
+      const uint32_t smem_base = smem_u32(smem);
+      uint32_t s = 0, ph = 0, chain = 0;
+      for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+        const int split = item / tiles;
+        const int box0 = (int)((int64_t)p.total_boxes * split / p.splits);
+        const int nbox = (int)((int64_t)p.total_boxes * (split + 1) / p.splits) - box0;
+        int kb = box0 % p.boxes_per_image;
+        for (int b0 = 0; b0 < nbox; b0 += p.chain_boxes, ++chain) {
+          const uint32_t buf = chain & 1u;
+          mbar_wait_wd(&bar_acc_empty[buf], ((chain >> 1) & 1u) ^ 1u);  // both CTAs drained this buffer
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * Cfg::kMmaN;
+          const int b1 = min(nbox, b0 + p.chain_boxes);
+          for (int b = b0; b < b1; ++b) {
+            mbar_wait_wd(&bar_conv[s], ph);
+            tc_fence_after();
+            const int valid = min(kBoxK, p.inner - kb * kBoxK);  // k beyond the image's extent is TMA zero fill
+            const int nk8 = (valid + 7) >> 3;
+            if (elect_one()) {
+              const uint32_t st = smem_base + s * Cfg::kStageBytes;
+#pragma unroll
+              for (int j = 0; j < kBoxK / 8; ++j) {
+                if (j < nk8) {
+                  const uint64_t a_hi = umma_desc_sw128(st + 32 * j);
+                  const uint64_t b_hi = umma_desc_sw128(st + Cfg::kXBytes + 32 * j);
+                  const uint64_t a_lo = umma_desc_sw128(st + Cfg::kRawBytes + 32 * j);
+                  const uint64_t b_lo = umma_desc_sw128(st + Cfg::kRawBytes + Cfg::kXBytes + 32 * j);
+                  umma_tf32_cg<CG>(d_tmem, a_lo, b_hi, idesc, (b > b0 || j > 0) ? 1u : 0u);
+                  umma_tf32_cg<CG>(d_tmem, a_hi, b_lo, idesc, 1u);
+                  umma_tf32_cg<CG>(d_tmem, a_hi, b_hi, idesc, 1u);
+                }
+              }
+              umma_commit_cg<CG>(&bar_empty[s]);
+              if (b == b1 - 1) umma_commit_cg<CG>(&bar_acc_full[buf]);
+            }
+            __syncwarp();
+            if (++kb == p.boxes_per_image) kb = 0;
+            if (++s == Cfg::kStages) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp < 2 + Cfg::kConvWarps) {
+    // ------------------------------------------------------------------ converters
+    const int ct = (warp - 2) * 32 + lane;  // chunk q of this thread: (q * 64 + ct) * 16 bytes into the raw region
+    uint32_t s = 0, ph = 0;
+    for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+      const int tile = item % tiles, split = item / tiles;
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int box0 = (int)((int64_t)p.total_boxes * split / p.splits);
+      const int nbox = (int)((int64_t)p.total_boxes * (split + 1) / p.splits) - box0;
+      float s2[Cfg::kPer];
+#pragma unroll
+      for (int q = 0; q < Cfg::kPer; ++q) s2[q] = 0.f;
+      for (int i = 0; i < nbox; ++i) {
+        mbar_wait_wd(&bar_raw[s], ph);
+        uint8_t *st = smem + (size_t)s * Cfg::kStageBytes + (uint32_t)ct * 16u;
+#pragma unroll
+        for (int q = 0; q < Cfg::kPer; ++q) {
+          const float4 v = *reinterpret_cast<const float4 *>(st + q * 1024);
+          float4 l;  // x - trunc_tf32(x) is exact (<= 13 significant bits); rounded to nearest tf32 (ties away)
+          l.x = __uint_as_float((__float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u)) + 0x1000u) & 0xffffe000u);
+          l.y = __uint_as_float((__float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u)) + 0x1000u) & 0xffffe000u);
+          l.z = __uint_as_float((__float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u)) + 0x1000u) & 0xffffe000u);
+          l.w = __uint_as_float((__float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u)) + 0x1000u) & 0xffffe000u);
+          *reinterpret_cast<float4 *>(st + Cfg::kRawBytes + q * 1024) = l;
+          s2[q] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2[q]))));
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to tcgen05.mma (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader<CG>(&bar_conv[s]);
+        if (++s == Cfg::kStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+      // Row sums of squares: chunk (q * 64 + ct) lies in tile row q * 8 + ct / 8; the 8 lanes of a row combine,
+      // then one fp64 atomic per row.  X rows are counted by the tiles of column 0, Y rows by those of row 0.
+      if (p.qa != nullptr) {
+        const int row_x = mt * (TM * CG) + (int)rank * TM, row_y = nt * (TN * CG) + (int)rank * TN;
+#pragma unroll
+        for (int q = 0; q < Cfg::kPer; ++q) {
+          float v = s2[q];
+          v += __shfl_xor_sync(0xffffffffu, v, 1);
+          v += __shfl_xor_sync(0xffffffffu, v, 2);
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          const int r = q * 8 + (ct >> 3);
+          if ((ct & 7) == 0) {
+            if (r < TM) {
+              if (nt == 0 && row_x + r < p.C) atomicAdd(p.qa + row_x + r, (double)v);
+            } else {
+              if (mt == 0 && row_y + (r - TM) < p.C) atomicAdd(p.qb + row_y + (r - TM), (double)v);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ promotion / epilogue
+    constexpr int COLS = Cfg::kCols;
+    const int q = warp & 3;             // TMEM lane quadrant this warp may read
+    const int half = (warp - 4) >> 2;   // which half of the accumulator columns
+    uint32_t chain = 0;
+    for (int item = cluster_id; item < p.total_items; item += n_clusters) {
+      const int tile = item % tiles, split = item / tiles;
+      const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      const int box0 = (int)((int64_t)p.total_boxes * split / p.splits);
+      const int nbox = (int)((int64_t)p.total_boxes * (split + 1) / p.splits) - box0;
+      float acc[COLS];
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) acc[c] = 0.f;
+      for (int b0 = 0; b0 < nbox; b0 += p.chain_boxes, ++chain) {
+        const uint32_t buf = chain & 1u;
+        mbar_wait_wd(&bar_acc_full[buf], (chain >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * Cfg::kMmaN + half * COLS;
+#pragma unroll
+        for (int c = 0; c < COLS / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t0 + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) acc[c * 32 + e] += __uint_as_float(v[e]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader<CG>(&bar_acc_empty[buf]);
+      }
+      const int64_t row = (int64_t)mt * (128 * CG) + rank * 128 + q * 32 + lane;
+      float4 *d4 = reinterpret_cast<float4 *>(p.partial + ((int64_t)split * p.ld_m + row) * p.ld_n +
+                                               (int64_t)nt * Cfg::kMmaN + half * COLS);
+#pragma unroll
+      for (int e = 0; e < COLS / 4; ++e) d4[e] = make_float4(acc[4 * e], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
+    }
+  }
+
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) tmem_dealloc_cg<CG>(tmem_base, Cfg::kTmemCols);
+}
+
+struct TmaGeometry {
+  int cg, tm, tn, m_tiles, n_tiles, ld_m, ld_n;
+};
+
+static TmaGeometry tma_geometry(int64_t C) {
+  TmaGeometry g;
+  if (C <= 64) {
+    g = {1, 64, 64, 1, 1, 128, 64};
+  } else if (C <= 128) {
+    g = {1, 128, 128, 1, 1, 128, 128};
+  } else {
+    const int t = (int)ceil_div(C, 256);
+    g = {2, 128, 128, t, t, t * 256, t * 256};
+  }
+  return g;
+}
+
+template <int CG, int TM, int TN>
+static int launch_tma(const CUtensorMap &tmx, const CUtensorMap &tmy, const TmaGramParams &p, cudaStream_t stream) {
+  using Cfg = TmaCfg<CG, TM, TN>;
+  if (int rc = ensure_dynamic_smem((const void *)gram_tma_kernel<CG, TM, TN>, Cfg::kSmemBytes, "gram_tma_kernel"))
+    return rc;
+  const int clusters = min(p.total_items, device_sm_count() / CG);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(clusters * CG));
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gram_tma_kernel<CG, TM, TN>, tmx, tmy, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("gram_tma_kernel<%d,%d,%d>: %s", CG, TM, TN, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return launch_status("gram_tma_kernel");
+}
+
+}  // namespace plb
+
+extern "C" int plb_gram_tma_geometry(int64_t C, int32_t *cta_group, int32_t *m_tiles, int32_t *n_tiles,
+                                     int32_t *ld_m, int32_t *ld_n) {
+  using namespace plb;
+  PLB_REQUIRE(C > 0, PLB_EINVAL, "plb_gram_tma_geometry: C must be positive");
+  const TmaGeometry g = tma_geometry(C);
+  if (cta_group) *cta_group = g.cg;
+  if (m_tiles) *m_tiles = g.m_tiles;
+  if (n_tiles) *n_tiles = g.n_tiles;
+  if (ld_m) *ld_m = g.ld_m;
+  if (ld_n) *ld_n = g.ld_n;
+  return PLB_OK;
+}
+
+extern "C" int plb_gram_tma(const float *x, const float *y, int64_t outer, int64_t C, int64_t inner, float *partial,
+                            int32_t splits, int32_t chain_kb, double *row_sumsq_x, double *row_sumsq_y, void *stream) {
+  using namespace plb;
+  PLB_REQUIRE(x && y && partial, PLB_EINVAL, "plb_gram_tma: null pointer");
+  PLB_REQUIRE(outer > 0 && inner > 0 && C > 0, PLB_EINVAL, "plb_gram_tma: empty operand");
+  PLB_REQUIRE(inner % 4 == 0, PLB_ESIZE,
+              "plb_gram_tma: inner must be a multiple of 4 (16-byte tensor-map strides; use the packed path)");
+  PLB_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)partial) & 15) == 0, PLB_EALIGN,
+              "plb_gram_tma: pointers must be 16-byte aligned");
+  PLB_REQUIRE((row_sumsq_x == nullptr) == (row_sumsq_y == nullptr), PLB_EINVAL,
+              "plb_gram_tma: row statistics for both operands or neither");
+  PLB_REQUIRE(outer < (1ll << 31) && C < (1ll << 31) && inner < (1ll << 31), PLB_ESIZE, "plb_gram_tma: extent too large");
+  const int64_t bpi = ceil_div(inner, kBoxK);
+  const int64_t total_boxes = outer * bpi;
+  PLB_REQUIRE(total_boxes < (1ll << 31), PLB_ESIZE, "plb_gram_tma: K too large");
+  PLB_REQUIRE(splits > 0 && splits <= total_boxes && chain_kb > 0, PLB_EINVAL, "plb_gram_tma: bad splits / chain");
+  const TmaGeometry g = tma_geometry(C);
+  CUtensorMap tmx, tmy;
+  if (int rc = make_operand_map(&tmx, x, outer, C, inner, g.tm)) return rc;
+  if (int rc = make_operand_map(&tmy, y, outer, C, inner, g.tn)) return rc;
+  TmaGramParams p;
+  p.partial = partial;
+  p.qa = row_sumsq_x;
+  p.qb = row_sumsq_y;
+  p.C = (int)C;
+  p.inner = (int)inner;
+  p.boxes_per_image = (int)bpi;
+  p.total_boxes = (int)total_boxes;
+  p.m_tiles = g.m_tiles;
+  p.n_tiles = g.n_tiles;
+  p.splits = splits;
+  p.total_items = g.m_tiles * g.n_tiles * splits;
+  p.ld_m = g.ld_m;
+  p.ld_n = g.ld_n;
+  p.chain_boxes = chain_kb / 2 > 0 ? chain_kb / 2 : 1;  // a box is two 16-wide k-blocks
+  cudaStream_t s = (cudaStream_t)stream;
+  if (g.cg == 2) return launch_tma<2, 128, 128>(tmx, tmy, p, s);
+  if (g.tm == 64) return launch_tma<1, 64, 64>(tmx, tmy, p, s);
+  return launch_tma<1, 128, 128>(tmx, tmy, p, s);
+}

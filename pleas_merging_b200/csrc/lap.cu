@@ -486,15 +486,7 @@ template <int CPT>
 static int launch_lap_v2(const float *const *cost, const int32_t *n, const int32_t *ld, int64_t *const *col4row,
                          double *objective, int32_t *status, int n_problems, int max_n, int maximize, size_t smem,
                          cudaStream_t stream) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(lap_kernel_v2<CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(lap_kernel_v2<%d>, %zu): %s", CPT, smem, cudaGetErrorString(e));
-      return (int)e;
-    }
-    configured = smem;
-  }
+  if (int rc = ensure_dynamic_smem((const void *)lap_kernel_v2<CPT>, (int)smem, "lap_kernel_v2")) return rc;
   int threads = (int)(ceil_div(max_n, 32 * CPT) * 32);
   threads = threads < 32 ? 32 : threads;  // <= 1024 by the caller's choice of CPT
   lap_kernel_v2<CPT><<<n_problems, threads, smem, stream>>>(cost, n, ld, col4row, objective, status, maximize);
@@ -511,15 +503,7 @@ extern "C" int plb_lap_solve_batched(const float *const *cost, const int32_t *n,
   PLB_REQUIRE(n_problems > 0 && max_n > 0, PLB_EINVAL, "plb_lap_solve_batched: empty batch");
   PLB_REQUIRE(max_n <= 4096, PLB_ESIZE, "plb_lap_solve_batched: n > 4096 exceeds the shared-memory working set");
   const size_t smem = lap_smem_bytes(max_n);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(lap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(lap_kernel, %zu): %s", smem, cudaGetErrorString(e));
-      return (int)e;
-    }
-    configured = smem;
-  }
+  if (int rc = ensure_dynamic_smem((const void *)lap_kernel, (int)smem, "lap_kernel")) return rc;
   // PLB_LAP_IMPL=v1 selects the first kernel (one column per thread, two barriers per step) for A/B
   // runs; PLB_LAP_COLS_PER_THREAD overrides the columns per thread of either kernel.
   static int impl = 0, cols_override = -1;

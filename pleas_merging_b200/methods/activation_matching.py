@@ -192,6 +192,9 @@ class _View:
 # pipeline ramp and tail (~19 us for ~4 us of work on a ResNet-50 pair), so their GEMMs are deferred
 # to the end of the batch and run as one grouped persistent launch per tile width.
 DEFER_FLOPS = float(os.environ.get("PLB_DEFER_FLOPS", "3e9"))
+# Taps below this many FLOPs keep the packed path even when the TMA-fed kernel could read them in place
+# (0: every eligible tap uses the fused kernel)
+TMA_MIN_FLOPS = float(os.environ.get("PLB_TMA_MIN_FLOPS", "0"))
 
 
 class _TapState:
@@ -285,8 +288,14 @@ class CrossAccumulator:
         st.plan, st.version, st.group, st.slot = None, -1, t.group, None
         # narrow taps (C <= 128) are HBM-bound: the fused kernel reads the activations once, in place,
         # right behind their producer — no planes, nothing deferred
-        st.direct = (not self.overlap) and xa.dtype == torch.float32 and xb.dtype == torch.float32 and \
-            ops.direct_gram_eligible(xa, xb, t.axis)
+        fp32 = xa.dtype == torch.float32 and xb.dtype == torch.float32
+        # TMA-fed fused kernel (any width): reads the activations in place, right behind their producer
+        if (not self.overlap) and fp32 and ops.tma_gram_eligible(xa, xb, t.axis) and \
+                2.0 * ra * rb * st.K >= TMA_MIN_FLOPS:
+            st.direct, st.deferred, st.pa, st.pb, st.version = True, False, None, None, None
+            st.plan = ops.TmaGramPlan(ra, oa, ia, self.device, pool=self.pool)
+            return st
+        st.direct = (not self.overlap) and fp32 and ops.direct_gram_eligible(xa, xb, t.axis)
         if st.direct:
             st.deferred, st.pa, st.pb, st.version = False, None, None, None
             st.plan = ops.DirectGramPlan(ra, st.K, self.device, pool=self.pool)

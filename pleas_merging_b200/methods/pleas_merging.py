@@ -254,7 +254,6 @@ class _LayerLS:
             plan_g.finalize(self.G, ops.MODE_INNER, accumulate=True)
             plan_r.run()
             plan_r.finalize(self.R, ops.MODE_INNER, accumulate=True)
-            self.count += L
 
     def out_positions(self, acts1):
         op = acts1[1]
@@ -372,6 +371,7 @@ class LstsqRunner:
         self.accs, self.flat, self.ws = None, None, _Workspace(self.device)
         self.step = GraphedStep(self._eager, self._rebind, use_cuda_graph)
         self._last_L = {}
+        self._L_by_shape = {}  # input shape -> {layer: output positions}; rows are counted per run(), not per launch
 
     def close(self):
         self.step.clear()
@@ -439,9 +439,13 @@ class LstsqRunner:
             self._bind_all()
         for n, a in self.accs.items():
             a.accumulate(self.acts1[n], self.acts2[n], self.ws)
+        self._L_by_shape[tuple(x.shape)] = Ls
 
     def run(self, x):
         self.step(x)
+        # sample rows seen by every layer (host bookkeeping: a CUDA-graph replay runs no Python)
+        for n, L in self._L_by_shape[tuple(x.shape)].items():
+            self.accs[n].count += L * len(self.accs[n].ipasses)
 
 
 def layer_objective(W, G, R, yy_plus=0.0):

@@ -60,11 +60,18 @@ class _GroupPlan:
 
 
 def _to_device_state(state, keys, device):
+    """Replaces the group tensors of ``state`` by contiguous fp32 CUDA copies; returns
+    ``{key: (device, dtype)}`` of the entries it replaced so an in-place caller can be handed its
+    own device / dtype back."""
+    moved = {}
     for k in keys:
         if k in state:
             t = state[k]
             if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                if t.device != device or t.dtype != torch.float32:
+                    moved[k] = (t.device, t.dtype)
                 state[k] = t.detach().to(device=device, dtype=torch.float32).contiguous()
+    return moved
 
 
 def weight_matching(
@@ -94,9 +101,10 @@ def weight_matching(
 
     group_keys = {ax.key for pg in spec.values() for ax in pg.state}
     state_as = [copy(sa) for sa in state_as]
+    moved_bs = []
     for sa, sb in zip(state_as, state_bs):
         _to_device_state(sa, group_keys, device)
-        _to_device_state(sb, group_keys, device)
+        moved_bs.append(_to_device_state(sb, group_keys, device))
 
     perm = make_identity_perm(spec) if init_perm is None else deepcopy(init_perm)
     if init_perm is not None:
@@ -110,7 +118,8 @@ def weight_matching(
     fused = lsa_solver is b200_solve_lsa and cross_weights is cross_features_inner_product
     plans = {}
     flag = torch.zeros(1, dtype=torch.int32, device=device)
-    gain = torch.zeros(1, dtype=torch.float64, device=device)
+    gains = torch.zeros(max(len(perm_names), 1), dtype=torch.float64, device=device)  # one slot per visit of a sweep
+    visited = []
 
     # Two visits of a sweep commute unless their groups touch a common tensor (the cost of one then
     # depends on the permutation the other applies).  Scheduling a sweep by levels of that conflict
@@ -132,9 +141,8 @@ def weight_matching(
         return out
 
     def finish_visit(iteration, p, A, newP):
-        ops.wm_progress(A, newP, flag, gain)
-        if verbose:
-            print(f"{iteration}/{p.key}:{p.axis}: {gain.item()}")
+        ops.wm_progress(A, newP, flag, gains[len(visited):len(visited) + 1])
+        visited.append(p)
         perm[p] = ops.compose_perm(perm[p], newP)
         all_costs[p] = A
         for sb in state_bs:
@@ -172,12 +180,20 @@ def weight_matching(
                     finish_visit(iteration, p, A, newP)
             if statuses:
                 ops.raise_on_lap_status(torch.cat(statuses))
-            progress = bool(flag.item())
+            progress = bool(flag.item())  # the sweep's one synchronising readback
             flag.zero_()
+            if verbose:  # the reference prints newL - oldL per visit (:82-83); same lines, after the sweep
+                for p, g in zip(visited, gains[:len(visited)].tolist()):
+                    print(f"{iteration}/{p.key}:{p.axis}: {g}")
+            visited.clear()
             if not progress:
                 break
         assert all(bool(c.any()) for c in all_costs.values()), "a group's weight cost matrix is all zero"
         perm = {k: v.cpu() for k, v in perm.items()}
+        if inplace:  # the caller's dicts get their tensors back on the device / dtype they came with
+            for sb, moved in zip(state_bs, moved_bs):
+                for k, (dev0, dt0) in moved.items():
+                    sb[k] = sb[k].to(device=dev0, dtype=dt0)
         if return_costs:
             return perm, all_costs
         return perm

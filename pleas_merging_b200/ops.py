@@ -12,7 +12,12 @@ import torch
 from . import _native as N
 
 MODE_INNER, MODE_NEG_CDIST = 0, 1
-NUM_SMS = 148
+NUM_SMS = 148  # B200; planning helpers ask the device (num_sms()) when one is present
+
+
+def num_sms(device=None):
+    """SM count of ``device`` (cached per ordinal); the B200 figure on a host without a GPU."""
+    return N.sm_count(device) if torch.cuda.is_available() else NUM_SMS
 # GEMM implementations behind plb_gemm_grouped:
 #   "tcgen05"    persistent tcgen05 3xTF32 kernel with in-kernel promotion (product path)
 #   "tcgen05_v1" one CTA per K chain, chains summed by the finalize kernel
@@ -165,9 +170,9 @@ def pack_split(x, axis, planes, kb_offset=0, row_index=None, rows=None, sumsq=No
     if PACK_TIMER is not None:  # bench instrumentation: CUDA events around this launch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    N.check(N.lib().plb_pack_split(x.data_ptr(), outer, src_rows, inner, N.ptr(row_index), rows,
+    N.call("plb_pack_split", x.device, x.data_ptr(), outer, src_rows, inner, N.ptr(row_index), rows,
                                    planes.hi.data_ptr(), planes.lo.data_ptr(), planes.row_groups, kb_offset,
-                                   N.ptr(sumsq), N.ptr(rowsum), N.stream_ptr()), "plb_pack_split")
+                                   N.ptr(sumsq), N.ptr(rowsum))
     if PACK_TIMER is not None:
         e1.record()
         # algorithmic bytes: every element read once (4 B) and written as a tf32 hi/lo pair (8 B)
@@ -195,9 +200,9 @@ def pack_split_pair(xa, xb, axis, pa, pb, sumsq_a=None, sumsq_b=None):
     if PACK_TIMER is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    N.check(N.lib().plb_pack_split_pair(xa.data_ptr(), xb.data_ptr(), outer, rows, inner, pa.hi.data_ptr(),
+    N.call("plb_pack_split_pair", xa.device, xa.data_ptr(), xb.data_ptr(), outer, rows, inner, pa.hi.data_ptr(),
                                         pa.lo.data_ptr(), pb.hi.data_ptr(), pb.lo.data_ptr(), pa.row_groups, 0,
-                                        N.ptr(sumsq_a), N.ptr(sumsq_b), N.stream_ptr()), "plb_pack_split_pair")
+                                        N.ptr(sumsq_a), N.ptr(sumsq_b))
     if PACK_TIMER is not None:
         e1.record()
         PACK_TIMER.append((e0, e1, 2 * 12.0 * rows * outer * inner))
@@ -223,17 +228,18 @@ def choose_splits(tiles, k_blocks, m_rows=128, n_rows=256, impl=None):
     minimises a two-term time model (tensor time / wave efficiency + partial traffic).
     v1 kernel: additionally one split per accumulation chain."""
     impl = _GEMM_IMPL if impl is None else impl
+    sms = num_sms()
     if impl != "tcgen05":
-        fill = min(NUM_SMS * 4 // max(tiles, 1), k_blocks // 4)
+        fill = min(sms * 4 // max(tiles, 1), k_blocks // 4)
         chain = -(-k_blocks // 16)
         return max(1, min(max(fill, chain), k_blocks))
-    max_s = max(1, min(k_blocks // 16, 2 * NUM_SMS))
+    max_s = max(1, min(k_blocks // 16, 2 * sms))
     flops = 2.0 * m_rows * n_rows * k_blocks * 16 * tiles
     tile_bytes = 4.0 * m_rows * n_rows * tiles
     best, best_t = 1, None
     for sp in range(1, max_s + 1):
         items = tiles * sp
-        eff = items / (-(-items // NUM_SMS) * NUM_SMS)
+        eff = items / (-(-items // sms) * sms)
         t = flops / (eff * 120e12) + 2.0 * sp * tile_bytes / 5e12 + 2e-6
         if best_t is None or t < best_t * 0.98:
             best, best_t = sp, t
@@ -283,9 +289,8 @@ class GemmPlan:
         self._launch(impl)
 
     def _launch(self, impl=None):
-        N.check(N.lib().plb_gemm_grouped(self.table.data_ptr(), 1, self.total_ctas, self.bn,
-                                         _impl_code(_GEMM_IMPL if impl is None else impl), N.stream_ptr()),
-                "plb_gemm_grouped")
+        N.call("plb_gemm_grouped", self.table.device, self.table.data_ptr(), 1, self.total_ctas, self.bn,
+                                         _impl_code(_GEMM_IMPL if impl is None else impl))
 
     def finalize(self, out, mode=MODE_INNER, qa=None, qb=None, accumulate=False):
         """out[i, j] (+)= f(sum_s partial_s[i, j]); out fp32 or fp64 [M, N] (row stride = ldc)."""
@@ -293,10 +298,9 @@ class GemmPlan:
             c32, c64 = None, out.data_ptr()
         else:
             c32, c64 = out.data_ptr(), None
-        N.check(N.lib().plb_cross_finalize(self.partial.data_ptr(), self.splits, self.ld_m, self.ld_n, self.M,
+        N.call("plb_cross_finalize", self.partial.device, self.partial.data_ptr(), self.splits, self.ld_m, self.ld_n, self.M,
                                            self.N, N.ptr(qa), N.ptr(qb), mode, c32, c64, out.stride(0),
-                                           int(accumulate), self.bn if self.symmetric else 0, N.stream_ptr()),
-                "plb_cross_finalize")
+                                           int(accumulate), self.bn if self.symmetric else 0)
 
 
 DIRECT_MAX_ROWS = int(os.environ.get("PLB_DIRECT_MAX_ROWS", "128"))  # 0 disables the fused narrow-tap kernel
@@ -321,7 +325,7 @@ class DirectGramPlan:
         self.bn = 64 if rows <= 64 else 128
         self.ld_m, self.ld_n = 128, self.bn
         kb = K // 16
-        self.splits = max(1, min(NUM_SMS, kb // 16))
+        self.splits = max(1, min(num_sms(device), kb // 16))
         need = self.splits * self.ld_m * self.ld_n
         self.partial = pool.empty(need) if pool is not None else torch.empty(need, dtype=torch.float32, device=device)
         self.alg_flops = 2.0 * rows * rows * K
@@ -333,12 +337,88 @@ class DirectGramPlan:
         if DIRECT_TIMER is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        N.check(N.lib().plb_gram_direct(x.data_ptr(), y.data_ptr(), outer, rows, inner, self.partial.data_ptr(),
-                                        self.splits, MAX_CHAIN_KB, N.ptr(qa), N.ptr(qb), N.stream_ptr()),
-                "plb_gram_direct")
+        N.call("plb_gram_direct", x.device, x.data_ptr(), y.data_ptr(), outer, rows, inner, self.partial.data_ptr(),
+                                        self.splits, MAX_CHAIN_KB, N.ptr(qa), N.ptr(qb))
         if DIRECT_TIMER is not None:
             e1.record()
-            DIRECT_TIMER.append((e0, e1, self.alg_bytes, self.alg_flops))
+            DIRECT_TIMER.append((e0, e1, self.alg_bytes, self.alg_flops, rows))
+
+    finalize = GemmPlan.finalize
+
+
+TMA_GRAM = os.environ.get("PLB_TMA_GRAM", "1") == "1"  # 0: keep the round-1 paths (gram_direct / pack + GEMM)
+TMA_MIN_INNER = 16
+
+
+def tma_gram_eligible(x, y, axis):
+    """True when a tap can use the TMA-fed fused kernel (plb_gram_tma): both operands fp32, contiguous,
+    16-byte aligned, the same [outer][C][inner] geometry, inner a multiple of 4 (legal tensor-map
+    strides) and at least TMA_MIN_INNER (shorter rows waste most of a 32-wide box)."""
+    if not TMA_GRAM or x.shape != y.shape or x.dtype != torch.float32 or y.dtype != torch.float32:
+        return False
+    if not (x.is_cuda and x.is_contiguous() and y.is_contiguous()):
+        return False
+    if (x.data_ptr() | y.data_ptr()) & 15:
+        return False
+    outer, rows, inner = as_rows_view(x, axis)
+    return rows >= 8 and inner % 4 == 0 and inner >= TMA_MIN_INNER and outer * inner >= 256
+
+
+def tma_geometry(rows):
+    """(cta_group, m_tiles, n_tiles, ld_m, ld_n) of plb_gram_tma for `rows` channels."""
+    out = [ctypes.c_int32() for _ in range(5)]
+    rc = N.lib().plb_gram_tma_geometry(rows, *[ctypes.byref(v) for v in out])
+    if rc != 0:
+        raise RuntimeError("plb_gram_tma_geometry failed")
+    return tuple(v.value for v in out)
+
+
+def choose_tma_splits(tiles, cta_group, total_boxes, tile_elems, sms):
+    """K splits of a TMA-fed Gram: fill the SM clusters; every split costs one partial tile written
+    and re-read by the epilogue, every work item a pipeline ramp."""
+    clusters = max(1, sms // cta_group)
+    max_s = max(1, min(total_boxes // 4, 4 * clusters))
+    best, best_t = 1, None
+    mma_s_per_box = 12 * 128 / 1.9e9  # 12 tcgen05.mma of 128 clocks per 32-wide box
+    for sp in range(1, max_s + 1):
+        items = tiles * sp
+        rounds = -(-items // clusters)
+        boxes = -(-total_boxes // sp)
+        t = rounds * (boxes * mma_s_per_box + 4e-6) + 2.0 * sp * tiles * tile_elems * 4 / 4e12
+        if best_t is None or t < best_t * 0.98:
+            best, best_t = sp, t
+    return best
+
+
+class TmaGramPlan:
+    """TMA-fed fused cross-Gram of one tap (any width): partial tiles + the finalize geometry."""
+
+    def __init__(self, rows, outer, inner, device, pool=None, splits=None):
+        self.M = self.N = rows
+        self.cta_group, self.m_tiles, self.n_tiles, self.ld_m, self.ld_n = tma_geometry(rows)
+        self.bn = self.ld_n // self.n_tiles
+        K = outer * inner
+        total_boxes = outer * ((inner + 31) // 32)
+        tiles = self.m_tiles * self.n_tiles
+        tile_elems = (self.ld_m // self.m_tiles) * self.bn
+        self.splits = splits if splits is not None else \
+            choose_tma_splits(tiles, self.cta_group, total_boxes, tile_elems, num_sms(device))
+        need = self.splits * self.ld_m * self.ld_n
+        self.partial = pool.empty(need) if pool is not None else torch.empty(need, dtype=torch.float32, device=device)
+        self.alg_flops = 2.0 * rows * rows * K
+        self.alg_bytes = 2.0 * rows * K * 4
+        self.symmetric = False
+
+    def run(self, x, y, axis, qa=None, qb=None):
+        outer, rows, inner = as_rows_view(x, axis)
+        if DIRECT_TIMER is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        N.call("plb_gram_tma", x.device, x.data_ptr(), y.data_ptr(), outer, rows, inner, self.partial.data_ptr(),
+               self.splits, MAX_CHAIN_KB, N.ptr(qa), N.ptr(qb))
+        if DIRECT_TIMER is not None:
+            e1.record()
+            DIRECT_TIMER.append((e0, e1, self.alg_bytes, self.alg_flops, rows))
 
     finalize = GemmPlan.finalize
 
@@ -366,8 +446,8 @@ class GroupedGemm:
         if GEMM_TIMER is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        N.check(N.lib().plb_gemm_grouped(self.table.data_ptr(), len(self.plans), self.total_items, self.bn,
-                                         _impl_code(name), N.stream_ptr()), "plb_gemm_grouped")
+        N.call("plb_gemm_grouped", self.table.device, self.table.data_ptr(), len(self.plans), self.total_items, self.bn,
+                                         _impl_code(name))
         if GEMM_TIMER is not None:
             e1.record()
             GEMM_TIMER.append((e0, e1, self.alg_flops, self.bn, len(self.plans)))
@@ -388,6 +468,11 @@ def cross_statistic(x, y, axis, mode):
     q = torch.zeros(ra + rb, dtype=torch.float64, device=dev) if need_q else None
     qa, qb = (q[:ra], q[ra:]) if need_q else (None, None)
     out = torch.empty(ra, rb, dtype=torch.float32, device=dev)
+    if tma_gram_eligible(x, y, axis):  # TMA-fed fused kernel straight from the activations, no packed planes
+        plan = TmaGramPlan(ra, oa, ia, dev)
+        plan.run(x, y, axis, qa, qb)
+        plan.finalize(out, mode, qa, qb, accumulate=False)
+        return out
     if direct_gram_eligible(x, y, axis):  # narrow tap: fused kernel, no packed planes
         plan = DirectGramPlan(ra, oa * ia, dev)
         plan.run(x, y, axis, qa, qb)
@@ -421,9 +506,9 @@ def lap_solve_batched(costs, maximize=True):
     meta = torch.tensor([ns, [m.stride(0) for m in mats]], dtype=torch.int32).to(dev)
     obj = torch.empty(len(mats), dtype=torch.float64, device=dev)
     status = torch.empty(len(mats), dtype=torch.int32, device=dev)
-    N.check(N.lib().plb_lap_solve_batched(table[0].data_ptr(), meta[0].data_ptr(), meta[1].data_ptr(),
+    N.call("plb_lap_solve_batched", dev, table[0].data_ptr(), meta[0].data_ptr(), meta[1].data_ptr(),
                                           table[1].data_ptr(), obj.data_ptr(), status.data_ptr(), len(mats),
-                                          max(ns), int(bool(maximize)), N.stream_ptr()), "plb_lap_solve_batched")
+                                          max(ns), int(bool(maximize)))
     return outs, obj, status
 
 
@@ -445,9 +530,9 @@ def get_blocks_group(cost, perm, ratio, identity):
     buf = torch.empty(4, n, dtype=torch.int64, device=dev)
     counts = torch.zeros(1, dtype=torch.int32, device=dev)
     perm = perm.to(device=dev, dtype=torch.int64).contiguous()
-    N.check(N.lib().plb_get_blocks(cost.data_ptr(), cost.stride(0), perm.data_ptr(), n, float(ratio), int(identity),
+    N.call("plb_get_blocks", dev, cost.data_ptr(), cost.stride(0), perm.data_ptr(), n, float(ratio), int(identity),
                                    buf[0].data_ptr(), buf[1].data_ptr(), buf[2].data_ptr(), buf[3].data_ptr(),
-                                   counts.data_ptr(), N.stream_ptr()), "plb_get_blocks")
+                                   counts.data_ptr())
     m = int(counts.item())
     return buf[0, :m], buf[1, :m], buf[2, :n - m], buf[3, :n - m]
 
@@ -497,9 +582,8 @@ def block_merge(w1, w2, blocks_by_axis):
     Oout = no + 2 * mo if bo is not None else O
     Iout = ni + 2 * mi if bi is not None else I
     out = torch.empty(Oout * Iout * R, dtype=torch.float32, device=w1.device)
-    N.check(N.lib().plb_block_merge(w1.data_ptr(), w2.data_ptr(), O, I, R, po[0], po[1], po[2], po[3], no, mo,
-                                    pi[0], pi[1], pi[2], pi[3], ni, mi, in_only, out.data_ptr(), N.stream_ptr()),
-            "plb_block_merge")
+    N.call("plb_block_merge", w1.device, w1.data_ptr(), w2.data_ptr(), O, I, R, po[0], po[1], po[2], po[3], no, mo,
+                                    pi[0], pi[1], pi[2], pi[3], ni, mi, in_only, out.data_ptr())
     if axes == [0, 1]:
         return out.view([Oout, Iout] + shape[2:])
     if axes == [0]:
@@ -518,21 +602,19 @@ def gather_axis(x, axis, P):
     if P.numel() != n:
         raise ValueError("gather_axis: permutation length mismatch")
     out = torch.empty(out_shape, dtype=torch.float32, device=x.device)
-    N.check(N.lib().plb_gather_axis(x.data_ptr(), out.data_ptr(), outer, n, inner, P.data_ptr(), N.stream_ptr()),
-            "plb_gather_axis")
+    N.call("plb_gather_axis", x.device, x.data_ptr(), out.data_ptr(), outer, n, inner, P.data_ptr())
     return out
 
 
 def compose_perm(a, b):
     out = torch.empty_like(a)
-    N.check(N.lib().plb_compose_perm(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), N.stream_ptr()),
-            "plb_compose_perm")
+    N.call("plb_compose_perm", a.device, a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel())
     return out
 
 
 def wm_progress(A, P, flag, gain=None):
-    N.check(N.lib().plb_wm_progress(A.data_ptr(), A.stride(0), P.data_ptr(), A.shape[0], flag.data_ptr(),
-                                    N.ptr(gain), N.stream_ptr()), "plb_wm_progress")
+    N.call("plb_wm_progress", A.device, A.data_ptr(), A.stride(0), P.data_ptr(), A.shape[0], flag.data_ptr(),
+                                    N.ptr(gain))
 
 
 # ------------------------------------------------------------------------------------ solve
@@ -542,8 +624,8 @@ def chol_solve_(G, B, ridge):
     assert G.dtype == torch.float64 and B.dtype == torch.float64 and G.is_cuda and B.is_cuda
     assert G.is_contiguous() and B.is_contiguous() and G.shape[0] == G.shape[1] == B.shape[0]
     info = torch.zeros(1, dtype=torch.int32, device=G.device)
-    N.check(N.lib().plb_chol_solve(G.data_ptr(), G.shape[0], B.data_ptr(), B.shape[1], float(ridge),
-                                   info.data_ptr(), N.stream_ptr()), "plb_chol_solve")
+    N.call("plb_chol_solve", G.device, G.data_ptr(), G.shape[0], B.data_ptr(), B.shape[1], float(ridge),
+                                   info.data_ptr())
     return info
 
 
@@ -562,8 +644,8 @@ def pack_im2col(x1, x2, chan1, chan2, scale1, scale2, cmerged, kernel, stride, p
         assert x2.shape == x1.shape
     Nb, C, H, W = x1.shape
     Ho, Wo = out_hw
-    N.check(N.lib().plb_pack_im2col(x1.data_ptr(), N.ptr(x2), Nb, C, H, W, N.ptr(chan1), N.ptr(chan2),
+    N.call("plb_pack_im2col", x1.device, x1.data_ptr(), N.ptr(x2), Nb, C, H, W, N.ptr(chan1), N.ptr(chan2),
                                     N.ptr(scale1), N.ptr(scale2), cmerged, kernel[0], kernel[1], stride[0],
                                     stride[1], padding[0], padding[1], dilation[0], dilation[1], Ho, Wo,
                                     int(bool(ones_row)), planes.hi.data_ptr(), planes.lo.data_ptr(),
-                                    planes.row_groups, kb_offset, N.stream_ptr()), "plb_pack_im2col")
+                                    planes.row_groups, kb_offset)

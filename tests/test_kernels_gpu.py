@@ -126,11 +126,12 @@ DIRECT_CASES = [((4, 64, 16, 16), 1), ((1, 128, 64, 64), 1), ((6, 24, 4, 16), 1)
 
 
 @pytest.mark.parametrize("shape,axis", DIRECT_CASES)
-def test_fused_narrow_tap_kernel(shape, axis):
-    """plb_gram_direct (no packed planes) == fp64 reference at 3xTF32 accuracy, == the packed path
-    to fp32 rounding, for both statistics; rows that are not a multiple of the tile and K ranges
-    that split unevenly included."""
+def test_fused_narrow_tap_kernel(shape, axis, monkeypatch):
+    """plb_gram_direct (round-1 narrow-tap kernel, cp.async loaders; kept for A/B runs behind PLB_TMA_GRAM=0)
+    == fp64 reference at 3xTF32 accuracy, == the packed path to fp32 rounding, for both statistics; rows
+    that are not a multiple of the tile and K ranges that split unevenly included."""
     ops = _ops()
+    monkeypatch.setattr(ops, "TMA_GRAM", False)
     g = torch.Generator().manual_seed(5)
     x = (torch.relu(torch.randn(*shape, generator=g)) + 0.1 * torch.randn(*shape, generator=g)).cuda()
     y = torch.relu(torch.randn(*shape, generator=g)).cuda()
@@ -153,6 +154,87 @@ def test_fused_narrow_tap_kernel(shape, axis):
     assert np.abs(D.cpu().numpy() - Dref).max() <= 1e-4 * np.abs(Dref).max()
     assert (G - Gp).abs().max() <= 2e-6 * Gp.abs().max()
     assert (D - Dp).abs().max() <= 1e-4 * Dp.abs().max()
+
+
+TMA_CASES = [((4, 64, 16, 16), 1), ((1, 128, 64, 64), 1), ((2, 72, 16, 16), 1), ((32, 64, 56, 56), 1),
+             ((3, 8, 16, 16), 1), ((20, 128, 4, 4), 1), ((7, 40, 48), 1), ((2, 256, 14, 14), 1),
+             ((3, 512, 28, 28), 1), ((4, 320, 8, 8), 1), ((4, 1024, 14, 14), 1), ((2, 256, 56, 56), 1),
+             ((8, 136, 6, 6), 1)]
+
+
+@pytest.mark.parametrize("shape,axis", TMA_CASES)
+def test_tma_fused_gram_kernel(shape, axis):
+    """plb_gram_tma (TMA boxes straight from the activations, in-kernel hi/lo split; cta_group::2 tile
+    pairs above 128 channels) == fp64 reference at 3xTF32 accuracy and == the packed path to fp32
+    rounding, for both statistics.  Covers channel counts that are not a tile multiple (TMA zero-fills
+    the rows), spatial extents that are not a multiple of the 32-wide box (14x14 = 196, 6x6 = 36, 48)
+    and several output tiles with K splits."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    x = (torch.relu(torch.randn(*shape, generator=g)) + 0.1 * torch.randn(*shape, generator=g)).cuda()
+    y = torch.relu(torch.randn(*shape, generator=g)).cuda()
+    assert ops.tma_gram_eligible(x, y, axis)
+    before = ops.N.LAUNCH_COUNTS["plb_gram_tma"]
+    G = ops.cross_statistic(x, y, axis, ops.MODE_INNER)
+    D = ops.cross_statistic(x, y, axis, ops.MODE_NEG_CDIST)
+    assert ops.N.LAUNCH_COUNTS["plb_gram_tma"] == before + 2
+    old, oldd = ops.TMA_GRAM, ops.DIRECT_MAX_ROWS
+    ops.TMA_GRAM, ops.DIRECT_MAX_ROWS = False, 0
+    try:
+        Gp = ops.cross_statistic(x, y, axis, ops.MODE_INNER)
+        Dp = ops.cross_statistic(x, y, axis, ops.MODE_NEG_CDIST)
+    finally:
+        ops.TMA_GRAM, ops.DIRECT_MAX_ROWS = old, oldd
+    X = O._rows(x.cpu().numpy(), axis).astype(np.float64)
+    Y = O._rows(y.cpu().numpy(), axis).astype(np.float64)
+    Gref = X @ Y.T
+    assert np.abs(G.cpu().numpy() - Gref).max() <= 2.5e-6 * np.abs(Gref).max()
+    Dref = -np.sqrt(np.maximum((X * X).sum(1)[:, None] + (Y * Y).sum(1)[None] - 2 * Gref, 0))
+    assert np.abs(D.cpu().numpy() - Dref).max() <= 1e-4 * np.abs(Dref).max()
+    assert (G - Gp).abs().max() <= 2e-6 * Gp.abs().max()
+    assert (D - Dp).abs().max() <= 1e-4 * Dp.abs().max()
+
+
+@pytest.mark.parametrize("splits", [1, 3, 7])
+def test_tma_fused_gram_any_split_and_row_norms(splits):
+    """Explicit K splits of plb_gram_tma give the same Gram (fp32 rounding apart) and exact row norms."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(6, 256, 10, 12, generator=g).cuda()
+    y = torch.randn(6, 256, 10, 12, generator=g).cuda()
+    plan = ops.TmaGramPlan(256, 6, 120, x.device, splits=splits)
+    q = torch.zeros(2, 256, dtype=torch.float64, device=x.device)
+    plan.run(x, y, 1, q[0], q[1])
+    out = torch.empty(256, 256, device=x.device)
+    plan.finalize(out, ops.MODE_INNER)
+    X = O._rows(x.cpu().numpy(), 1).astype(np.float64)
+    Y = O._rows(y.cpu().numpy(), 1).astype(np.float64)
+    Gref = X @ Y.T
+    assert np.abs(out.cpu().numpy() - Gref).max() <= 2.5e-6 * np.abs(Gref).max()
+    np.testing.assert_allclose(q[0].cpu().numpy(), (X * X).sum(1), rtol=1e-6)
+    np.testing.assert_allclose(q[1].cpu().numpy(), (Y * Y).sum(1), rtol=1e-6)
+
+
+@pytest.mark.parametrize("C", [64, 256])
+def test_raw_fp32_word_as_tf32_operand_is_truncated(C):
+    """The fused kernels feed the RAW fp32 word as the tf32 "hi" operand and take lo against
+    trunc_tf32(x): correct only if kind::tf32 ignores (truncates) the 13 low mantissa bits.  Every value
+    here has low bits 0x1800 set, where round-to-nearest tf32 differs from truncation by a full tf32
+    ulp: a tensor core that rounded internally would be off by ~2^-11 relative, 500x the bound."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(13)
+    shape = (4, C, 16, 16)
+    bits = torch.randint(0, 1 << 23, shape, generator=g, dtype=torch.int32)
+    bits = (bits & ~0x1FFF) | 0x1800 | (127 << 23)  # 1.xxx with the bits just below the tf32 mantissa set
+    x = bits.view(torch.float32).cuda().contiguous()
+    y = torch.flip(x, dims=[1]).contiguous()
+    for eligible, fn in ((ops.tma_gram_eligible(x, y, 1), None),):
+        assert eligible
+    G = ops.cross_statistic(x, y, 1, ops.MODE_INNER).cpu().numpy()
+    X = O._rows(x.cpu().numpy(), 1).astype(np.float64)
+    Y = O._rows(y.cpu().numpy(), 1).astype(np.float64)
+    Gref = X @ Y.T
+    assert np.abs(G - Gref).max() <= 2.5e-6 * np.abs(Gref).max()
 
 
 @pytest.mark.parametrize("impl", ["tcgen05", "tcgen05_v1"])
