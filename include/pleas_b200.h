@@ -31,6 +31,10 @@ extern "C" {
 /* cross-statistic modes (pleas/methods/activation_matching.py:14-46) */
 #define PLB_MODE_INNER 0      /* G = X Y^T            cross_features_inner_product :14-28 */
 #define PLB_MODE_NEG_CDIST 1  /* -sqrt(max(qa+qb-2G,0)) cross_features_cdist      :31-46 */
+#define PLB_MODE_CORR 2       /* Pearson correlation of the unit pairs from G, the row sums and the row sums of
+                                 squares: (G - sa sb/K) / sqrt((qa - sa^2/K)(qb - sb^2/K)); 0 for a unit without
+                                 variance.  Not in the reference (it ships the two siblings above): the third
+                                 statistic BASELINE.json's north_star names; plb_cross_finalize_corr */
 
 int plb_version(void);
 const char *plb_last_error_string(void);
@@ -71,6 +75,11 @@ int plb_pack_split(const float *x, int64_t outer, int64_t src_rows, int64_t inne
 int plb_pack_split_pair(const float *xa, const float *xb, int64_t outer, int64_t src_rows, int64_t inner,
                         float *hi_a, float *lo_a, float *hi_b, float *lo_b, int32_t row_groups,
                         int32_t kb_offset, double *sumsq_a, double *sumsq_b, void *stream);
+/* same, additionally accumulating the rows' plain sums (correlation statistic) */
+int plb_pack_split_pair_sums(const float *xa, const float *xb, int64_t outer, int64_t src_rows, int64_t inner,
+                             float *hi_a, float *lo_a, float *hi_b, float *lo_b, int32_t row_groups,
+                             int32_t kb_offset, double *sumsq_a, double *sumsq_b, double *sum_a,
+                             double *sum_b, void *stream);
 
 /* Two-source gather-average + im2col pack for the PLeaS normal equations
  * (pleas_merging.py:116-123, 146-147: X-bar = cat[(x1[bi1]+x2[bi2])/2, x1[bi1c], x2[bi2c]]).
@@ -106,12 +115,17 @@ int plb_gram_direct(const float *x, const float *y, int64_t outer, int64_t C, in
  * (cluster of 2, tcgen05 cta_group::2) per 256 x 256 tile.  Writes partial[s] = X[:, Ks] Y[:, Ks]^T
  * for `splits` K ranges as [splits][ld_m][ld_n] fp32 (geometry from plb_gram_tma_geometry), to be
  * reduced by plb_cross_finalize, and adds the rows' sums of squares to the fp64 vectors (atomics:
- * zero them first; both or neither).  chain_kb = 16-wide k-blocks per accumulation chain (4).
- * Replaces cross_features_inner_product / cross_features_cdist (activation_matching.py:14-46)
- * together with its movedim/reshape copy (:26-27, 44-45). */
+ * zero them first; both or neither); row_sum_x / row_sum_y (may be NULL) additionally receive the
+ * rows' plain sums for the correlation statistic.  chain_kb = 16-wide k-blocks per accumulation
+ * chain (4).  Replaces cross_features_inner_product / cross_features_cdist
+ * (activation_matching.py:14-46) together with its movedim/reshape copy (:26-27, 44-45). */
 int plb_gram_tma(const float *x, const float *y, int64_t outer, int64_t C, int64_t inner,
                  float *partial, int32_t splits, int32_t chain_kb, double *row_sumsq_x,
-                 double *row_sumsq_y, void *stream);
+                 double *row_sumsq_y, double *row_sum_x, double *row_sum_y, void *stream);
+
+/* Experiments only (profiles/experiments/tma_trace.py): CTA 0 of every later plb_gram_tma launch records four
+ * clock64 stamps per pipeline box into dev_buf (>= 1024 uint64); NULL switches tracing off. */
+int plb_debug_set_trace(unsigned long long *dev_buf);
 
 /* Host-only: tiling plb_gram_tma uses for C rows: CTAs per work item (1 or 2), output tiles and the
  * padded leading dimensions of the partial tiles. */
@@ -154,6 +168,14 @@ int plb_cross_finalize(const float *partial, int32_t splits, int64_t ld_m, int64
                        int64_t M, int64_t N, const double *qa, const double *qb, int32_t mode,
                        float *cost, double *cost64, int64_t ldc, int32_t accumulate, int32_t sym_bn,
                        void *stream);
+
+/* Correlation epilogue (PLB_MODE_CORR): cost[i, j] (+)= corr(x_i, y_j) from the K-split partials of
+ * G = X Y^T, the rows' sums of squares qa/qb and sums sa/sb (fp64, as accumulated by plb_gram_tma /
+ * plb_pack_split) and the contraction length K.  Same partial layout as plb_cross_finalize. */
+int plb_cross_finalize_corr(const float *partial, int32_t splits, int64_t ld_m, int64_t ld_n,
+                            int64_t M, int64_t N, const double *qa, const double *qb,
+                            const double *sa, const double *sb, int64_t K, float *cost, int64_t ldc,
+                            int32_t accumulate, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Batched linear sum assignment — replaces scipy_solve_lsa (pleas/core/solvers.py:18-33,

@@ -31,9 +31,15 @@ _SIGNATURES = {
     "plb_pack_split_pair": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32,
                                            c_ptr, c_ptr, c_ptr]),
     "plb_gram_direct": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
-    "plb_gram_tma": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_ptr]),
+    "plb_gram_tma": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_i32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr,
+                                    c_ptr]),
+    "plb_pack_split_pair_sums": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i32,
+                                                c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "plb_cross_finalize_corr": (ctypes.c_int, [c_ptr, c_i32, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr,
+                                               c_i64, c_ptr, c_i64, c_i32, c_ptr]),
     "plb_gram_tma_geometry": (ctypes.c_int, [c_i64, ctypes.POINTER(c_i32), ctypes.POINTER(c_i32),
                                              ctypes.POINTER(c_i32), ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
+    "plb_debug_set_trace": (ctypes.c_int, [c_ptr]),
     "plb_pack_im2col": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64,
                                        c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64, c_i64, c_i32,
                                        c_ptr, c_ptr, c_i32, c_i32, c_ptr]),

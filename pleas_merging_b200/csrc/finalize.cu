@@ -110,6 +110,35 @@ __global__ void __launch_bounds__(256) cross_finalize_reduce_kernel(const float 
   epilogue_store<OutT>(gs, i, j, qa, qb, mode, cost, ldc, accumulate, accumulate ? cost[i * ldc + j] : (OutT)0);
 }
 
+// Correlation epilogue: Pearson coefficient of unit i of model A and unit j of model B over the K positions of
+// the tap, from the cross-Gram and the rows' first and second moments — all in fp64 (the covariance is a
+// difference of nearly equal numbers whenever the means are large against the spread, e.g. after a ReLU).
+__global__ void __launch_bounds__(256) cross_finalize_corr_kernel(const float *__restrict__ partial, int splits,
+                                                                  int64_t ld_m, int64_t ld_n, int64_t M, int64_t N,
+                                                                  const double *__restrict__ qa,
+                                                                  const double *__restrict__ qb,
+                                                                  const double *__restrict__ sa,
+                                                                  const double *__restrict__ sb, double inv_k,
+                                                                  float *__restrict__ cost, int64_t ldc,
+                                                                  int accumulate) {
+  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t i = blockIdx.y;
+  if (j >= N) return;
+  const float *p = partial + i * ld_n + j;
+  const int64_t split_stride = ld_m * ld_n;
+  double g = 0.0;
+  for (int s = 0; s < splits; ++s) g += (double)p[(int64_t)s * split_stride];
+  const double ma = sa[i], mb = sb[j];
+  const double cov = g - ma * mb * inv_k;
+  const double va = qa[i] - ma * ma * inv_k, vb = qb[j] - mb * mb * inv_k;
+  // a unit without variance on this batch (a dead ReLU channel) correlates with nothing: 0, not NaN,
+  // so the assignment problem stays well defined
+  const double eps_a = 1e-12 * qa[i], eps_b = 1e-12 * qb[j];
+  float v = 0.f;
+  if (va > eps_a && vb > eps_b) v = (float)(cov / sqrt(va * vb));
+  cost[i * ldc + j] = accumulate ? cost[i * ldc + j] + v : v;
+}
+
 template <typename OutT>
 static void launch_finalize(const float *partial, int splits, int64_t ld_m, int64_t ld_n, int64_t M, int64_t N,
                             const double *qa, const double *qb, int mode, OutT *cost, int64_t ldc, int accumulate,
@@ -145,4 +174,19 @@ extern "C" int plb_cross_finalize(const float *partial, int32_t splits, int64_t 
   else
     launch_finalize<float>(partial, splits, ld_m, ld_n, M, N, qa, qb, mode, cost, ldc, accumulate, sym_bn, s);
   return launch_status("cross_finalize");
+}
+
+extern "C" int plb_cross_finalize_corr(const float *partial, int32_t splits, int64_t ld_m, int64_t ld_n, int64_t M,
+                                       int64_t N, const double *qa, const double *qb, const double *sa,
+                                       const double *sb, int64_t K, float *cost, int64_t ldc, int32_t accumulate,
+                                       void *stream) {
+  using namespace plb;
+  PLB_REQUIRE(partial && cost && qa && qb && sa && sb, PLB_EINVAL, "plb_cross_finalize_corr: null pointer");
+  PLB_REQUIRE(splits > 0 && M > 0 && N > 0 && M <= ld_m && N <= ld_n && ldc >= N && K > 0, PLB_EINVAL,
+              "plb_cross_finalize_corr: bad geometry");
+  PLB_REQUIRE(M <= 65535, PLB_ESIZE, "plb_cross_finalize_corr: M too large");
+  dim3 grid((unsigned)ceil_div(N, 256), (unsigned)M);
+  cross_finalize_corr_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partial, splits, ld_m, ld_n, M, N, qa, qb, sa, sb,
+                                                                     1.0 / (double)K, cost, ldc, accumulate);
+  return launch_status("cross_finalize_corr_kernel");
 }

@@ -32,6 +32,7 @@
 //               LEADER's barrier (remote mbarrier arrive for the peer CTA)
 //   warps 4-11  promotion / epilogue (two per TMEM lane quadrant, half the columns each)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -56,20 +57,19 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-constexpr int kBoxK = 32;  // k per TMA box = one 128-byte swizzle row of fp32
-
-// [outer][C][inner] fp32 as a 3-D tensor map (inner, C, outer), boxes of (32 k, box_rows, 1), 128-byte swizzle;
-// out-of-range rows / k read as zeros.
+// [outer][C][inner] fp32 as a 3-D tensor map (inner, C, outer), boxes of (box_k k, box_rows, 1) whose rows are
+// one swizzle row: 32 k = 128-byte swizzle, 16 k = 64-byte swizzle; out-of-range rows / k read as zeros.
 static int make_operand_map(CUtensorMap *m, const float *base, int64_t outer, int64_t C, int64_t inner,
-                            int box_rows) {
+                            int box_rows, int box_k) {
   EncodeTiledFn enc = encode_tiled();
   PLB_REQUIRE(enc != nullptr, PLB_EINVAL, "plb_gram_tma: cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)C, (cuuint64_t)outer};
   cuuint64_t gstride[2] = {(cuuint64_t)inner * 4, (cuuint64_t)inner * (cuuint64_t)C * 4};
-  cuuint32_t box[3] = {(cuuint32_t)kBoxK, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, gdim, gstride, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_k == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PLB_REQUIRE(r == CUDA_SUCCESS, PLB_EINVAL, "plb_gram_tma: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return PLB_OK;
@@ -178,27 +178,35 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // K-major operand tile with 128-byte swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor): rows are 128 bytes,
 // 8-row groups 1024 bytes apart (SBO), LBO unused for a K extent inside one swizzle row, version 1,
 // layout_type 2 = SWIZZLE_128B.  The tile base is 1024-byte aligned; a k8 step advances the start by 32 bytes.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+// ROW_BYTES = 64 is the same with the 64-byte swizzle (layout_type 4): 8-row groups 512 bytes apart.
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t umma_desc_sw(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61;
   return d;
 }
 
 struct TmaGramParams {
   float *partial;    // [splits][ld_m][ld_n]
   double *qa, *qb;   // row sums of squares (fp64 atomics) or nullptr
+  double *sa, *sb;   // row sums (correlation statistic; SUMS instantiation only)
   int C, inner, boxes_per_image, total_boxes;
   int m_tiles, n_tiles, splits, total_items;
   int ld_m, ld_n, chain_boxes;
+  unsigned long long *trace;  // experiments only (plb_debug_set_trace): per-box clock64 stamps of CTA 0, or nullptr
+  int debug;  // experiments only (PLB_TMA_DEBUG): 1 = converters skip their work, 2 = hi x hi MMA only (WRONG results)
 };
 
-template <int CG, int TM, int TN>
+template <int CG, int TM, int TN, int KBOX>
 struct TmaCfg {
-  static constexpr int kXBytes = TM * 128, kYBytes = TN * 128;
+  static constexpr int kBoxK = KBOX;                    // k per TMA box = one swizzle row of fp32 (32: 128 B, 16: 64 B)
+  static constexpr int kRowBytes = KBOX * 4;
+  static constexpr int kCpr = kRowBytes / 16;           // 16-byte chunks per tile row
+  static constexpr int kXBytes = TM * kRowBytes, kYBytes = TN * kRowBytes;
   static constexpr int kRawBytes = kXBytes + kYBytes;   // what TMA lands per stage and CTA
   static constexpr int kStageBytes = 2 * kRawBytes;     // [X raw = hi][Y raw = hi][X lo][Y lo]
   static constexpr int kStages = (192 * 1024) / kStageBytes;
@@ -208,16 +216,17 @@ struct TmaCfg {
   static constexpr int kMmaM = 128 * CG, kMmaN = TN * CG;
   static constexpr int kTmemCols = 2 * kMmaN;
   static constexpr int kCols = kMmaN / 2;               // accumulator columns per promotion warp
-  static constexpr int kChunks = (TM + TN) * 8;         // 16-byte chunks of the raw region
+  static constexpr int kChunks = (TM + TN) * kCpr;      // 16-byte chunks of the raw region
   static constexpr int kPer = kChunks / (kConvWarps * 32);
   static_assert(kStages >= 2 && kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "geometry");
   static_assert(kChunks % (kConvWarps * 32) == 0, "converter mapping");
 };
 
-template <int CG, int TM, int TN>
+template <int CG, int TM, int TN, int KBOX, bool SUMS>
 __global__ void __launch_bounds__(384, 1) gram_tma_kernel(const __grid_constant__ CUtensorMap tmx,
                                                           const __grid_constant__ CUtensorMap tmy, TmaGramParams p) {
-  using Cfg = TmaCfg<CG, TM, TN>;
+  using Cfg = TmaCfg<CG, TM, TN, KBOX>;
+  constexpr int kBoxK = KBOX;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_raw[Cfg::kStages];    // TMA -> converters (this CTA)
   __shared__ uint64_t bar_conv[Cfg::kStages];   // converters of both CTAs -> MMA issuer (leader's copy is used)
@@ -265,6 +274,7 @@ __global__ void __launch_bounds__(384, 1) gram_tma_kernel(const __grid_constant_
       int img = box0 / p.boxes_per_image, kb = box0 - img * p.boxes_per_image;
       for (int i = 0; i < nbox; ++i) {
         mbar_wait_wd(&bar_empty[s], ph ^ 1u);
+        if (p.trace && blockIdx.x == 0 && lane == 0 && i < 256) p.trace[i * 4 + 0] = clock64();
         if (elect_one()) {
           uint8_t *st = smem + (size_t)s * Cfg::kStageBytes;
           mbar_arrive_expect_tx(&bar_raw[s], Cfg::kRawBytes);
@@ -302,6 +312,7 @@ __global__ void __launch_bounds__(384, 1) gram_tma_kernel(const __grid_constant_
           for (int b = b0; b < b1; ++b) {
             mbar_wait_wd(&bar_conv[s], ph);
             tc_fence_after();
+            if (p.trace && blockIdx.x == 0 && lane == 0 && b < 256) p.trace[b * 4 + 3] = clock64();
             const int valid = min(kBoxK, p.inner - kb * kBoxK);  // k beyond the image's extent is TMA zero fill
             const int nk8 = (valid + 7) >> 3;
             if (elect_one()) {
@@ -309,13 +320,17 @@ __global__ void __launch_bounds__(384, 1) gram_tma_kernel(const __grid_constant_
 #pragma unroll
               for (int j = 0; j < kBoxK / 8; ++j) {
                 if (j < nk8) {
-                  const uint64_t a_hi = umma_desc_sw128(st + 32 * j);
-                  const uint64_t b_hi = umma_desc_sw128(st + Cfg::kXBytes + 32 * j);
-                  const uint64_t a_lo = umma_desc_sw128(st + Cfg::kRawBytes + 32 * j);
-                  const uint64_t b_lo = umma_desc_sw128(st + Cfg::kRawBytes + Cfg::kXBytes + 32 * j);
-                  umma_tf32_cg<CG>(d_tmem, a_lo, b_hi, idesc, (b > b0 || j > 0) ? 1u : 0u);
-                  umma_tf32_cg<CG>(d_tmem, a_hi, b_lo, idesc, 1u);
-                  umma_tf32_cg<CG>(d_tmem, a_hi, b_hi, idesc, 1u);
+                  const uint64_t a_hi = umma_desc_sw<Cfg::kRowBytes>(st + 32 * j);
+                  const uint64_t b_hi = umma_desc_sw<Cfg::kRowBytes>(st + Cfg::kXBytes + 32 * j);
+                  const uint64_t a_lo = umma_desc_sw<Cfg::kRowBytes>(st + Cfg::kRawBytes + 32 * j);
+                  const uint64_t b_lo = umma_desc_sw<Cfg::kRowBytes>(st + Cfg::kRawBytes + Cfg::kXBytes + 32 * j);
+                  if (p.debug != 2) {
+                    umma_tf32_cg<CG>(d_tmem, a_lo, b_hi, idesc, (b > b0 || j > 0) ? 1u : 0u);
+                    umma_tf32_cg<CG>(d_tmem, a_hi, b_lo, idesc, 1u);
+                    umma_tf32_cg<CG>(d_tmem, a_hi, b_hi, idesc, 1u);
+                  } else {
+                    umma_tf32_cg<CG>(d_tmem, a_hi, b_hi, idesc, (b > b0 || j > 0) ? 1u : 0u);
+                  }
                 }
               }
               umma_commit_cg<CG>(&bar_empty[s]);
@@ -340,47 +355,67 @@ __global__ void __launch_bounds__(384, 1) gram_tma_kernel(const __grid_constant_
       const int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
       const int box0 = (int)((int64_t)p.total_boxes * split / p.splits);
       const int nbox = (int)((int64_t)p.total_boxes * (split + 1) / p.splits) - box0;
-      float s2[Cfg::kPer];
+      float s2[Cfg::kPer], s1[SUMS ? Cfg::kPer : 1];
 #pragma unroll
       for (int q = 0; q < Cfg::kPer; ++q) s2[q] = 0.f;
+#pragma unroll
+      for (int q = 0; q < (SUMS ? Cfg::kPer : 1); ++q) s1[q] = 0.f;
       for (int i = 0; i < nbox; ++i) {
         mbar_wait_wd(&bar_raw[s], ph);
+        if (p.trace && blockIdx.x == 0 && ct == 0 && i < 256) p.trace[i * 4 + 1] = clock64();
         uint8_t *st = smem + (size_t)s * Cfg::kStageBytes + (uint32_t)ct * 16u;
+        if (p.debug != 1)
 #pragma unroll
         for (int q = 0; q < Cfg::kPer; ++q) {
           const float4 v = *reinterpret_cast<const float4 *>(st + q * 1024);
-          float4 l;  // x - trunc_tf32(x) is exact (<= 13 significant bits); rounded to nearest tf32 (ties away)
-          l.x = __uint_as_float((__float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u)) + 0x1000u) & 0xffffe000u);
-          l.y = __uint_as_float((__float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u)) + 0x1000u) & 0xffffe000u);
-          l.z = __uint_as_float((__float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u)) + 0x1000u) & 0xffffe000u);
-          l.w = __uint_as_float((__float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u)) + 0x1000u) & 0xffffe000u);
+          // x - trunc_tf32(x) is exact (<= 13 significant bits).  Adding half a tf32 ulp (0x1000) to its bit
+          // pattern and letting the tensor core drop the 13 low bits rounds it to nearest (ties away): the
+          // final mask is the hardware's, so the split costs two integer ops and one subtraction per value.
+          float4 l;
+          l.x = __uint_as_float(__float_as_uint(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u)) + 0x1000u);
+          l.y = __uint_as_float(__float_as_uint(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u)) + 0x1000u);
+          l.z = __uint_as_float(__float_as_uint(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u)) + 0x1000u);
+          l.w = __uint_as_float(__float_as_uint(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u)) + 0x1000u);
           *reinterpret_cast<float4 *>(st + Cfg::kRawBytes + q * 1024) = l;
           s2[q] = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2[q]))));
+          if (SUMS) s1[q] += (v.x + v.y) + (v.z + v.w);
         }
         fence_proxy_async();  // generic-proxy stores -> visible to tcgen05.mma (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive_leader<CG>(&bar_conv[s]);
+        if (p.trace && blockIdx.x == 0 && ct == 0 && i < 256) p.trace[i * 4 + 2] = clock64();
         if (++s == Cfg::kStages) {
           s = 0;
           ph ^= 1u;
         }
       }
-      // Row sums of squares: chunk (q * 64 + ct) lies in tile row q * 8 + ct / 8; the 8 lanes of a row combine,
-      // then one fp64 atomic per row.  X rows are counted by the tiles of column 0, Y rows by those of row 0.
+      // Row sums of squares: chunk (q * 64 + ct) lies in tile row (q * 64 + ct) / kCpr; the kCpr lanes of a row
+      // combine, then one fp64 atomic per row.  X rows are counted by the tiles of column 0, Y rows by those of row 0.
       if (p.qa != nullptr) {
         const int row_x = mt * (TM * CG) + (int)rank * TM, row_y = nt * (TN * CG) + (int)rank * TN;
 #pragma unroll
         for (int q = 0; q < Cfg::kPer; ++q) {
-          float v = s2[q];
+          float v = s2[q], w = SUMS ? s1[q] : 0.f;
           v += __shfl_xor_sync(0xffffffffu, v, 1);
           v += __shfl_xor_sync(0xffffffffu, v, 2);
-          v += __shfl_xor_sync(0xffffffffu, v, 4);
-          const int r = q * 8 + (ct >> 3);
-          if ((ct & 7) == 0) {
+          if (Cfg::kCpr == 8) v += __shfl_xor_sync(0xffffffffu, v, 4);
+          if (SUMS) {
+            w += __shfl_xor_sync(0xffffffffu, w, 1);
+            w += __shfl_xor_sync(0xffffffffu, w, 2);
+            if (Cfg::kCpr == 8) w += __shfl_xor_sync(0xffffffffu, w, 4);
+          }
+          const int r = (q * 64 + ct) / Cfg::kCpr;
+          if ((ct & (Cfg::kCpr - 1)) == 0) {
             if (r < TM) {
-              if (nt == 0 && row_x + r < p.C) atomicAdd(p.qa + row_x + r, (double)v);
+              if (nt == 0 && row_x + r < p.C) {
+                atomicAdd(p.qa + row_x + r, (double)v);
+                if (SUMS) atomicAdd(p.sa + row_x + r, (double)w);
+              }
             } else {
-              if (mt == 0 && row_y + (r - TM) < p.C) atomicAdd(p.qb + row_y + (r - TM), (double)v);
+              if (mt == 0 && row_y + (r - TM) < p.C) {
+                atomicAdd(p.qb + row_y + (r - TM), (double)v);
+                if (SUMS) atomicAdd(p.sb + row_y + (r - TM), (double)w);
+              }
             }
           }
         }
@@ -430,6 +465,8 @@ __global__ void __launch_bounds__(384, 1) gram_tma_kernel(const __grid_constant_
   if (warp == 1) tmem_dealloc_cg<CG>(tmem_base, Cfg::kTmemCols);
 }
 
+static unsigned long long *g_trace = nullptr;
+
 struct TmaGeometry {
   int cg, tm, tn, m_tiles, n_tiles, ld_m, ld_n;
 };
@@ -447,10 +484,11 @@ static TmaGeometry tma_geometry(int64_t C) {
   return g;
 }
 
-template <int CG, int TM, int TN>
+template <int CG, int TM, int TN, int KBOX, bool SUMS>
 static int launch_tma(const CUtensorMap &tmx, const CUtensorMap &tmy, const TmaGramParams &p, cudaStream_t stream) {
-  using Cfg = TmaCfg<CG, TM, TN>;
-  if (int rc = ensure_dynamic_smem((const void *)gram_tma_kernel<CG, TM, TN>, Cfg::kSmemBytes, "gram_tma_kernel"))
+  using Cfg = TmaCfg<CG, TM, TN, KBOX>;
+  if (int rc = ensure_dynamic_smem((const void *)gram_tma_kernel<CG, TM, TN, KBOX, SUMS>, Cfg::kSmemBytes,
+                                   "gram_tma_kernel"))
     return rc;
   const int clusters = min(p.total_items, device_sm_count() / CG);
   cudaLaunchConfig_t cfg = {};
@@ -465,7 +503,7 @@ static int launch_tma(const CUtensorMap &tmx, const CUtensorMap &tmy, const TmaG
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gram_tma_kernel<CG, TM, TN>, tmx, tmy, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gram_tma_kernel<CG, TM, TN, KBOX, SUMS>, tmx, tmy, p);
   if (e != cudaSuccess) {
     cudaGetLastError();
     set_error("gram_tma_kernel<%d,%d,%d>: %s", CG, TM, TN, cudaGetErrorString(e));
@@ -475,6 +513,13 @@ static int launch_tma(const CUtensorMap &tmx, const CUtensorMap &tmy, const TmaG
 }
 
 }  // namespace plb
+
+// experiments only: CTA 0 of every later plb_gram_tma launch writes 4 clock64 stamps per box (first 256 boxes
+// of its first work item) into dev_buf: [issue ok, raw landed, converted, MMA start]; nullptr switches it off
+extern "C" int plb_debug_set_trace(unsigned long long *dev_buf) {
+  plb::g_trace = dev_buf;
+  return PLB_OK;
+}
 
 extern "C" int plb_gram_tma_geometry(int64_t C, int32_t *cta_group, int32_t *m_tiles, int32_t *n_tiles,
                                      int32_t *ld_m, int32_t *ld_n) {
@@ -490,7 +535,8 @@ extern "C" int plb_gram_tma_geometry(int64_t C, int32_t *cta_group, int32_t *m_t
 }
 
 extern "C" int plb_gram_tma(const float *x, const float *y, int64_t outer, int64_t C, int64_t inner, float *partial,
-                            int32_t splits, int32_t chain_kb, double *row_sumsq_x, double *row_sumsq_y, void *stream) {
+                            int32_t splits, int32_t chain_kb, double *row_sumsq_x, double *row_sumsq_y,
+                            double *row_sum_x, double *row_sum_y, void *stream) {
   using namespace plb;
   PLB_REQUIRE(x && y && partial, PLB_EINVAL, "plb_gram_tma: null pointer");
   PLB_REQUIRE(outer > 0 && inner > 0 && C > 0, PLB_EINVAL, "plb_gram_tma: empty operand");
@@ -500,19 +546,33 @@ extern "C" int plb_gram_tma(const float *x, const float *y, int64_t outer, int64
               "plb_gram_tma: pointers must be 16-byte aligned");
   PLB_REQUIRE((row_sumsq_x == nullptr) == (row_sumsq_y == nullptr), PLB_EINVAL,
               "plb_gram_tma: row statistics for both operands or neither");
+  PLB_REQUIRE((row_sum_x == nullptr) == (row_sum_y == nullptr) && (row_sum_x == nullptr || row_sumsq_x != nullptr),
+              PLB_EINVAL, "plb_gram_tma: row sums need both operands and the sums of squares");
   PLB_REQUIRE(outer < (1ll << 31) && C < (1ll << 31) && inner < (1ll << 31), PLB_ESIZE, "plb_gram_tma: extent too large");
-  const int64_t bpi = ceil_div(inner, kBoxK);
+  const TmaGeometry g = tma_geometry(C);
+  // k per TMA box / pipeline stage: 32 (128-byte swizzle rows: the DRAM-friendly choice for the HBM-bound narrow
+  // taps) or 16 (64-byte swizzle: twice the stages in the same shared memory, i.e. finer hand-overs for the
+  // tensor-bound CTA-pair tiles).  PLB_TMA_BOXK_WIDE / PLB_TMA_BOXK_NARROW override for A/B runs.
+  static int boxk_wide = 0, boxk_narrow = 0;
+  if (boxk_wide == 0) {
+    const char *w = getenv("PLB_TMA_BOXK_WIDE"), *n = getenv("PLB_TMA_BOXK_NARROW");
+    boxk_wide = (w && atoi(w) == 32) ? 32 : 16;
+    boxk_narrow = (n && atoi(n) == 16) ? 16 : 32;
+  }
+  const int box_k = g.cg == 2 ? boxk_wide : boxk_narrow;
+  const int64_t bpi = ceil_div(inner, box_k);
   const int64_t total_boxes = outer * bpi;
   PLB_REQUIRE(total_boxes < (1ll << 31), PLB_ESIZE, "plb_gram_tma: K too large");
   PLB_REQUIRE(splits > 0 && splits <= total_boxes && chain_kb > 0, PLB_EINVAL, "plb_gram_tma: bad splits / chain");
-  const TmaGeometry g = tma_geometry(C);
   CUtensorMap tmx, tmy;
-  if (int rc = make_operand_map(&tmx, x, outer, C, inner, g.tm)) return rc;
-  if (int rc = make_operand_map(&tmy, y, outer, C, inner, g.tn)) return rc;
+  if (int rc = make_operand_map(&tmx, x, outer, C, inner, g.tm, box_k)) return rc;
+  if (int rc = make_operand_map(&tmy, y, outer, C, inner, g.tn, box_k)) return rc;
   TmaGramParams p;
   p.partial = partial;
   p.qa = row_sumsq_x;
   p.qb = row_sumsq_y;
+  p.sa = row_sum_x;
+  p.sb = row_sum_y;
   p.C = (int)C;
   p.inner = (int)inner;
   p.boxes_per_image = (int)bpi;
@@ -523,9 +583,26 @@ extern "C" int plb_gram_tma(const float *x, const float *y, int64_t outer, int64
   p.total_items = g.m_tiles * g.n_tiles * splits;
   p.ld_m = g.ld_m;
   p.ld_n = g.ld_n;
-  p.chain_boxes = chain_kb / 2 > 0 ? chain_kb / 2 : 1;  // a box is two 16-wide k-blocks
+  p.chain_boxes = chain_kb * 16 / box_k > 0 ? chain_kb * 16 / box_k : 1;  // chain_kb counts 16-wide k-blocks
+  static int debug = -1;
+  if (debug < 0) {
+    const char *d = getenv("PLB_TMA_DEBUG");
+    debug = d ? atoi(d) : 0;
+  }
+  p.debug = debug;
+  p.trace = g_trace;
   cudaStream_t s = (cudaStream_t)stream;
-  if (g.cg == 2) return launch_tma<2, 128, 128>(tmx, tmy, p, s);
-  if (g.tm == 64) return launch_tma<1, 64, 64>(tmx, tmy, p, s);
-  return launch_tma<1, 128, 128>(tmx, tmy, p, s);
+  const bool sums = row_sum_x != nullptr;
+#define PLB_TMA_DISPATCH(CGV, TMV, TNV)                                                                   \
+  do {                                                                                                      \
+    if (box_k == 32)                                                                                        \
+      return sums ? launch_tma<CGV, TMV, TNV, 32, true>(tmx, tmy, p, s)                                     \
+                  : launch_tma<CGV, TMV, TNV, 32, false>(tmx, tmy, p, s);                                   \
+    return sums ? launch_tma<CGV, TMV, TNV, 16, true>(tmx, tmy, p, s)                                       \
+                : launch_tma<CGV, TMV, TNV, 16, false>(tmx, tmy, p, s);                                     \
+  } while (0)
+  if (g.cg == 2) PLB_TMA_DISPATCH(2, 128, 128);
+  if (g.tm == 64) PLB_TMA_DISPATCH(1, 64, 64);
+  PLB_TMA_DISPATCH(1, 128, 128);
+#undef PLB_TMA_DISPATCH
 }

@@ -113,6 +113,7 @@ struct PackPair {
   const float *x[2];
   float *hi[2], *lo[2];
   double *sumsq[2];
+  double *sum[2];
 };
 
 template <bool VEC4>
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(256) pack_split_pair_kernel(PackPair pp, int64
                                                               int k_blocks) {
   const int z = blockIdx.z;
   pack_split_body<VEC4>(pp.x[z], src_rows, inner, K, nullptr, rows, pp.hi[z], pp.lo[z], row_groups, kb_offset,
-                        k_blocks, pp.sumsq[z], nullptr);
+                        k_blocks, pp.sumsq[z], pp.sum[z]);
 }
 
 struct Im2colGeom {
@@ -228,13 +229,14 @@ extern "C" int plb_pack_split(const float *x, int64_t outer, int64_t src_rows, i
   return launch_status("pack_split_kernel");
 }
 
-extern "C" int plb_pack_split_pair(const float *xa, const float *xb, int64_t outer, int64_t src_rows, int64_t inner,
-                                   float *hi_a, float *lo_a, float *hi_b, float *lo_b, int32_t row_groups,
-                                   int32_t kb_offset, double *sumsq_a, double *sumsq_b, void *stream) {
+extern "C" int plb_pack_split_pair_sums(const float *xa, const float *xb, int64_t outer, int64_t src_rows,
+                                        int64_t inner, float *hi_a, float *lo_a, float *hi_b, float *lo_b,
+                                        int32_t row_groups, int32_t kb_offset, double *sumsq_a, double *sumsq_b,
+                                        double *sum_a, double *sum_b, void *stream) {
   using namespace plb;
   PLB_REQUIRE(xa && xb && hi_a && lo_a && hi_b && lo_b, PLB_EINVAL, "plb_pack_split_pair: null pointer");
   PLB_REQUIRE(outer > 0 && src_rows > 0 && inner > 0, PLB_EINVAL, "plb_pack_split_pair: empty operand");
-  PLB_REQUIRE((sumsq_a == nullptr) == (sumsq_b == nullptr), PLB_EINVAL,
+  PLB_REQUIRE((sumsq_a == nullptr) == (sumsq_b == nullptr) && (sum_a == nullptr) == (sum_b == nullptr), PLB_EINVAL,
               "plb_pack_split_pair: row statistics must be requested for both operands or neither");
   const int64_t K = outer * inner, rows = src_rows;
   PLB_REQUIRE(K < (int64_t)1 << 31 && inner < (int64_t)1 << 31, PLB_ESIZE, "plb_pack_split_pair: K too large");
@@ -246,7 +248,7 @@ extern "C" int plb_pack_split_pair(const float *xa, const float *xb, int64_t out
   dim3 grid((unsigned)ceil_div(k_blocks, kKbPerBlock), (unsigned)ceil_div(rows, 8), 2);
   PLB_REQUIRE(grid.y <= 65535, PLB_ESIZE, "plb_pack_split_pair: too many rows");
   cudaStream_t s = (cudaStream_t)stream;
-  PackPair pp{{xa, xb}, {hi_a, hi_b}, {lo_a, lo_b}, {sumsq_a, sumsq_b}};
+  PackPair pp{{xa, xb}, {hi_a, hi_b}, {lo_a, lo_b}, {sumsq_a, sumsq_b}, {sum_a, sum_b}};
   const bool vec4 = (inner % 4 == 0) && ((((uintptr_t)xa | (uintptr_t)xb) & 15) == 0);
   if (vec4)
     pack_split_pair_kernel<true><<<grid, 256, 0, s>>>(pp, src_rows, (uint32_t)inner, (uint32_t)K, (int)rows,
@@ -255,6 +257,13 @@ extern "C" int plb_pack_split_pair(const float *xa, const float *xb, int64_t out
     pack_split_pair_kernel<false><<<grid, 256, 0, s>>>(pp, src_rows, (uint32_t)inner, (uint32_t)K, (int)rows,
                                                        row_groups, kb_offset, k_blocks);
   return launch_status("pack_split_pair_kernel");
+}
+
+extern "C" int plb_pack_split_pair(const float *xa, const float *xb, int64_t outer, int64_t src_rows, int64_t inner,
+                                   float *hi_a, float *lo_a, float *hi_b, float *lo_b, int32_t row_groups,
+                                   int32_t kb_offset, double *sumsq_a, double *sumsq_b, void *stream) {
+  return plb_pack_split_pair_sums(xa, xb, outer, src_rows, inner, hi_a, lo_a, hi_b, lo_b, row_groups, kb_offset,
+                                  sumsq_a, sumsq_b, nullptr, nullptr, stream);
 }
 
 extern "C" int plb_pack_im2col(const float *x1, const float *x2, int64_t N, int64_t cin_src, int64_t H, int64_t W,

@@ -44,7 +44,16 @@ def cross_features_cdist(x, y, a: int):
     return ops.cross_statistic(x, y, a, ops.MODE_NEG_CDIST)
 
 
-_FUSED_MODES = {cross_features_inner_product: ops.MODE_INNER, cross_features_cdist: ops.MODE_NEG_CDIST}
+def cross_features_correlation(x, y, a: int):
+    """Pearson correlation between the axis-``a`` slices of x and y over all other axes — the third
+    statistic BASELINE.json's north_star names (not in the reference, which ships the two siblings above):
+    built from the cross-Gram, the per-unit sums and sums of squares the fused kernel accumulates in the
+    same pass.  A unit without variance correlates with nothing (0, where numpy.corrcoef gives NaN)."""
+    return ops.cross_statistic(x, y, a, ops.MODE_CORR)
+
+
+_FUSED_MODES = {cross_features_inner_product: ops.MODE_INNER, cross_features_cdist: ops.MODE_NEG_CDIST,
+                cross_features_correlation: ops.MODE_CORR}
 
 
 # ------------------------------------------------------------------ dual-model graph
@@ -283,8 +292,9 @@ class CrossAccumulator:
         st = _TapState()
         st.ra, st.rb, st.K, st.kb = ra, rb, oa * ia, (oa * ia + 15) // 16
         # fp64 row norms live in the slab too (zeroed by begin_batch before the first use)
-        st.q = self.pool.empty(2 * (ra + rb)).view(torch.float64).zero_() \
-            if self.mode == ops.MODE_NEG_CDIST else None
+        # [qa | qb] sums of squares, [sa | sb] sums for the correlation statistic
+        nq = {ops.MODE_INNER: 0, ops.MODE_NEG_CDIST: ra + rb, ops.MODE_CORR: 2 * (ra + rb)}[self.mode]
+        st.q = self.pool.empty(2 * nq).view(torch.float64).zero_() if nq else None
         st.plan, st.version, st.group, st.slot = None, -1, t.group, None
         # narrow taps (C <= 128) are HBM-bound: the fused kernel reads the activations once, in place,
         # right behind their producer — no planes, nothing deferred
@@ -295,7 +305,8 @@ class CrossAccumulator:
             st.direct, st.deferred, st.pa, st.pb, st.version = True, False, None, None, None
             st.plan = ops.TmaGramPlan(ra, oa, ia, self.device, pool=self.pool)
             return st
-        st.direct = (not self.overlap) and fp32 and ops.direct_gram_eligible(xa, xb, t.axis)
+        st.direct = (not self.overlap) and fp32 and self.mode != ops.MODE_CORR and \
+            ops.direct_gram_eligible(xa, xb, t.axis)
         if st.direct:
             st.deferred, st.pa, st.pb, st.version = False, None, None, None
             st.plan = ops.DirectGramPlan(ra, st.K, self.device, pool=self.pool)
@@ -352,27 +363,40 @@ class CrossAccumulator:
             self._next_slot = (st.slot + 1) % self.arena.slots
         return t, st
 
+    @staticmethod
+    def _moments(st):
+        """(qa, qb, sa, sb) views of the tap's fp64 row-moment buffer (None where the mode has none)."""
+        if st.q is None:
+            return None, None, None, None
+        n = st.ra + st.rb
+        qa, qb = st.q[:st.ra], st.q[st.ra:n]
+        if st.q.numel() > n:
+            return qa, qb, st.q[n:n + st.ra], st.q[n + st.ra:]
+        return qa, qb, None, None
+
     def _pack(self, t, st, xa, xb):
         if xa.dtype != torch.float32:  # half / bf16 models: the statistics are computed in fp32
             xa = xa.float()
         if xb.dtype != torch.float32:
             xb = xb.float()
-        qa, qb = (st.q[:st.ra], st.q[st.ra:]) if st.q is not None else (None, None)
-        ops.pack_split_pair(xa, xb, t.axis, st.pa, st.pb, qa, qb)
+        qa, qb, sa, sb = self._moments(st)
+        ops.pack_split_pair(xa, xb, t.axis, st.pa, st.pb, qa, qb, sa, sb)
 
     def _multiply(self, st):
-        qa, qb = (st.q[:st.ra], st.q[st.ra:]) if st.q is not None else (None, None)
         st.plan.run()
-        st.plan.finalize(self.costs[st.group], self.mode, qa, qb, accumulate=True)
+        self._multiply_epilogue(st)
 
     def tap(self, idx, xa, xb):
         t, st = self._state(idx, xa, xb)
         if st.direct:
-            qa, qb = (st.q[:st.ra], st.q[st.ra:]) if st.q is not None else (None, None)
+            qa, qb, sa, sb = self._moments(st)
             if not xa.is_contiguous() or not xb.is_contiguous():  # same shape as a contiguous earlier batch
                 xa, xb = xa.contiguous(), xb.contiguous()
-            st.plan.run(xa, xb, t.axis, qa, qb)
-            st.plan.finalize(self.costs[st.group], self.mode, qa, qb, accumulate=True)
+            if sa is not None:
+                st.plan.run(xa, xb, t.axis, qa, qb, sa, sb)
+            else:
+                st.plan.run(xa, xb, t.axis, qa, qb)
+            self._multiply_epilogue(st)
             return
         if not self.overlap:
             self._pack(t, st, xa, xb)
@@ -434,8 +458,8 @@ class CrossAccumulator:
             self._multiply_epilogue(st)
 
     def _multiply_epilogue(self, st):
-        qa, qb = (st.q[:st.ra], st.q[st.ra:]) if st.q is not None else (None, None)
-        st.plan.finalize(self.costs[st.group], self.mode, qa, qb, accumulate=True)
+        qa, qb, sa, sb = self._moments(st)
+        st.plan.finalize(self.costs[st.group], self.mode, qa, qb, accumulate=True, sa=sa, sb=sb, K=st.K)
 
 
 # ------------------------------------------------------------------ public API

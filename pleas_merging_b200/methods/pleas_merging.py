@@ -604,13 +604,16 @@ def _train_adam(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, sepa
 
 def train(dataloader, model1, model2, model3, spec, perm, costs, budget_ratios, WANDB, MAX_STEPS, wandb_run,
           separate_classifier=False, merging="perm_gradmask", num_classes=1000, lr=5e-4, verbose=False,
-          model_type="rn50", *, solver="lstsq", ridge=1e-6, stats=None, distributed=False, use_cuda_graph=True):
+          model_type="rn50", *, solver="lstsq", ridge=1e-4, stats=None, distributed=False, use_cuda_graph=True):
     """Fit the merged model's layers to the source models' activations (reference :305-405).
 
     Same positional signature as the reference.  ``solver="lstsq"`` (default) is the closed
     form over the first ``MAX_STEPS + 1`` batches (the reference's loop consumes that many);
     ``solver="adam"`` replays the reference optimiser.  ``ridge`` is relative to the mean
-    diagonal of each layer's Gram matrix and is escalated tenfold when a pivot fails.  ``stats`` (dict) receives per-layer objectives.
+    diagonal of each layer's Gram matrix (default 1e-4: layers with barely more sample rows than unknowns
+    — a classifier fitted on a few hundred images — are otherwise dominated by directions the calibration
+    data hardly excites; tests/test_configs_gpu.py measures the sensitivity) and is escalated tenfold when a
+    pivot fails.  ``stats`` (dict) receives per-layer objectives.
     ``distributed=True`` (initialised torch.distributed job, same loader on every rank) deals the
     batches round-robin, reduces every layer's normal equations onto the rank that owns the layer
     (balanced by solve cost), solves layer-parallel and all-reduces the fitted weights."""

@@ -11,7 +11,7 @@ import torch
 
 from . import _native as N
 
-MODE_INNER, MODE_NEG_CDIST = 0, 1
+MODE_INNER, MODE_NEG_CDIST, MODE_CORR = 0, 1, 2
 NUM_SMS = 148  # B200; planning helpers ask the device (num_sms()) when one is present
 
 
@@ -180,14 +180,15 @@ def pack_split(x, axis, planes, kb_offset=0, row_index=None, rows=None, sumsq=No
     return kb
 
 
-def pack_split_pair(xa, xb, axis, pa, pb, sumsq_a=None, sumsq_b=None):
+def pack_split_pair(xa, xb, axis, pa, pb, sumsq_a=None, sumsq_b=None, sum_a=None, sum_b=None):
     """Packs the two operands of one tap (same shape, all rows) with ONE launch; falls back to two
     ``pack_split`` calls when the geometries differ."""
     _require_cuda_f32(xa, "pack_split_pair")
     _require_cuda_f32(xb, "pack_split_pair")
-    if xa.shape != xb.shape or pa.row_groups != pb.row_groups or (sumsq_a is None) != (sumsq_b is None):
-        pack_split(xa, axis, pa, sumsq=sumsq_a)
-        pack_split(xb, axis, pb, sumsq=sumsq_b)
+    if xa.shape != xb.shape or pa.row_groups != pb.row_groups or (sumsq_a is None) != (sumsq_b is None) \
+            or (sum_a is None) != (sum_b is None):
+        pack_split(xa, axis, pa, sumsq=sumsq_a, rowsum=sum_a)
+        pack_split(xb, axis, pb, sumsq=sumsq_b, rowsum=sum_b)
         return
     if not xa.is_contiguous():
         xa = xa.contiguous()
@@ -200,9 +201,9 @@ def pack_split_pair(xa, xb, axis, pa, pb, sumsq_a=None, sumsq_b=None):
     if PACK_TIMER is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    N.call("plb_pack_split_pair", xa.device, xa.data_ptr(), xb.data_ptr(), outer, rows, inner, pa.hi.data_ptr(),
-                                        pa.lo.data_ptr(), pb.hi.data_ptr(), pb.lo.data_ptr(), pa.row_groups, 0,
-                                        N.ptr(sumsq_a), N.ptr(sumsq_b))
+    N.call("plb_pack_split_pair_sums", xa.device, xa.data_ptr(), xb.data_ptr(), outer, rows, inner, pa.hi.data_ptr(),
+           pa.lo.data_ptr(), pb.hi.data_ptr(), pb.lo.data_ptr(), pa.row_groups, 0, N.ptr(sumsq_a), N.ptr(sumsq_b),
+           N.ptr(sum_a), N.ptr(sum_b))
     if PACK_TIMER is not None:
         e1.record()
         PACK_TIMER.append((e0, e1, 2 * 12.0 * rows * outer * inner))
@@ -292,8 +293,16 @@ class GemmPlan:
         N.call("plb_gemm_grouped", self.table.device, self.table.data_ptr(), 1, self.total_ctas, self.bn,
                                          _impl_code(_GEMM_IMPL if impl is None else impl))
 
-    def finalize(self, out, mode=MODE_INNER, qa=None, qb=None, accumulate=False):
-        """out[i, j] (+)= f(sum_s partial_s[i, j]); out fp32 or fp64 [M, N] (row stride = ldc)."""
+    def finalize(self, out, mode=MODE_INNER, qa=None, qb=None, accumulate=False, sa=None, sb=None, K=None):
+        """out[i, j] (+)= f(sum_s partial_s[i, j]); out fp32 or fp64 [M, N] (row stride = ldc).  MODE_CORR
+        additionally takes the row sums sa / sb and the contraction length K."""
+        if mode == MODE_CORR:
+            if out.dtype != torch.float32 or sa is None or sb is None or qa is None or qb is None or not K:
+                raise ValueError("finalize: the correlation epilogue needs fp32 output, qa/qb, sa/sb and K")
+            N.call("plb_cross_finalize_corr", self.partial.device, self.partial.data_ptr(), self.splits, self.ld_m,
+                   self.ld_n, self.M, self.N, qa.data_ptr(), qb.data_ptr(), sa.data_ptr(), sb.data_ptr(), int(K),
+                   out.data_ptr(), out.stride(0), int(accumulate))
+            return
         if out.dtype == torch.float64:
             c32, c64 = None, out.data_ptr()
         else:
@@ -409,13 +418,13 @@ class TmaGramPlan:
         self.alg_bytes = 2.0 * rows * K * 4
         self.symmetric = False
 
-    def run(self, x, y, axis, qa=None, qb=None):
+    def run(self, x, y, axis, qa=None, qb=None, sa=None, sb=None):
         outer, rows, inner = as_rows_view(x, axis)
         if DIRECT_TIMER is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
         N.call("plb_gram_tma", x.device, x.data_ptr(), y.data_ptr(), outer, rows, inner, self.partial.data_ptr(),
-               self.splits, MAX_CHAIN_KB, N.ptr(qa), N.ptr(qb))
+               self.splits, MAX_CHAIN_KB, N.ptr(qa), N.ptr(qb), N.ptr(sa), N.ptr(sb))
         if DIRECT_TIMER is not None:
             e1.record()
             DIRECT_TIMER.append((e0, e1, self.alg_bytes, self.alg_flops, rows))
@@ -455,34 +464,39 @@ class GroupedGemm:
 
 def cross_statistic(x, y, axis, mode):
     """One tap: [x.shape[axis], y.shape[axis]] cross-statistic matrix of two activations
-    (cross_features_inner_product / cross_features_cdist, activation_matching.py:14-46)."""
+    (cross_features_inner_product / cross_features_cdist, activation_matching.py:14-46; MODE_CORR: the
+    Pearson correlation of the unit pairs)."""
     _require_cuda_f32(x, "cross_statistic")
     _require_cuda_f32(y, "cross_statistic")
     oa, ra, ia = as_rows_view(x, axis)
     ob, rb, ib = as_rows_view(y, axis)
     if oa * ia != ob * ib:
         raise ValueError(f"cross_statistic: contraction sizes differ ({oa * ia} vs {ob * ib})")
-    kb = (oa * ia + 15) // 16
+    K = oa * ia
+    kb = (K + 15) // 16
     dev = x.device
-    need_q = mode == MODE_NEG_CDIST
-    q = torch.zeros(ra + rb, dtype=torch.float64, device=dev) if need_q else None
-    qa, qb = (q[:ra], q[ra:]) if need_q else (None, None)
+    qa = qb = sa = sb = None
+    if mode != MODE_INNER:  # fp64 row moments: [qa | qb | sa | sb]
+        q = torch.zeros(2 * (ra + rb), dtype=torch.float64, device=dev)
+        qa, qb = q[:ra], q[ra:ra + rb]
+        if mode == MODE_CORR:
+            sa, sb = q[ra + rb:2 * ra + rb], q[2 * ra + rb:]
     out = torch.empty(ra, rb, dtype=torch.float32, device=dev)
     if tma_gram_eligible(x, y, axis):  # TMA-fed fused kernel straight from the activations, no packed planes
         plan = TmaGramPlan(ra, oa, ia, dev)
-        plan.run(x, y, axis, qa, qb)
-        plan.finalize(out, mode, qa, qb, accumulate=False)
+        plan.run(x, y, axis, qa, qb, sa, sb)
+        plan.finalize(out, mode, qa, qb, accumulate=False, sa=sa, sb=sb, K=K)
         return out
-    if direct_gram_eligible(x, y, axis):  # narrow tap: fused kernel, no packed planes
-        plan = DirectGramPlan(ra, oa * ia, dev)
+    if mode != MODE_CORR and direct_gram_eligible(x, y, axis):  # round-1 narrow-tap kernel (PLB_TMA_GRAM=0)
+        plan = DirectGramPlan(ra, K, dev)
         plan.run(x, y, axis, qa, qb)
         plan.finalize(out, mode, qa, qb, accumulate=False)
         return out
     pa, pb = Planes(ra, kb, dev), Planes(rb, kb, dev)
-    pack_split_pair(x, y, axis, pa, pb, qa, qb)
+    pack_split_pair(x, y, axis, pa, pb, qa, qb, sa, sb)
     plan = GemmPlan(pa, pb, ra, rb, kb)
     plan.run()
-    plan.finalize(out, mode, qa, qb, accumulate=False)
+    plan.finalize(out, mode, qa, qb, accumulate=False, sa=sa, sb=sb, K=K)
     return out
 
 

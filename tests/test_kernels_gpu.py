@@ -237,6 +237,27 @@ def test_raw_fp32_word_as_tf32_operand_is_truncated(C):
     assert np.abs(G - Gref).max() <= 2.5e-6 * np.abs(Gref).max()
 
 
+CORR_CASES = [((4, 64, 16, 16), 1), ((3, 200, 9, 10), 1), ((2, 256, 14, 14), 1), ((6, 24), 1), ((2, 300, 7, 7), 1),
+              ((3, 512, 12, 12), 1)]
+
+
+@pytest.mark.parametrize("shape,axis", CORR_CASES)
+def test_cross_statistic_correlation(shape, axis):
+    """PLB_MODE_CORR (cross-Gram + fused row sums / sums of squares + fp64 epilogue) == numpy.corrcoef in
+    float64 to 1e-4 absolute (north-star bar; measured ~1e-6), through the TMA-fed kernel where the tap is
+    eligible and the packed path otherwise; a dead unit (all zeros) correlates with nothing."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(17)
+    x = torch.relu(torch.randn(*shape, generator=g) + 0.5)  # post-ReLU: large means against the spread
+    y = torch.relu(torch.randn(*shape, generator=g)) + 0.3 * x
+    x.select(axis, 1).zero_()  # a dead channel
+    C = ops.cross_statistic(x.cuda(), y.cuda(), axis, ops.MODE_CORR).cpu().numpy()
+    ref = O.cross_corr(x.numpy(), y.numpy(), axis)
+    assert np.isfinite(C).all() and (C[1] == 0).all()
+    assert np.abs(C - ref).max() <= 1e-4
+    assert np.abs(C - ref).max() <= 2e-5  # what 3xTF32 + fp64 moments actually deliver
+
+
 @pytest.mark.parametrize("impl", ["tcgen05", "tcgen05_v1"])
 def test_gemm_long_k_accuracy_and_splits(impl):
     """Long contractions stay at fp32-level accuracy for any K split: the persistent kernel
