@@ -488,12 +488,22 @@ def _run_b200(args):
               f"after the timed CUDA-graph region; tensor peak = TF32 dense rate measured in this run "
               f"({tf32['how']}: burst {tf32_burst:.0f}, sustained {tf32['tf32_tflops_sustained']:.0f} TFLOP/s); "
               f"isolated launches are judged against the burst figure")
-    wide = [(a, b, f) for a, b, _, f, rows in direct_timer if rows > 128]
+    # the wide-tap launches split by size: a tap of >= 3 GFLOP keeps the machine busy for tens of microseconds;
+    # the small ones (C = 256..512 at 14x14) are a few microseconds of work behind the same launch and pipeline ramp,
+    # and an un-captured launch additionally waits for the host to submit it
+    BIG = 3e9
+    wide = [(a, b, f) for a, b, _, f, rows in direct_timer if rows > 128 and f >= BIG]
+    wide_small = [(a, b, f) for a, b, _, f, rows in direct_timer if rows > 128 and f < BIG]
     narrow = [(a, b, n) for a, b, n, _, rows in direct_timer if rows <= 128]
     out["roofline"] = tensor_roofline(
         "gram_tma_kernel<2,128,128>", wide,
-        "wide taps (C >= 256, TMA-eligible): achieved = 3 x algorithmic FLOPs (2*C^2*K per tap) / summed launch time; "
-        + common)
+        "wide taps of >= 3 GFLOP (C >= 256, TMA-eligible; 92 % of the step's Gram FLOPs that take this kernel): achieved = "
+        "3 x algorithmic FLOPs (2*C^2*K per tap) / summed launch time; " + common)
+    if out["roofline"] is not None and wide_small:
+        r = tensor_roofline("gram_tma_kernel<2,128,128>", wide_small,
+                            "the same kernel on the wide taps below 3 GFLOP (launch / ramp / submission bound); " + common)
+        out["roofline"]["small_taps"] = {k: r[k] for k in ("achieved", "frac", "algorithmic_tflops", "kernel_ms_per_step",
+                                                           "launches_per_step")}
     packed = [(a, b, f) for a, b, f, _, _ in timer]
     if out["roofline"] is None:  # PLB_TMA_GRAM=0: the packed-plane GEMM is the dominant kernel again
         out["roofline"] = tensor_roofline("gemm3xtf32_v2_kernel", packed, "packed-plane 3xTF32 GEMM; " + common)
