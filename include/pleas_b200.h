@@ -169,6 +169,29 @@ int plb_cross_finalize(const float *partial, int32_t splits, int64_t ld_m, int64
                        float *cost, double *cost64, int64_t ldc, int32_t accumulate, int32_t sym_bn,
                        void *stream);
 
+/* All taps of a calibration batch in ONE launch (activation_matching.py:123-134: the per-tap cross features of a
+ * batch, summed per permutation group).  For every group the taps tap_begin..tap_end-1 (in that order) are
+ * reduced over their K splits, passed through the statistic's epilogue and added up; each cost entry is read
+ * and written once: cost[i, j] (+)= sum_t f_t(G_t[i, j]).  Tables live in device memory; blocks of group g are
+ * block_begin .. block_begin + B(n) - 1 with B(n) = ceil(n / 256) * ceil(n / 4) for n >= 256, else
+ * ceil(n / 64) * ceil(n / 16); total_blocks is their sum.  sa / sb / K are only read in
+ * PLB_MODE_CORR, qa / qb not in PLB_MODE_INNER. */
+typedef struct PlbFinalizeTap {
+  const float *partial;        /* [splits][ld_m][ld_n] fp32 */
+  const double *qa, *qb;       /* row sums of squares */
+  const double *sa, *sb;       /* row sums */
+  int64_t ld_m, ld_n, K;
+  int32_t splits, reserved;
+} PlbFinalizeTap;
+typedef struct PlbFinalizeGroup {
+  float *cost;                 /* [n][ldc] fp32 */
+  int64_t ldc;
+  int32_t n, tap_begin, tap_end, block_begin;
+} PlbFinalizeGroup;
+int plb_cross_finalize_grouped(const PlbFinalizeTap *taps_dev, const PlbFinalizeGroup *groups_dev,
+                               int32_t n_groups, int32_t total_blocks, int32_t mode, int32_t accumulate,
+                               void *stream);
+
 /* Correlation epilogue (PLB_MODE_CORR): cost[i, j] (+)= corr(x_i, y_j) from the K-split partials of
  * G = X Y^T, the rows' sums of squares qa/qb and sums sa/sb (fp64, as accumulated by plb_gram_tma /
  * plb_pack_split) and the contraction length K.  Same partial layout as plb_cross_finalize. */

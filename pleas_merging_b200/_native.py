@@ -22,6 +22,18 @@ class GemmProblem(ctypes.Structure):
     ]
 
 
+class FinalizeTap(ctypes.Structure):
+    """Mirror of PlbFinalizeTap (include/pleas_b200.h)."""
+    _fields_ = [("partial", c_ptr), ("qa", c_ptr), ("qb", c_ptr), ("sa", c_ptr), ("sb", c_ptr),
+                ("ld_m", c_i64), ("ld_n", c_i64), ("K", c_i64), ("splits", c_i32), ("reserved", c_i32)]
+
+
+class FinalizeGroup(ctypes.Structure):
+    """Mirror of PlbFinalizeGroup (include/pleas_b200.h)."""
+    _fields_ = [("cost", c_ptr), ("ldc", c_i64), ("n", c_i32), ("tap_begin", c_i32), ("tap_end", c_i32),
+                ("block_begin", c_i32)]
+
+
 _SIGNATURES = {
     "plb_version": (ctypes.c_int, []),
     "plb_last_error_string": (ctypes.c_char_p, []),
@@ -35,6 +47,7 @@ _SIGNATURES = {
                                     c_ptr]),
     "plb_pack_split_pair_sums": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i32,
                                                 c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "plb_cross_finalize_grouped": (ctypes.c_int, [c_ptr, c_ptr, c_i32, c_i32, c_i32, c_i32, c_ptr]),
     "plb_cross_finalize_corr": (ctypes.c_int, [c_ptr, c_i32, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr,
                                                c_i64, c_ptr, c_i64, c_i32, c_ptr]),
     "plb_gram_tma_geometry": (ctypes.c_int, [c_i64, ctypes.POINTER(c_i32), ctypes.POINTER(c_i32),

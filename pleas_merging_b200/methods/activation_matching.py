@@ -204,6 +204,8 @@ DEFER_FLOPS = float(os.environ.get("PLB_DEFER_FLOPS", "3e9"))
 # Taps below this many FLOPs keep the packed path even when the TMA-fed kernel could read them in place
 # (0: every eligible tap uses the fused kernel)
 TMA_MIN_FLOPS = float(os.environ.get("PLB_TMA_MIN_FLOPS", "0"))
+# pending K-split partial tiles that trigger a grouped epilogue launch (they should still be L2-resident)
+FINALIZE_FLUSH_BYTES = int(float(os.environ.get("PLB_FINALIZE_FLUSH_MB", "1e9")) * 2 ** 20)
 
 
 class _TapState:
@@ -246,6 +248,9 @@ class CrossAccumulator:
         self.arena = _Arena(device, slots=4 if overlap else 1)
         self._retired = []  # plans replaced by a rebind; captured graphs may still point at them
         self._pending = []  # deferred (small) taps of the batch in flight
+        self._final = []    # taps whose epilogue joins the next grouped launch
+        self._final_bytes = 0
+        self._final_tables = {}
         self._groups = {}   # tuple of deferred states -> GroupedGemm
         self.pool = ops.SlabPool(device)      # planes / partial tiles / row norms of the deferred taps
         self.tables = ops.TableArena(device)  # GEMM problem-table entries
@@ -273,7 +278,7 @@ class CrossAccumulator:
         return g.call_function(_tap_dispatch, (self.sink_id, len(self.taps) - 1, na, nb))
 
     def begin_batch(self, reset_costs):
-        self._pending, self._pack_events, self._live = [], [], []
+        self._pending, self._pack_events, self._live, self._final, self._final_bytes = [], [], [], [], 0
         self._slot_free, self._next_slot = {}, 0
         if reset_costs:
             self.flat.zero_()
@@ -337,8 +342,10 @@ class CrossAccumulator:
             self._retired.append((st.plan, st.pa, st.pb))
         st.pa = _View(b[0], b[1], st.ra, rga, st.kb)
         st.pb = _View(b[2], b[3], st.rb, rgb, st.kb)
+        # own partial tiles (not the arena's): every tap's epilogue is deferred to ONE grouped launch at the end
+        # of the batch, so its partials must survive until then
         st.plan = ops.GemmPlan(st.pa, st.pb, st.ra, st.rb, st.kb, splits=splits,
-                               partial=self.arena.partial[st.slot], tables=self.tables)
+                               partial=self.pool.empty(splits * m_tiles * 128 * n_tiles * bn), tables=self.tables)
         st.plan.alg_flops = 2.0 * st.ra * st.rb * st.K
         st.version = self.arena.version
 
@@ -456,10 +463,53 @@ class CrossAccumulator:
             grp.run()
         for st in pending:
             self._multiply_epilogue(st)
+        self._finalize_all()
 
     def _multiply_epilogue(self, st):
-        qa, qb, sa, sb = self._moments(st)
-        st.plan.finalize(self.costs[st.group], self.mode, qa, qb, accumulate=True, sa=sa, sb=sb, K=st.K)
+        """The tap's split-K reduction + statistic epilogue joins the batch's grouped launch (ONE per batch by
+        default).  PLB_FINALIZE_FLUSH_MB flushes earlier, while the partial tiles are still in L2 — measured slower
+        on a ResNet-50 pair: 28.3 ms/step with 38 launches (48 MB), 27.6 with 20 (96 MB), 26.3 with one, although
+        that one reads its 2 GB of partials back from DRAM."""
+        self._final.append(st)
+        pl = st.plan
+        self._final_bytes += 4 * pl.splits * pl.ld_m * pl.ld_n
+        if self._final_bytes >= FINALIZE_FLUSH_BYTES:
+            self._finalize_all()
+
+    def _finalize_all(self):
+        """ONE launch for the epilogues of all taps of the batch (plb_cross_finalize_grouped): per permutation
+        group the taps are reduced and added in tap order, each cost entry is touched once."""
+        sts, self._final, self._final_bytes = self._final, [], 0
+        if not sts:
+            return
+        key = tuple((id(st), id(st.plan)) for st in sts)  # a rebind replaces the plan (new partial tiles)
+        entry = self._final_tables.get(key)
+        if entry is None:
+            by_group = {}
+            for st in sts:
+                by_group.setdefault(st.group, []).append(st)
+            taps_raw, groups_raw, blocks = bytearray(), bytearray(), 0
+            ntaps = 0
+            for gi in sorted(by_group):
+                n = self.costs[gi].shape[0]
+                members = by_group[gi]
+                for st in members:
+                    qa, qb, sa, sb = self._moments(st)
+                    pl = st.plan
+                    taps_raw += bytes(ops.N.FinalizeTap(pl.partial.data_ptr(), ops.N.ptr(qa), ops.N.ptr(qb),
+                                                        ops.N.ptr(sa), ops.N.ptr(sb), pl.ld_m, pl.ld_n, st.K,
+                                                        pl.splits, 0))
+                groups_raw += bytes(ops.N.FinalizeGroup(self.costs[gi].data_ptr(), self.costs[gi].stride(0), n, ntaps,
+                                                        ntaps + len(members), blocks))
+                ntaps += len(members)
+                blocks += ops.finalize_grouped_blocks(n)
+            dev = self.device
+            entry = (torch.frombuffer(taps_raw, dtype=torch.uint8).to(dev), torch.frombuffer(groups_raw, dtype=torch.uint8).to(dev),
+                     len(by_group), blocks, [(st, st.plan) for st in sts])  # keeps states / plans / buffers alive
+            self._final_tables[key] = entry
+        taps_t, groups_t, ngroups, blocks, _ = entry
+        ops.N.call("plb_cross_finalize_grouped", self.device, taps_t.data_ptr(), groups_t.data_ptr(), ngroups, blocks,
+                   self.mode, 1)
 
 
 # ------------------------------------------------------------------ public API
