@@ -9,7 +9,7 @@ from .core.compiler import check_permutation_spec, get_permutation_spec
 from .core.solvers import b200_solve_lsa
 from .core.utils import (Axis, Permutation, PermutationGroup, PermutationSpec, apply_perm, invert_perm,
                          make_identity_perm, make_random_perm, perm_eq)
-from .methods import (activation_matching, cross_features_cdist, cross_features_correlation,
+from .methods import (activation_matching, clear_caches, cross_features_cdist, cross_features_correlation,
                       cross_features_inner_product, get_blocks,
                       partial_merge, reset_bn_stats, train, weight_matching)
 

@@ -302,7 +302,13 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v2(const float *const *__r
   const int n = ns[prob];
   const int64_t ld = lds[prob];
   const float *__restrict__ C = costs[prob];
-  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  // The block is sized for the LARGEST problem of the batch; a smaller problem keeps only the warps its own
+  // columns need (CPT columns per thread) and retires the rest before the first barrier: every Dijkstra step
+  // pays one block barrier and a cross-warp reduction, so a 64-unit group behind a 2048-unit one would
+  // otherwise synchronise 32 warps per step instead of 1.
+  const int need = max(32, (((n + CPT - 1) / CPT + 31) / 32) * 32);
+  const int tid = threadIdx.x, nthr = min((int)blockDim.x, need), lane = tid & 31, warp = tid >> 5;
+  if (tid >= nthr) return;
   const int nwarps = nthr >> 5;
   const double sgn = maximize ? -1.0 : 1.0;
   LapSmem s = carve(lap_smem, n);

@@ -43,11 +43,24 @@ def get_blocks(spec: PermutationSpec, perm: Permutation, costs, ratios: Ratios, 
     a ratio within 1e-3 of 1.0 forces the identity permutation."""
     ratios = expand_ratios(spec, ratios)
     device = _device_of(costs)
-    blocks = {}
-    for axis, P in perm.items():
+    # every group's kernel is enqueued first; ONE readback of all merged-unit counts then sizes the views
+    axes = list(perm.keys())
+    sizes = [int(perm[a].numel()) for a in axes]
+    bufs = torch.empty(4, max(sum(sizes), 1), dtype=torch.int64, device=device)
+    counts = torch.zeros(max(len(axes), 1), dtype=torch.int32, device=device)
+    perms_dev = torch.cat([perm[a].reshape(-1).to(torch.int64) for a in axes]).to(device) if axes else None
+    off, spans = 0, []
+    for gi, (axis, n) in enumerate(zip(axes, sizes)):
         r = float(ratios[axis])
         C = costs[axis].to(device=device, dtype=torch.float32)
-        blocks[axis] = ops.get_blocks_group(C, P, r, abs(r - 1.0) < 1e-3)
+        ops.get_blocks_launch(C, perms_dev[off:off + n], r, abs(r - 1.0) < 1e-3, bufs[:, off:off + n],
+                              counts[gi:gi + 1])
+        spans.append((off, n))
+        off += n
+    merged = counts.cpu().tolist()
+    blocks = {}
+    for axis, (o, n), m in zip(axes, spans, merged):
+        blocks[axis] = (bufs[0, o:o + m], bufs[1, o:o + m], bufs[2, o:o + n - m], bufs[3, o:o + n - m])
     return blocks
 
 

@@ -65,8 +65,11 @@ class SlabPool:
     first calibration batch stall the host behind the queued forward kernels (measured: 1.4-2.4 s
     for a ResNet-50 pair).  A pool takes chunks of 0.5 GB and up (doubling), hands out 256-byte
     aligned float32 views, and on ``release()`` returns its chunks to a per-device free list that
-    later pools reuse, so repeated calls allocate nothing."""
-    _free = {}  # device -> list of float32 chunks
+    later pools reuse, so repeated calls allocate nothing.  A released chunk carries an event recorded
+    on the releasing stream; whoever reuses it waits for that event first (side streams of the previous
+    owner may still be reading it).  ``SlabPool.trim()`` hands the cached chunks back to PyTorch's
+    allocator."""
+    _free = {}  # device -> list of (float32 chunk, release event)
 
     def __init__(self, device):
         self.device = torch.device(device)
@@ -78,10 +81,13 @@ class SlabPool:
         need = (nfloats + 63) // 64 * 64
         if not self.chunks or self.used + need > self.chunks[-1].numel():
             free = SlabPool._free.setdefault(self.device, [])
-            fit = [c for c in free if c.numel() >= need]
+            fit = [e for e in free if e[0].numel() >= need]
             if fit:
-                chunk = min(fit, key=lambda c: c.numel())
-                free[:] = [c for c in free if c is not chunk]  # identity, not tensor ==
+                entry = min(fit, key=lambda e: e[0].numel())
+                free[:] = [e for e in free if e is not entry]  # identity, not tensor ==
+                chunk, ev = entry
+                if ev is not None:
+                    torch.cuda.current_stream(self.device).wait_event(ev)
             else:
                 chunk = torch.empty(max(need, self.next_floats), dtype=torch.float32, device=self.device)
                 self.next_floats = min(self.next_floats * 2, 1 << 30)
@@ -92,8 +98,18 @@ class SlabPool:
         return out
 
     def release(self):
-        SlabPool._free.setdefault(self.device, []).extend(self.chunks)
+        if self.chunks:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            SlabPool._free.setdefault(self.device, []).extend((c, ev) for c in self.chunks)
         self.chunks, self.used = [], 0
+
+    @classmethod
+    def trim(cls, device=None):
+        """Returns the cached free chunks (of ``device``, or of every device) to the caching allocator."""
+        for dev in list(cls._free):
+            if device is None or torch.device(device) == dev:
+                cls._free[dev] = []
 
 
 class TableArena:
@@ -509,6 +525,9 @@ def cross_statistic(x, y, axis, mode):
 
 # ------------------------------------------------------------------------------------ LAP
 
+LAP_MAX_N = 4096  # plb_lap_solve_batched / plb_get_blocks keep all per-unit state in shared memory
+
+
 def lap_solve_batched(costs, maximize=True):
     """Solves all square problems in one launch.  Returns (list of int64 CUDA tensors,
     objective fp64 CUDA tensor, status int32 CUDA tensor)."""
@@ -522,6 +541,9 @@ def lap_solve_batched(costs, maximize=True):
             raise ValueError(f"lap_solve_batched: square cost matrices only, got {tuple(c.shape)}")
         mats.append(c if c.stride(1) == 1 else c.contiguous())
     ns = [m.shape[0] for m in mats]
+    if max(ns) > LAP_MAX_N:
+        raise ValueError(f"lap_solve_batched: a permutation group has {max(ns)} units; the shared-memory assignment "
+                         f"kernel holds at most {LAP_MAX_N} (45 B of solver state per unit in 227 KB)")
     outs = [torch.empty(n, dtype=torch.int64, device=dev) for n in ns]
     table = torch.tensor([[m.data_ptr() for m in mats], [o.data_ptr() for o in outs]], dtype=torch.int64).to(dev)
     meta = torch.tensor([ns, [m.stride(0) for m in mats]], dtype=torch.int32).to(dev)
@@ -543,17 +565,24 @@ def raise_on_lap_status(status):
 
 # ------------------------------------------------------------------------------------ blocks
 
+def get_blocks_launch(cost, perm, ratio, identity, buf, count):
+    """Enqueues get_blocks for one group (partial_matching.py:76-86) into caller-provided buffers: buf int64
+    [4, n] receives Q[mask], P[mask], Q[~mask], P[~mask] (order-preserving, front-packed), count int32[1] the
+    number of merged units.  No synchronisation."""
+    _require_cuda_f32(cost, "get_blocks")
+    n = cost.shape[0]
+    N.call("plb_get_blocks", cost.device, cost.data_ptr(), cost.stride(0), perm.data_ptr(), n, float(ratio),
+           int(identity), buf[0].data_ptr(), buf[1].data_ptr(), buf[2].data_ptr(), buf[3].data_ptr(), count.data_ptr())
+
+
 def get_blocks_group(cost, perm, ratio, identity):
     """(Q[mask], P[mask], Q[~mask], P[~mask]) for one group (partial_matching.py:76-86)."""
-    _require_cuda_f32(cost, "get_blocks_group")
     n = cost.shape[0]
     dev = cost.device
     buf = torch.empty(4, n, dtype=torch.int64, device=dev)
     counts = torch.zeros(1, dtype=torch.int32, device=dev)
     perm = perm.to(device=dev, dtype=torch.int64).contiguous()
-    N.call("plb_get_blocks", dev, cost.data_ptr(), cost.stride(0), perm.data_ptr(), n, float(ratio), int(identity),
-                                   buf[0].data_ptr(), buf[1].data_ptr(), buf[2].data_ptr(), buf[3].data_ptr(),
-                                   counts.data_ptr())
+    get_blocks_launch(cost, perm, ratio, identity, buf, counts)
     m = int(counts.item())
     return buf[0, :m], buf[1, :m], buf[2, :n - m], buf[3, :n - m]
 
