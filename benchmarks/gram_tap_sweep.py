@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--tf32-peak", type=float, default=757.0)
     ap.add_argument("--hbm-peak", type=float, default=6550.0)
     ap.add_argument("--only", default=None, help="C,H filter, e.g. 256,56")
+    ap.add_argument("--nbuf", type=int, default=None, help="operand pairs to rotate through (default: enough to exceed L2; "
+                    "1 keeps a small tap L2-resident)")
     args = ap.parse_args()
     if args.impl != "tma":
         ops.TMA_GRAM = False
@@ -41,7 +43,7 @@ def main():
             continue
         B = args.batch
         nbytes = 2 * B * C * H * H * 4
-        nbuf = max(2, min(16, int(300e6 // nbytes) + 1))
+        nbuf = args.nbuf or max(2, min(16, int(300e6 // nbytes) + 1))
         g = torch.Generator(device=dev).manual_seed(C * 1000 + H)
         xs = [torch.relu(torch.randn(B, C, H, H, generator=g, device=dev)) for _ in range(nbuf)]
         ys = [torch.relu(torch.randn(B, C, H, H, generator=g, device=dev)) for _ in range(nbuf)]

@@ -63,13 +63,19 @@ static int make_operand_map(CUtensorMap *m, const float *base, int64_t outer, in
                             int box_rows, int box_k) {
   EncodeTiledFn enc = encode_tiled();
   PLB_REQUIRE(enc != nullptr, PLB_EINVAL, "plb_gram_tma: cuTensorMapEncodeTiled is not available from this driver");
+  static int exp_flags = -1;  // experiments only (PLB_TMA_EXP): bit 1 = no L2 promotion, bit 2 = 128 B promotion
+  if (exp_flags < 0) {
+    const char *e = getenv("PLB_TMA_EXP");
+    exp_flags = e ? atoi(e) : 0;
+  }
   cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)C, (cuuint64_t)outer};
   cuuint64_t gstride[2] = {(cuuint64_t)inner * 4, (cuuint64_t)inner * (cuuint64_t)C * 4};
   cuuint32_t box[3] = {(cuuint32_t)box_k, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_k == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   (exp_flags & 2) ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                   : ((exp_flags & 4) ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PLB_REQUIRE(r == CUDA_SUCCESS, PLB_EINVAL, "plb_gram_tma: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return PLB_OK;
@@ -319,7 +325,7 @@ __global__ void __launch_bounds__(384, 1) gram_tma_kernel(const __grid_constant_
               const uint32_t st = smem_base + s * Cfg::kStageBytes;
 #pragma unroll
               for (int j = 0; j < kBoxK / 8; ++j) {
-                if (j < nk8) {
+                if (j < nk8 && p.debug != 3) {
                   const uint64_t a_hi = umma_desc_sw<Cfg::kRowBytes>(st + 32 * j);
                   const uint64_t b_hi = umma_desc_sw<Cfg::kRowBytes>(st + Cfg::kXBytes + 32 * j);
                   const uint64_t a_lo = umma_desc_sw<Cfg::kRowBytes>(st + Cfg::kRawBytes + 32 * j);
@@ -364,7 +370,7 @@ __global__ void __launch_bounds__(384, 1) gram_tma_kernel(const __grid_constant_
         mbar_wait_wd(&bar_raw[s], ph);
         if (p.trace && blockIdx.x == 0 && ct == 0 && i < 256) p.trace[i * 4 + 1] = clock64();
         uint8_t *st = smem + (size_t)s * Cfg::kStageBytes + (uint32_t)ct * 16u;
-        if (p.debug != 1)
+        if (p.debug != 1 && p.debug != 3)
 #pragma unroll
         for (int q = 0; q < Cfg::kPer; ++q) {
           const float4 v = *reinterpret_cast<const float4 *>(st + q * 1024);
