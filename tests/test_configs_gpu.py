@@ -276,3 +276,40 @@ def test_train_rn18_logits_adam_replay_vs_reference():
     err = _rel_l2(logits, G["logits/adam"])
     print(f"adam replay vs reference: logit rel-L2 {err:.2e}")
     assert err <= 5e-2
+
+
+# ----------------------------------------------------------------------------------------- config 4
+
+def test_config4_rn101_domainnet_vs_oracle():
+    """BASELINE config 4's model pair — ResNet-101 with the 345-class DomainNet head
+    (experiments/shared_label_space/run_domainnet.py:182-186), 71 permutation groups, 344 taps — on one batch of
+    4 x 224x224 (the oracle port's CPU forward bounds the size): cost matrices within the 1e-4 bar of the oracle and
+    identical permutations (or an equal optimum within 1e-6 on the oracle's costs); the spec equals the reference's
+    (tests/golden/spec_resnet101.json; the head changes no permutation group)."""
+    import torchvision
+
+    P = _pkg()
+
+    def build(seed):
+        torch.manual_seed(seed)
+        m = torchvision.models.resnet101()
+        m.fc = torch.nn.Linear(2048, 345)
+        return m.eval()
+
+    m1, m2 = build(0), build(1)
+    spec = P.get_permutation_spec(m1, ((1, 3, 224, 224),))
+    jspec = load_spec_json("resnet101")
+    assert [(k.key, k.axis, pg.size) for k, pg in spec.items()] == [(g["key"][0], g["key"][1], g["size"]) for g in jspec]
+    g = torch.Generator().manual_seed(123)
+    loader = [(torch.randn(4, 3, 224, 224, generator=g), 0)]
+    ocosts = O.matching_costs(jspec, m1, m2, loader, 1, "cdist", "sum")
+    perm, costs = P.activation_matching(spec, m1.cuda(), m2.cuda(), loader, 1, output_costs=True)
+    flips, worst = 0, 0.0
+    for k in spec:
+        oc = ocosts[(k.key, k.axis)]
+        worst = max(worst, _relerr(costs[k].cpu().numpy(), oc))
+        operm, _ = O.solve_lsa(oc, True)
+        flips += _perm_or_objective(perm[k].numpy(), operm, oc, str(k))
+    assert worst <= 1e-4
+    print(f"config 4 (ResNet-101 / 345 classes): max cost rel-err {worst:.2e}; assignments differing from the oracle: "
+          f"{flips} of {sum(pg.size for pg in spec.values())}")
