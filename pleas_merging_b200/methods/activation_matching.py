@@ -251,6 +251,7 @@ class CrossAccumulator:
         self._final = []    # taps whose epilogue joins the next grouped launch
         self._final_bytes = 0
         self._final_tables = {}
+        self._last_final = None
         self._groups = {}   # tuple of deferred states -> GroupedGemm
         self.pool = ops.SlabPool(device)      # planes / partial tiles / row norms of the deferred taps
         self.tables = ops.TableArena(device)  # GEMM problem-table entries
@@ -355,6 +356,8 @@ class CrossAccumulator:
             for st in t.states.values():
                 if not st.deferred and not st.direct and st.version != self.arena.version:
                     self._bind(st)
+        if self._last_final:  # the epilogue table of the next (captured) batch exists before the capture starts
+            self._final_table(self._last_final)
 
     def _state(self, idx, xa, xb):
         t = self.taps[idx]
@@ -476,12 +479,8 @@ class CrossAccumulator:
         if self._final_bytes >= FINALIZE_FLUSH_BYTES:
             self._finalize_all()
 
-    def _finalize_all(self):
-        """ONE launch for the epilogues of all taps of the batch (plb_cross_finalize_grouped): per permutation
-        group the taps are reduced and added in tap order, each cost entry is touched once."""
-        sts, self._final, self._final_bytes = self._final, [], 0
-        if not sts:
-            return
+    def _final_table(self, sts):
+        """Device tables (taps in order per group) of the grouped epilogue for this list of tap states."""
         key = tuple((id(st), id(st.plan)) for st in sts)  # a rebind replaces the plan (new partial tiles)
         entry = self._final_tables.get(key)
         if entry is None:
@@ -503,11 +502,19 @@ class CrossAccumulator:
                                                         ntaps + len(members), blocks))
                 ntaps += len(members)
                 blocks += ops.finalize_grouped_blocks(n)
-            dev = self.device
-            entry = (torch.frombuffer(taps_raw, dtype=torch.uint8).to(dev), torch.frombuffer(groups_raw, dtype=torch.uint8).to(dev),
+            entry = (self.tables.put(bytes(taps_raw)), self.tables.put(bytes(groups_raw)),
                      len(by_group), blocks, [(st, st.plan) for st in sts])  # keeps states / plans / buffers alive
             self._final_tables[key] = entry
-        taps_t, groups_t, ngroups, blocks, _ = entry
+        return entry
+
+    def _finalize_all(self):
+        """ONE launch for the epilogues of the pending taps (plb_cross_finalize_grouped): per permutation
+        group the taps are reduced and added in tap order, each cost entry is touched once."""
+        sts, self._final, self._final_bytes = self._final, [], 0
+        if not sts:
+            return
+        self._last_final = sts
+        taps_t, groups_t, ngroups, blocks, _ = self._final_table(sts)
         ops.N.call("plb_cross_finalize_grouped", self.device, taps_t.data_ptr(), groups_t.data_ptr(), ngroups, blocks,
                    self.mode, 1)
 

@@ -166,6 +166,7 @@ class _Workspace:
     def __init__(self, device):
         self.device, self.cap, self.buf, self.version = device, {}, {}, 0
         self._retired = []  # outgrown buffers stay alive: captured CUDA graphs may point at them
+        self.tables = ops.TableArena(device)  # GEMM problem entries through pinned staging (no synchronising copies)
 
     def ensure(self, name, floats):
         if self.cap.get(name, 0) < floats:
@@ -230,9 +231,9 @@ class _LayerLS:
         pu = _View(ws.buf["u_hi"], ws.buf["u_lo"], self.K, rgu, kb)
         py = _View(ws.buf["y_hi"], ws.buf["y_lo"], self.cout, rgy, kb)
         plan_g = ops.GemmPlan(pu, pu, self.K, self.K, kb, symmetric=True, partial=ws.buf["partial"],
-                              splits=self._geometry(self.K, True, kb)[3])
+                              splits=self._geometry(self.K, True, kb)[3], tables=ws.tables)
         plan_r = ops.GemmPlan(pu, py, self.K, self.cout, kb, partial=ws.buf["partial"],
-                              splits=self._geometry(self.cout, False, kb)[3])
+                              splits=self._geometry(self.cout, False, kb)[3], tables=ws.tables)
         plan_g.alg_flops = 2.0 * self.K * self.K * L
         plan_r.alg_flops = 2.0 * self.K * self.cout * L
         self.bound[L, ws.version] = (pu, py, plan_g, plan_r)

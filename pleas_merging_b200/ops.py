@@ -29,6 +29,18 @@ PACK_TIMER = None  # set to a list by bench.py to collect (start, end, algorithm
 GEMM_TIMER = None  # set to a list by bench.py to collect (start, end, flops, bn, n_problems) per GEMM launch
 
 
+def _timer_events():
+    """Two CUDA events for bracketing ONE launch on the current stream (bench instrumentation).  A short spin
+    kernel is enqueued first so that the stream is still busy while the host submits the event, the launch and the
+    second event: otherwise the first event completes at once and the measured interval includes the host's
+    submission latency of the launch (~5-10 us from Python, 10 % of a 70 us kernel), which a CUDA-graph replay
+    of the same launch never sees."""
+    torch.cuda._sleep(60000)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    return e0, e1
+
+
 def set_gemm_impl(name):
     global _GEMM_IMPL
     assert name in ("tcgen05", "tcgen05_v1", "simt")
@@ -113,31 +125,32 @@ class SlabPool:
 
 
 class TableArena:
-    """Device memory for GEMM problem-table entries, filled through a pinned staging mirror with
-    asynchronous copies (a pageable cudaMemcpy per plan would synchronise the device each time)."""
+    """Device memory for kernel argument tables (GEMM problem entries, epilogue tap / group tables), filled
+    through a pinned staging mirror with asynchronous copies (a pageable cudaMemcpy per table would synchronise
+    the device each time, and must never be captured into a CUDA graph)."""
     ENTRY = ctypes.sizeof(N.GemmProblem)
 
     def __init__(self, device, capacity=4096):
-        self.device, self.capacity, self.count = torch.device(device), capacity, 0
-        self.dev = torch.empty(capacity * self.ENTRY, dtype=torch.uint8, device=self.device)
-        self.host = torch.empty(capacity * self.ENTRY, dtype=torch.uint8).pin_memory()
+        self.device, self.nbytes, self.used = torch.device(device), capacity * self.ENTRY, 0
+        self.dev = torch.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+        self.host = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
         self._older = []
 
     def put(self, raw):
+        """Copies ``raw`` (bytes) into the arena (16-byte aligned) and returns the device view."""
         n = len(raw)
-        assert n % self.ENTRY == 0
-        k = n // self.ENTRY
-        if self.count + k > self.capacity:  # start a fresh block; views into the old one stay valid
+        need = (n + 15) // 16 * 16
+        if self.used + need > self.nbytes:  # start a fresh block; views into the old one stay valid
             self._older.append((self.dev, self.host))
-            self.capacity = max(self.capacity, 2 * k)
-            self.dev = torch.empty(self.capacity * self.ENTRY, dtype=torch.uint8, device=self.device)
-            self.host = torch.empty(self.capacity * self.ENTRY, dtype=torch.uint8).pin_memory()
-            self.count = 0
-        lo, hi = self.count * self.ENTRY, (self.count + k) * self.ENTRY
+            self.nbytes = max(self.nbytes, 2 * need)
+            self.dev = torch.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+            self.host = torch.empty(self.nbytes, dtype=torch.uint8).pin_memory()
+            self.used = 0
+        lo, hi = self.used, self.used + n
         self.host[lo:hi] = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
         view = self.dev[lo:hi]
         view.copy_(self.host[lo:hi], non_blocking=True)
-        self.count += k
+        self.used += need
         return view
 
 
@@ -184,8 +197,7 @@ def pack_split(x, axis, planes, kb_offset=0, row_index=None, rows=None, sumsq=No
     if kb_offset + kb > planes.k_blocks or rows > planes.row_groups * 8:
         raise ValueError("pack_split: operand does not fit the planes")
     if PACK_TIMER is not None:  # bench instrumentation: CUDA events around this launch
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0, e1 = _timer_events()
     N.call("plb_pack_split", x.device, x.data_ptr(), outer, src_rows, inner, N.ptr(row_index), rows,
                                    planes.hi.data_ptr(), planes.lo.data_ptr(), planes.row_groups, kb_offset,
                                    N.ptr(sumsq), N.ptr(rowsum))
@@ -215,8 +227,7 @@ def pack_split_pair(xa, xb, axis, pa, pb, sumsq_a=None, sumsq_b=None, sum_a=None
     if kb > min(pa.k_blocks, pb.k_blocks) or rows > pa.row_groups * 8:
         raise ValueError("pack_split_pair: operands do not fit the planes")
     if PACK_TIMER is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0, e1 = _timer_events()
     N.call("plb_pack_split_pair_sums", xa.device, xa.data_ptr(), xb.data_ptr(), outer, rows, inner, pa.hi.data_ptr(),
            pa.lo.data_ptr(), pb.hi.data_ptr(), pb.lo.data_ptr(), pa.row_groups, 0, N.ptr(sumsq_a), N.ptr(sumsq_b),
            N.ptr(sum_a), N.ptr(sum_b))
@@ -304,8 +315,7 @@ class GemmPlan:
 
     def run(self, impl=None):
         if GEMM_TIMER is not None:  # bench instrumentation: CUDA events around this launch
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            e0, e1 = _timer_events()
             self._launch(impl)
             e1.record()
             GEMM_TIMER.append((e0, e1, self.alg_flops, self.bn, 1))
@@ -367,8 +377,7 @@ class DirectGramPlan:
     def run(self, x, y, axis, qa=None, qb=None):
         outer, rows, inner = as_rows_view(x, axis)
         if DIRECT_TIMER is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            e0, e1 = _timer_events()
         N.call("plb_gram_direct", x.device, x.data_ptr(), y.data_ptr(), outer, rows, inner, self.partial.data_ptr(),
                                         self.splits, MAX_CHAIN_KB, N.ptr(qa), N.ptr(qb))
         if DIRECT_TIMER is not None:
@@ -444,8 +453,7 @@ class TmaGramPlan:
     def run(self, x, y, axis, qa=None, qb=None, sa=None, sb=None):
         outer, rows, inner = as_rows_view(x, axis)
         if DIRECT_TIMER is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            e0, e1 = _timer_events()
         N.call("plb_gram_tma", x.device, x.data_ptr(), y.data_ptr(), outer, rows, inner, self.partial.data_ptr(),
                self.splits, MAX_CHAIN_KB, N.ptr(qa), N.ptr(qb), N.ptr(sa), N.ptr(sb))
         if DIRECT_TIMER is not None:
@@ -476,8 +484,7 @@ class GroupedGemm:
     def run(self, impl=None):
         name = _GEMM_IMPL if impl is None else impl
         if GEMM_TIMER is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            e0, e1 = _timer_events()
         N.call("plb_gemm_grouped", self.table.device, self.table.data_ptr(), len(self.plans), self.total_items, self.bn,
                                          _impl_code(name))
         if GEMM_TIMER is not None:
