@@ -173,8 +173,8 @@ int plb_cross_finalize(const float *partial, int32_t splits, int64_t ld_m, int64
  * batch, summed per permutation group).  For every group the taps tap_begin..tap_end-1 (in that order) are
  * reduced over their K splits, passed through the statistic's epilogue and added up; each cost entry is read
  * and written once: cost[i, j] (+)= sum_t f_t(G_t[i, j]).  Tables live in device memory; blocks of group g are
- * block_begin .. block_begin + B(n) - 1 with B(n) = ceil(n / 256) * ceil(n / 4) for n >= 256, else
- * ceil(n / 64) * ceil(n / 16); total_blocks is their sum.  sa / sb / K are only read in
+ * block_begin .. block_begin + B(n) - 1 with B(n) = ceil(n / 256) * ceil(n / 16) for n >= 256, else
+ * ceil(n / 64) * ceil(n / 64); total_blocks is their sum.  sa / sb / K are only read in
  * PLB_MODE_CORR, qa / qb not in PLB_MODE_INNER. */
 typedef struct PlbFinalizeTap {
   const float *partial;        /* [splits][ld_m][ld_n] fp32 */

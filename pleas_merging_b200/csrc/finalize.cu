@@ -178,15 +178,14 @@ extern "C" int plb_cross_finalize(const float *partial, int32_t splits, int64_t 
 
 namespace plb {
 
-// One launch for ALL taps of a calibration batch.  A block owns a 16-row x 64-column tile of one permutation
-// group's cost matrix (thread = one column x 4 rows, consecutive lanes = consecutive columns) and walks the
-// group's taps in order: each tap's K-split partials are streamed with 8 independent loads in flight per thread
-// and summed in fp64 in a fixed order, the tap's statistic epilogue is applied, the taps' values are added up in
-// registers and the cost entries are read and written ONCE per batch (the per-tap kernels did one
+// One launch for ALL taps of a calibration batch.  A block owns a tile of one permutation group's cost matrix
+// (thread = 4 consecutive columns x 4 rows; consecutive lanes = consecutive float4 of a partial row) and walks the
+// group's taps in order: each tap's K-split partials are streamed as float4 with 8 independent 16-byte loads in
+// flight per thread and summed in fp64 in a fixed order, the tap's statistic epilogue is applied, the taps' values
+// are added up in registers and the cost entries are read and written ONCE per batch (the per-tap kernels did one
 // read-modify-write per tap and cost 174 launches per ResNet-50 batch).  No atomics, no shared memory.
-// Tile: 256 columns x 4 rows from 256 units up (each warp-row of a split is then part of a 1 KB contiguous run),
-// 64 columns x 16 rows below.
-constexpr int kGRows = 4;
+// Tile: 256 columns x 16 rows from 256 units up, 64 columns x 64 rows below (block = 256 threads either way).
+constexpr int kGRows = 4, kGVec = 4;
 
 __global__ void __launch_bounds__(256) cross_finalize_grouped_kernel(const PlbFinalizeTap *__restrict__ taps,
                                                                      const PlbFinalizeGroup *__restrict__ groups,
@@ -198,70 +197,94 @@ __global__ void __launch_bounds__(256) cross_finalize_grouped_kernel(const PlbFi
   }
   const PlbFinalizeGroup g = groups[lo];
   const int local = (int)blockIdx.x - g.block_begin;
-  const int cols = g.n >= 256 ? 256 : 64, tile_rows = g.n >= 256 ? kGRows : 4 * kGRows;
+  const int cols = g.n >= 256 ? 256 : 64;                 // columns per block
+  const int tpr = cols / kGVec;                           // threads per tile row: 64 or 16
+  const int tile_rows = (256 / tpr) * kGRows;             // 16 or 64
   const int col_blocks = (g.n + cols - 1) / cols;
-  const int tx = threadIdx.x % cols, ty = threadIdx.x / cols;
-  const int64_t j = (int64_t)(local % col_blocks) * cols + tx;
+  const int tx = threadIdx.x % tpr, ty = threadIdx.x / tpr;
+  const int64_t j = (int64_t)(local % col_blocks) * cols + tx * kGVec;
   const int64_t i0 = (int64_t)(local / col_blocks) * tile_rows + ty * kGRows;
   if (j >= g.n || i0 >= g.n) return;
   bool live[kGRows];
-  float total[kGRows];
+  float total[kGRows][kGVec];
 #pragma unroll
   for (int r = 0; r < kGRows; ++r) {
     live[r] = i0 + r < g.n;
-    total[r] = 0.f;
+#pragma unroll
+    for (int c = 0; c < kGVec; ++c) total[r][c] = 0.f;
   }
   for (int t = g.tap_begin; t < g.tap_end; ++t) {
     const PlbFinalizeTap tp = taps[t];
-    const int64_t split_stride = tp.ld_m * tp.ld_n;
-    const float *p[kGRows];
-    double gs[kGRows];
+    const int64_t split_stride = tp.ld_m * tp.ld_n;  // ld_n is a multiple of 64: every float4 below is aligned and in range
+    const float4 *p[kGRows];
+    double gs[kGRows][kGVec];
 #pragma unroll
     for (int r = 0; r < kGRows; ++r) {
-      p[r] = tp.partial + (live[r] ? i0 + r : i0) * tp.ld_n + j;  // dead rows re-read row i0 (always valid)
-      gs[r] = 0.0;
+      p[r] = reinterpret_cast<const float4 *>(tp.partial + (live[r] ? i0 + r : i0) * tp.ld_n + j);  // dead rows re-read row i0
+#pragma unroll
+      for (int c = 0; c < kGVec; ++c) gs[r][c] = 0.0;
     }
+    const int64_t stride4 = split_stride / 4;
     int s2 = 0;
-    for (; s2 + 1 < tp.splits; s2 += 2) {  // 2 splits x 4 rows = 8 independent loads in flight
-      float v0[kGRows], v1[kGRows];
+    for (; s2 + 1 < tp.splits; s2 += 2) {  // 2 splits x 4 rows = 8 independent 16-byte loads in flight
+      float4 v0[kGRows], v1[kGRows];
 #pragma unroll
       for (int r = 0; r < kGRows; ++r) {
-        v0[r] = p[r][(int64_t)s2 * split_stride];
-        v1[r] = p[r][(int64_t)(s2 + 1) * split_stride];
+        v0[r] = p[r][(int64_t)s2 * stride4];
+        v1[r] = p[r][(int64_t)(s2 + 1) * stride4];
       }
 #pragma unroll
-      for (int r = 0; r < kGRows; ++r) gs[r] += (double)v0[r] + (double)v1[r];
+      for (int r = 0; r < kGRows; ++r) {
+        gs[r][0] += (double)v0[r].x + (double)v1[r].x;
+        gs[r][1] += (double)v0[r].y + (double)v1[r].y;
+        gs[r][2] += (double)v0[r].z + (double)v1[r].z;
+        gs[r][3] += (double)v0[r].w + (double)v1[r].w;
+      }
     }
     if (s2 < tp.splits) {
 #pragma unroll
-      for (int r = 0; r < kGRows; ++r) gs[r] += (double)p[r][(int64_t)s2 * split_stride];
+      for (int r = 0; r < kGRows; ++r) {
+        const float4 v = p[r][(int64_t)s2 * stride4];
+        gs[r][0] += (double)v.x;
+        gs[r][1] += (double)v.y;
+        gs[r][2] += (double)v.z;
+        gs[r][3] += (double)v.w;
+      }
     }
 #pragma unroll
     for (int r = 0; r < kGRows; ++r) {
       if (!live[r]) continue;
       const int64_t i = i0 + r;
-      float v;
-      if (mode == PLB_MODE_NEG_CDIST) {
-        const float gf = (float)gs[r];
-        const float d2 = ((float)tp.qa[i] + (float)tp.qb[j]) - 2.0f * gf;
-        v = -sqrtf(fmaxf(d2, 0.f));
-      } else if (mode == PLB_MODE_CORR) {
-        const double inv_k = 1.0 / (double)tp.K;
-        const double ma = tp.sa[i], mb = tp.sb[j];
-        const double cov = gs[r] - ma * mb * inv_k;
-        const double va = tp.qa[i] - ma * ma * inv_k, vb = tp.qb[j] - mb * mb * inv_k;
-        v = (va > 1e-12 * tp.qa[i] && vb > 1e-12 * tp.qb[j]) ? (float)(cov / sqrt(va * vb)) : 0.f;
-      } else {
-        v = (float)gs[r];
+#pragma unroll
+      for (int c = 0; c < kGVec; ++c) {
+        if (j + c >= g.n) continue;
+        float v;
+        if (mode == PLB_MODE_NEG_CDIST) {
+          const float gf = (float)gs[r][c];
+          const float d2 = ((float)tp.qa[i] + (float)tp.qb[j + c]) - 2.0f * gf;
+          v = -sqrtf(fmaxf(d2, 0.f));
+        } else if (mode == PLB_MODE_CORR) {
+          const double inv_k = 1.0 / (double)tp.K;
+          const double ma = tp.sa[i], mb = tp.sb[j + c];
+          const double cov = gs[r][c] - ma * mb * inv_k;
+          const double va = tp.qa[i] - ma * ma * inv_k, vb = tp.qb[j + c] - mb * mb * inv_k;
+          v = (va > 1e-12 * tp.qa[i] && vb > 1e-12 * tp.qb[j + c]) ? (float)(cov / sqrt(va * vb)) : 0.f;
+        } else {
+          v = (float)gs[r][c];
+        }
+        total[r][c] += v;
       }
-      total[r] += v;
     }
   }
 #pragma unroll
   for (int r = 0; r < kGRows; ++r) {
     if (!live[r]) continue;
-    float *c = g.cost + (i0 + r) * g.ldc + j;
-    *c = accumulate ? *c + total[r] : total[r];
+#pragma unroll
+    for (int c = 0; c < kGVec; ++c) {
+      if (j + c >= g.n) continue;
+      float *cp = g.cost + (i0 + r) * g.ldc + j + c;
+      *cp = accumulate ? *cp + total[r][c] : total[r][c];
+    }
   }
 }
 

@@ -237,9 +237,9 @@ def pack_split_pair(xa, xb, axis, pa, pb, sumsq_a=None, sumsq_b=None, sum_a=None
 
 
 def finalize_grouped_blocks(n):
-    """Blocks plb_cross_finalize_grouped uses for an n x n cost matrix: 256-column x 4-row tiles from
-    256 units up (1 KB contiguous per partial row), 64-column x 16-row tiles below."""
-    cols, rows = (256, 4) if n >= 256 else (64, 16)
+    """Blocks plb_cross_finalize_grouped uses for an n x n cost matrix: 256-column x 16-row tiles from
+    256 units up (1 KB contiguous per partial row), 64-column x 64-row tiles below."""
+    cols, rows = (256, 16) if n >= 256 else (64, 64)
     return ((n + cols - 1) // cols) * ((n + rows - 1) // rows)
 
 

@@ -449,6 +449,16 @@ def test_built_library_is_sm100a_native_sass():
     for n, b in body("gram_direct_kernel").items():
         assert "UTCHMMA" in b and "LDTM" in b and "LDGSTS" in b, n
     assert all("REDUX" in b for b in body("lap_kernel_v2").values())
+    # round 2: the TMA-fed Gram kernel — tensor-map loads (UTMALDG), TMEM loads, and for the CTA-pair
+    # instantiation 2-CTA MMAs with a multicast commit
+    tma = body("gram_tma_kernel")
+    assert len(tma) >= 6
+    for n, b in tma.items():
+        assert "UTMALDG" in b and "UTCHMMA" in b and "LDTM" in b, n
+        if "ILi1E" in n:  # stage hand-overs use CTA-scope barrier semantics: no GPU-scope fence anywhere
+            assert "MEMBAR.ALL.GPU" not in b and "CCTL.IVALL" not in b, n
+    pair = [b for n, b in tma.items() if "ILi2E" in n]
+    assert pair and all("UTCHMMA.2CTA" in b and "UTCBAR.2CTA.MULTICAST" in b for b in pair)
 
 
 def test_parallel_helpers_single_process_edges():
@@ -501,3 +511,61 @@ def test_public_api_signatures_match_the_reference():
                 assert got == default, (name, prm.name, got, default)
         for extra in mine[len(params):]:  # additions must not break positional calls written for the reference
             assert extra.default is not inspect.Parameter.empty or extra.kind is extra.KEYWORD_ONLY, (name, extra.name)
+
+
+def test_tma_planning_helpers_and_struct_mirrors():
+    """Host-side planning of the TMA-fed Gram kernel and of the grouped epilogue (no compute calls):
+    tiling from the C ABI's geometry helper, K-split choice, block counts, ctypes mirrors of the header structs."""
+    import ctypes
+
+    from pleas_merging_b200 import _native, ops
+
+    assert ops.tma_geometry(64) == (1, 1, 1, 128, 64)
+    assert ops.tma_geometry(128) == (1, 1, 1, 128, 128)
+    assert ops.tma_geometry(256) == (2, 1, 1, 256, 256)
+    assert ops.tma_geometry(320) == (2, 2, 2, 512, 512)  # rows past 320 are TMA zero fill
+    assert ops.tma_geometry(2048) == (2, 8, 8, 2048, 2048)
+    # K splits: one narrow tile spreads over (almost) all SMs; 16 wide tiles take few splits; never more splits
+    # than a quarter of the boxes
+    assert 100 <= ops.choose_tma_splits(1, 1, 12544, 128 * 64, 148) <= 148
+    assert ops.choose_tma_splits(16, 2, 224, 256 * 256, 148) in (4, 5, 9)
+    assert ops.choose_tma_splits(1, 2, 8, 256 * 256, 148) <= 2
+    assert ops.choose_tma_splits(4, 2, 3, 256 * 256, 148) == 1
+    # grouped epilogue: 256-column x 16-row tiles from 256 units up, 64 x 64 below
+    assert ops.finalize_grouped_blocks(64) == 1 and ops.finalize_grouped_blocks(65) == 4
+    assert ops.finalize_grouped_blocks(256) == 16 and ops.finalize_grouped_blocks(2048) == 8 * 128
+    assert ctypes.sizeof(_native.FinalizeTap) == 72 and ctypes.sizeof(_native.FinalizeGroup) == 32
+    header = open(os.path.join(ROOT, "include", "pleas_b200.h")).read()
+    for field in ("partial", "qa", "qb", "sa", "sb", "ld_m", "ld_n", "K", "splits"):
+        assert re.search(r"typedef struct PlbFinalizeTap \{[^}]*\b%s\b" % field, header, re.S), field
+    for field in ("cost", "ldc", "n", "tap_begin", "tap_end", "block_begin"):
+        assert re.search(r"typedef struct PlbFinalizeGroup \{[^}]*\b%s\b" % field, header, re.S), field
+
+
+def test_runner_cache_fingerprints_detect_what_invalidates_a_captured_graph():
+    """The calibration runner (fx graph + plans + CUDA graph) is reused across activation_matching calls only
+    while every parameter / buffer keeps its storage, shape and dtype and the modules keep their training flags."""
+    import importlib
+
+    import torch
+
+    from oracle import tinynet
+
+    AM = importlib.import_module("pleas_merging_b200.methods.activation_matching")
+    import pleas_merging_b200 as P
+
+    m, _ = tinynet.make_pair(12, 10)
+    fp = AM._model_fingerprint(m)
+    assert AM._model_fingerprint(m) == fp
+    with torch.no_grad():
+        next(m.parameters()).add_(1.0)  # new VALUES in the same storage: a replay reads them in place
+    assert AM._model_fingerprint(m) == fp
+    m.train()
+    assert AM._model_fingerprint(m) != fp  # BatchNorm would run with batch statistics
+    m.eval()
+    assert AM._model_fingerprint(m) == fp
+    first = next(m.parameters())
+    first.data = first.data.clone()  # re-allocated storage: a captured graph would read the old one
+    assert AM._model_fingerprint(m) != fp
+    spec = P.get_permutation_spec(m, ((1, 3, 16, 16),))
+    assert AM._spec_fingerprint(spec) == AM._spec_fingerprint(P.get_permutation_spec(m, ((1, 3, 16, 16),)))
