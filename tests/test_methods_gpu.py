@@ -588,3 +588,29 @@ def test_activation_matching_correlation_statistic(accumulate):
         assert (costs[k] - costs2[k]).abs().max() <= 2e-5, k  # fused loop == generic plug-in path
         assert_perm_or_objective(perm[k].numpy(), operm[(k.key, k.axis)], oc, str(k))
         assert_perm_or_objective(perm2[k].numpy(), operm[(k.key, k.axis)], oc, str(k))
+
+
+def test_models_on_a_non_current_device():
+    """Tensors on cuda:1 while cuda:0 is the current device (plain ``model.to('cuda:1')``, which the reference
+    handles): every C-ABI call must be issued with the tensors' device current and on its stream.  Needs 2 GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    P = _pkg()
+    m1, m2 = tinynet.make_pair(12, 10)
+    spec = P.get_permutation_spec(m1, ((1, 3, 16, 16),))
+    loader = tinynet.make_loader(3, 4, 16)
+    assert torch.cuda.current_device() == 0
+    ref_perm, ref_costs = P.activation_matching(spec, copy.deepcopy(m1).cuda(0), copy.deepcopy(m2).cuda(0), loader, 3,
+                                                output_costs=True, accumulate="sum")
+    a, b = m1.to("cuda:1"), m2.to("cuda:1")
+    perm, costs = P.activation_matching(spec, a, b, loader, 3, output_costs=True, accumulate="sum")
+    assert torch.cuda.current_device() == 0
+    for k in spec:
+        assert costs[k].device == torch.device("cuda", 1)
+        assert torch.equal(perm[k], ref_perm[k]), k
+        assert float((costs[k].cpu() - ref_costs[k].cpu()).abs().max()) <= 2e-6 * float(ref_costs[k].abs().max()), k
+    merged = P.partial_merge(spec, a, b, perm, costs, 0.5)
+    P.train(loader, a, b, merged, spec, perm, costs, 0.5, False, 2, None, num_classes=10, model_type="rn18")
+    wperm = P.weight_matching(spec, a.state_dict(), b.state_dict(), verbose=False)
+    wref = P.weight_matching(spec, m1.to("cuda:0").state_dict(), m2.to("cuda:0").state_dict(), verbose=False)
+    assert all(torch.equal(wperm[k], wref[k]) for k in spec)
