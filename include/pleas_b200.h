@@ -212,6 +212,17 @@ int plb_lap_solve_batched(const float *const *cost, const int32_t *n, const int3
                           int64_t *const *col4row, double *objective, int32_t *status,
                           int32_t n_problems, int32_t max_n, int32_t maximize, void *stream);
 
+/* The same solver started from column duals of a related problem (weight_matching.py:59-91 re-solves every group
+ * once per sweep while the costs change little): v_in[p] (DEVICE array of device pointers, entries may be NULL = cold
+ * start) holds fp64[n_p] column duals in the solver's minimisation form, scaled by v_scale; rows whose arg-min
+ * reduced-cost column is free keep it, the others are inserted by shortest augmenting paths as usual.  The result
+ * is an optimal assignment and equals plb_lap_solve_batched's whenever the optimum is unique (SciPy's tie-breaking
+ * is only reproduced by the cold start).  v_out[p] (may be NULL) receives the final column duals. */
+int plb_lap_solve_batched_warm(const float *const *cost, const int32_t *n, const int32_t *ld,
+                               int64_t *const *col4row, double *objective, int32_t *status,
+                               int32_t n_problems, int32_t max_n, int32_t maximize,
+                               const double *const *v_in, double v_scale, double *const *v_out, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * partial_merge building blocks (pleas/methods/partial_matching.py:47-176)
  * --------------------------------------------------------------------------------------- */

@@ -60,6 +60,8 @@ _SIGNATURES = {
     "plb_cross_finalize": (ctypes.c_int, [c_ptr, c_i32, c_i64, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_i32, c_ptr,
                                           c_ptr, c_i64, c_i32, c_i32, c_ptr]),
     "plb_lap_solve_batched": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr]),
+    "plb_lap_solve_batched_warm": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i32, c_ptr,
+                                                  c_f64, c_ptr, c_ptr]),
     "plb_get_blocks": (ctypes.c_int, [c_ptr, c_i64, c_ptr, c_i32, c_f32, c_i32, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
                                       c_ptr]),
     "plb_block_merge": (ctypes.c_int, [c_ptr, c_ptr, c_i64, c_i64, c_i64, c_ptr, c_ptr, c_ptr, c_ptr, c_i64, c_i64,

@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v2(const float *const *__r
                                                         const int32_t *__restrict__ lds,
                                                         int64_t *const *__restrict__ outs,
                                                         double *__restrict__ objective, int32_t *__restrict__ status,
-                                                        int maximize) {
+                                                        int maximize, const double *const *__restrict__ v_in,
+                                                        double v_scale, double *const *__restrict__ v_out) {
   extern __shared__ __align__(16) uint8_t lap_smem[];
   __shared__ uint64_t w_key[2][32];
   __shared__ uint32_t w_rank[2][32];
@@ -342,9 +343,59 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v2(const float *const *__r
     return;
   }
 
+  // Warm start (optional): column duals of a related problem (weight matching re-solves every group once per
+  // sweep on slowly changing costs).  Any v gives feasible duals with u_i = min_j (c_ij - v_j); a row keeps its
+  // arg-min column when no smaller row claimed it (reduced cost 0 on the matched edge), the other rows stay free
+  // and are inserted by the search below, which only needs dual feasibility and complementary slackness.  The
+  // result is an optimal assignment — identical to the cold start's whenever the optimum is unique.
+  const double *vin = (v_in != nullptr) ? v_in[prob] : nullptr;
+  if (vin != nullptr) {
+    for (int k = tid; k < n; k += nthr) s.v[k] = v_scale * vin[k];
+    __syncthreads();
+    for (int i = warp; i < n; i += nwarps) {
+      const float *__restrict__ crow = C + (int64_t)i * ld;
+      double best = INFINITY;
+      int bj = n;
+      for (int j = lane; j < n; j += 32) {
+        const double r = __dsub_rn(sgn * (double)__ldg(crow + j), s.v[j]);
+        if (r < best) {
+          best = r;
+          bj = j;
+        }
+      }
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, m);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, m);
+        if (ob < best || (ob == best && oj < bj)) {
+          best = ob;
+          bj = oj;
+        }
+      }
+      if (lane == 0) {
+        s.u[i] = best;
+        s.pred[i] = bj;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 0; i < n; ++i) {
+        const int j = s.pred[i];
+        if (j < n && s.row4col[j] < 0) {
+          s.row4col[j] = i;
+          s.col4row[i] = j;
+        }
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += nthr) s.pred[k] = -1;
+    __syncthreads();
+  }
+
   int result = 0;
   uint32_t step = 0;  // parity selects the warp-winner buffer
   for (int cur = 0; cur < n; ++cur) {
+    if (s.col4row[cur] >= 0) continue;  // matched by the warm start (uniform: shared memory, read after a barrier)
     for (int k = tid; k < n; k += nthr) {
       s.dist[k] = INFINITY;
       s.todo[k] = n - 1 - k;
@@ -469,6 +520,8 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v2(const float *const *__r
     }
     return;
   }
+  if (v_out != nullptr && v_out[prob] != nullptr)
+    for (int k = tid; k < n; k += nthr) v_out[prob][k] = s.v[k];
   int64_t *out = outs[prob];
   double part = 0.0;
   for (int i = tid; i < n; i += nthr) {
@@ -491,19 +544,20 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v2(const float *const *__r
 template <int CPT>
 static int launch_lap_v2(const float *const *cost, const int32_t *n, const int32_t *ld, int64_t *const *col4row,
                          double *objective, int32_t *status, int n_problems, int max_n, int maximize, size_t smem,
-                         cudaStream_t stream) {
+                         const double *const *v_in, double v_scale, double *const *v_out, cudaStream_t stream) {
   if (int rc = ensure_dynamic_smem((const void *)lap_kernel_v2<CPT>, (int)smem, "lap_kernel_v2")) return rc;
   int threads = (int)(ceil_div(max_n, 32 * CPT) * 32);
   threads = threads < 32 ? 32 : threads;  // <= 1024 by the caller's choice of CPT
-  lap_kernel_v2<CPT><<<n_problems, threads, smem, stream>>>(cost, n, ld, col4row, objective, status, maximize);
+  lap_kernel_v2<CPT><<<n_problems, threads, smem, stream>>>(cost, n, ld, col4row, objective, status, maximize, v_in,
+                                                            v_scale, v_out);
   return launch_status("lap_kernel_v2");
 }
 
 }  // namespace plb
 
-extern "C" int plb_lap_solve_batched(const float *const *cost, const int32_t *n, const int32_t *ld,
-                                     int64_t *const *col4row, double *objective, int32_t *status,
-                                     int32_t n_problems, int32_t max_n, int32_t maximize, void *stream) {
+static int lap_solve_impl(const float *const *cost, const int32_t *n, const int32_t *ld, int64_t *const *col4row,
+                          double *objective, int32_t *status, int32_t n_problems, int32_t max_n, int32_t maximize,
+                          const double *const *v_in, double v_scale, double *const *v_out, void *stream) {
   using namespace plb;
   PLB_REQUIRE(cost && n && ld && col4row && objective && status, PLB_EINVAL, "plb_lap_solve_batched: null pointer");
   PLB_REQUIRE(n_problems > 0 && max_n > 0, PLB_EINVAL, "plb_lap_solve_batched: empty batch");
@@ -527,15 +581,37 @@ extern "C" int plb_lap_solve_batched(const float *const *cost, const int32_t *n,
     while (cpt < 8 && (int64_t)cpt * 1024 < max_n) cpt *= 2;
     cudaStream_t st = (cudaStream_t)stream;
     switch (cpt) {
-      case 1: return launch_lap_v2<1>(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, smem, st);
-      case 2: return launch_lap_v2<2>(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, smem, st);
-      case 4: return launch_lap_v2<4>(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, smem, st);
-      default: return launch_lap_v2<8>(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, smem, st);
+      case 1: return launch_lap_v2<1>(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, smem, v_in,
+                                       v_scale, v_out, st);
+      case 2: return launch_lap_v2<2>(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, smem, v_in,
+                                       v_scale, v_out, st);
+      case 4: return launch_lap_v2<4>(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, smem, v_in,
+                                       v_scale, v_out, st);
+      default: return launch_lap_v2<8>(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, smem, v_in,
+                                       v_scale, v_out, st);
     }
   }
+  PLB_REQUIRE(v_in == nullptr && v_out == nullptr, PLB_EINVAL,
+              "plb_lap_solve_batched_warm: the warm start needs the v2 kernel (unset PLB_LAP_IMPL=v1)");
   const int cols_per_thread = cols_override > 0 ? cols_override : 1;
   int threads = (int)(ceil_div(max_n, 32 * cols_per_thread) * 32);
   threads = threads < 32 ? 32 : (threads > 1024 ? 1024 : threads);
   lap_kernel<<<n_problems, threads, smem, (cudaStream_t)stream>>>(cost, n, ld, col4row, objective, status, maximize);
   return launch_status("lap_kernel");
+}
+
+extern "C" int plb_lap_solve_batched(const float *const *cost, const int32_t *n, const int32_t *ld,
+                                     int64_t *const *col4row, double *objective, int32_t *status,
+                                     int32_t n_problems, int32_t max_n, int32_t maximize, void *stream) {
+  return lap_solve_impl(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, nullptr, 1.0, nullptr,
+                        stream);
+}
+
+extern "C" int plb_lap_solve_batched_warm(const float *const *cost, const int32_t *n, const int32_t *ld,
+                                          int64_t *const *col4row, double *objective, int32_t *status,
+                                          int32_t n_problems, int32_t max_n, int32_t maximize,
+                                          const double *const *v_in, double v_scale, double *const *v_out,
+                                          void *stream) {
+  return lap_solve_impl(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, v_in, v_scale, v_out,
+                        stream);
 }

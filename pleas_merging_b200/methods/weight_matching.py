@@ -25,6 +25,10 @@ from ..core.utils import Permutation, PermutationSpec, StateDict, apply_perm, ma
 from .activation_matching import cross_features_inner_product
 
 
+# warm-started assignment solves between sweeps (PLB_WM_WARM=0: every solve cold, i.e. SciPy's tie-breaking too)
+WARM_START = __import__("os").environ.get("PLB_WM_WARM", "1") == "1"
+
+
 class _GroupPlan:
     """Packed operands and GEMM plan of one permutation group."""
 
@@ -117,6 +121,7 @@ def weight_matching(
     rng.manual_seed(seed)
     fused = lsa_solver is b200_solve_lsa and cross_weights is cross_features_inner_product
     plans = {}
+    duals_prev = {}
     flag = torch.zeros(1, dtype=torch.int32, device=device)
     gains = torch.zeros(max(len(perm_names), 1), dtype=torch.float64, device=device)  # one slot per visit of a sweep
     visited = []
@@ -159,9 +164,14 @@ def weight_matching(
                         if p not in plans:
                             plans[p] = _GroupPlan(spec[p], p, state_as, state_bs, skip_suffixes, skip_missing, device)
                         mats.append(plans[p].build_cost(state_bs))
-                    newPs, _, status = ops.lap_solve_batched(mats, True)
+                    # every group is re-solved once per sweep on costs that change little: the solver starts from
+                    # the column duals of the group's previous visit (same optimum, far fewer augmenting steps)
+                    newPs, _, status, duals = ops.lap_solve_batched(
+                        mats, True, v_init=[duals_prev.get(p) for p in wave] if WARM_START else None,
+                        return_duals=True)
                     statuses.append(status)
-                    for p, A, newP in zip(wave, mats, newPs):
+                    for p, A, newP, v in zip(wave, mats, newPs, duals):
+                        duals_prev[p] = v[newP]  # B's units are about to be permuted by newP: so are its columns
                         finish_visit(iteration, p, A, newP)
             else:
                 for p in order:

@@ -500,3 +500,34 @@ def test_pack_im2col_vs_unfold():
         lo = unpack_planes(planes.lo, rows, Kc, planes.row_groups)
         got = hi.astype(np.float64) + lo
         assert np.abs(got - ref.numpy()).max() <= 2.0 ** -21 * max(np.abs(ref.numpy()).max(), 1.0)
+
+
+@pytest.mark.parametrize("n", [5, 64, 257, 1024])
+def test_lap_warm_start_reaches_the_same_optimum(n):
+    """plb_lap_solve_batched_warm: started from the column duals of a related problem (or from arbitrary duals)
+    the solver returns the optimal assignment — the cold start's / SciPy's whenever the optimum is unique."""
+    from scipy.optimize import linear_sum_assignment
+
+    ops = _ops()
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n)).astype(np.float32)
+    Ad = torch.from_numpy(A).cuda()
+    cold, obj0, st0, v = ops.lap_solve_batched([Ad], True, return_duals=True)
+    assert int(st0.item()) == 0
+    assert (cold[0].cpu().numpy() == linear_sum_assignment(A, maximize=True)[1]).all()
+    # (1) the same problem from its own duals: nothing left to augment
+    again, obj1, st1 = ops.lap_solve_batched([Ad], True, v_init=[v[0]])
+    assert torch.equal(again[0], cold[0]) and float(obj1.item()) == pytest.approx(float(obj0.item()), rel=1e-12)
+    # (2) a perturbed, column-permuted problem from the permuted duals (what weight matching does between sweeps)
+    P = torch.from_numpy(rng.permutation(n)).cuda()
+    B = (Ad[:, P] + 0.05 * torch.from_numpy(rng.standard_normal((n, n)).astype(np.float32)).cuda()).contiguous()
+    ref = linear_sum_assignment(B.cpu().numpy(), maximize=True)[1]
+    warm, objw, stw = ops.lap_solve_batched([B], True, v_init=[v[0][P].contiguous()])
+    assert int(stw.item()) == 0 and (warm[0].cpu().numpy() == ref).all()
+    # (3) arbitrary duals and a scale: still the optimum
+    junk = torch.from_numpy(rng.standard_normal(n)).cuda()
+    w2, _, _ = ops.lap_solve_batched([B], True, v_init=[junk], v_scale=3.0)
+    assert (w2[0].cpu().numpy() == ref).all()
+    # (4) mixed batch: one warm, one cold problem in the same launch
+    w3, _, _ = ops.lap_solve_batched([B, Ad], True, v_init=[v[0][P].contiguous(), None])
+    assert (w3[0].cpu().numpy() == ref).all() and torch.equal(w3[1], cold[0])
