@@ -38,6 +38,13 @@ METRIC = "rn50_pair_merge_calib_samples_per_s"
 UNIT = "samples/s"
 
 
+def workload_of(model_name, batch=None):
+    """The workload both arms run (identical `config.workload`): what differs is who executes it."""
+    return (f"{model_name} pair (random init, eval), activation_matching cost accumulation over batches of "
+            f"{BATCH if batch is None else batch}x3x{HW}x{HW}, -cdist statistic on all taps, accumulate=sum, "
+            f"exact-fp32 forwards")
+
+
 def num_classes_of(model_name):
     return 345 if model_name == "resnet101_domainnet" else 1000
 
@@ -156,8 +163,8 @@ def run_reference(args):
               "node": sorted((a.key, a.axis) for a in pg.node)} for k, pg in spec.items()]
     b = args.cpu_sample
     g = torch.Generator().manual_seed(123)
-    steps = min(args.steps, 3)  # bounded: ~6-10 s of CPU work per 32-sample step
-    warm = min(args.warmup, 1)
+    steps = min(args.steps, 20)  # ~6 s of CPU work per 32-sample step: the driver's 20 steps are honoured
+    warm = min(args.warmup, 2)
     loader = [(torch.randn(b, 3, HW, HW, generator=g), 0) for _ in range(steps + warm)]
     if warm:
         O.matching_costs(jspec, m1, m2, loader[:warm], warm, "cdist", "sum")
@@ -170,9 +177,10 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model} pair (random init, eval), activation_matching accumulation over "
-                               f"batches of {b}x3x{HW}x{HW}, -cdist statistic on all taps, accumulate=sum; CPU "
-                               f"reference path (oracle port), {steps} steps after {warm} warm-up"},
+        "config": {"workload": workload_of(args.model, b)},
+        "implementation": f"CPU reference path: oracle port of activation_matching's cost loop (torch CPU forwards + numpy "
+                          f"-cdist per tap), {torch.get_num_threads()} host threads, {steps} steps of {b} samples after "
+                          f"{warm} warm-up",
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -438,12 +446,12 @@ def _run_b200(args):
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{args.model} pair (random init, eval), activation_matching accumulation over "
-                                  f"{K} batches of {BATCH}x3x{HW}x{HW} per GPU, -cdist statistic on {taps} taps, "
-                                  f"accumulate=sum, 3xTF32 tcgen05 Gram kernels, "
-                                  + ("TF32 cuDNN forwards (secondary number)" if args.tf32_convs else "exact-fp32 cuDNN forwards"),
-                      "parallelism": f"batch-sharded x{world}, one NCCL all-reduce of the cost matrices",
-                      "l2": "inputs larger than L2: every step streams ~10 GB of activations"},
+           "config": {"workload": workload_of(args.model) if not args.tf32_convs else
+                      workload_of(args.model).replace("exact-fp32 forwards", "TF32 cuDNN forwards (secondary number)")},
+           "implementation": {"kernels": f"3xTF32 tcgen05 Gram kernels on {taps} taps, {K} batches per GPU replayed as one "
+                                         f"CUDA graph per batch",
+                              "parallelism": f"batch-sharded x{world}, one NCCL all-reduce of the cost matrices",
+                              "l2": "inputs larger than L2: every step streams ~10 GB of activations"},
            "gpu_launches": launches, "launches_per_step": launch_mix}
     if parity_ok is not None:
         out["parity_ok"] = parity_ok
