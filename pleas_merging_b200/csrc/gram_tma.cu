@@ -244,6 +244,12 @@ __global__ void __launch_bounds__(384, 1) gram_tma_kernel(const __grid_constant_
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[1016] = clock64();
+    p.trace[1022] = gt;
+  }
   const int cluster_id = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int n_clusters = (int)gridDim.x / CG;
   const int tiles = p.m_tiles * p.n_tiles;
@@ -267,6 +273,7 @@ __global__ void __launch_bounds__(384, 1) gram_tma_kernel(const __grid_constant_
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[1017] = clock64();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -461,14 +468,22 @@ __global__ void __launch_bounds__(384, 1) gram_tma_kernel(const __grid_constant_
       const int64_t row = (int64_t)mt * (128 * CG) + rank * 128 + q * 32 + lane;
       float4 *d4 = reinterpret_cast<float4 *>(p.partial + ((int64_t)split * p.ld_m + row) * p.ld_n +
                                                (int64_t)nt * Cfg::kMmaN + half * COLS);
+      if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0) p.trace[1018] = clock64();  // last chain drained
 #pragma unroll
       for (int e = 0; e < COLS / 4; ++e) d4[e] = make_float4(acc[4 * e], acc[4 * e + 1], acc[4 * e + 2], acc[4 * e + 3]);
+      if (p.trace && blockIdx.x == 0 && warp == 4 && lane == 0) p.trace[1019] = clock64();  // partial tile stored
     }
   }
 
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) tmem_dealloc_cg<CG>(tmem_base, Cfg::kTmemCols);
+  if (p.trace && blockIdx.x == 0 && threadIdx.x == 32) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[1020] = clock64();
+    p.trace[1023] = gt;
+  }
 }
 
 static unsigned long long *g_trace = nullptr;
