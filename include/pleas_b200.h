@@ -260,6 +260,34 @@ int plb_wm_progress(const float *A, int64_t ld, const int64_t *P, int32_t n, int
                     double *gain, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Forward convolution of the SOURCE models inside the calibration / PLeaS loops.
+ *
+ * The reference runs the two source models through ATen's fp32 convolutions
+ * (pleas/methods/activation_matching.py:123 `gm_cross(x)`, pleas_merging.py:262-281 the hooked
+ * forwards); on a B200 those are cuDNN's SIMT fp32 kernels and 60 % of a calibration step.  This
+ * is the same arithmetic as an implicit GEMM on the tensor cores with the 3xTF32 split of the
+ * Gram kernels (fp32-level accuracy, fp32 accumulation):
+ *     out[n, co, oh, ow] = bias[co] + sum_{ci,kh,kw} x[n, ci, oh*s - ph + kh, ow*s - pw + kw] w[co, ci, kh, kw]
+ * NCHW fp32 contiguous, groups = 1, dilation = 1, zero padding.
+ *
+ * plb_conv_pack_weights splits w into tf32 hi / lo planes in the order the kernel's tensor map
+ * reads: planes[2][taps][Cout][Kc].  Cin % 32 == 0: taps = KH*KW, Kc = Cin, plane[t][co][ci].
+ * Otherwise ("flat" form, e.g. the 3-channel stem): taps = 1, Kc = ceil32(Cin*KH*KW),
+ * plane[0][co][ci*KH*KW + kh*KW + kw], zero padded.  plb_conv_packed_floats returns the number of
+ * floats of the whole packed buffer (host-only helper).  Weights are constants of the source
+ * models: pack once, reuse for every batch. */
+int64_t plb_conv_packed_floats(int64_t Cout, int64_t Cin, int32_t KH, int32_t KW);
+int plb_conv_pack_weights(const float *w, int64_t Cout, int64_t Cin, int32_t KH, int32_t KW, float *packed,
+                          void *stream);
+
+/* One launch for up to two convolutions of identical geometry (the same layer of the two source
+ * models).  x / out / bias (bias entries may be NULL) are HOST arrays of `nprob` device pointers. */
+int plb_conv2d_forward(const float *const *x, const float *const *packed_w, const float *const *bias,
+                       float *const *out, int32_t nprob, int64_t NB, int64_t Cin, int64_t IH, int64_t IW,
+                       int64_t Cout, int32_t KH, int32_t KW, int32_t stride, int32_t pad_h, int32_t pad_w,
+                       void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * PLeaS closed form: solve (G + ridge*I) X = B for symmetric positive definite G (fp64,
  * column/row symmetric so layout-agnostic), in place: G is overwritten by its Cholesky
  * factor (lower), B [n, nrhs] row-major by the solution.  Replaces the Adam loop of

@@ -1,0 +1,129 @@
+"""Forward convolutions of the source models on the library's 3xTF32 tcgen05 implicit-GEMM kernel
+(csrc/conv.cu, plb_conv2d_forward) instead of ATen's cuDNN fp32 kernels.
+
+The reference's loops (pleas/methods/activation_matching.py:123, pleas_merging.py:262-281) spend most of
+their time in the two source models' convolutions; the weights of those models are constants of the merge,
+so they are split into tf32 hi / lo planes once (``PackedConv``) and every batch runs the same layer of
+BOTH models in one launch (``conv2d_pair``).
+
+``eligible(module)`` names what the kernel covers: plain ``nn.Conv2d`` (groups 1, dilation 1, zero padding,
+equal strides, fp32).  Anything else keeps the module's own forward.  ``PLB_CONV=0`` switches the path off.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import _native as N
+
+ENABLED = os.environ.get("PLB_CONV", "1") == "1"
+MAX_FLAT_K = 1024
+CONV_TIMER = None  # bench: list of (start event, end event, algorithmic flops, bytes)
+
+
+def eligible(mod) -> bool:
+    if not ENABLED or type(mod) is not torch.nn.Conv2d:
+        return False
+    if mod.groups != 1 or tuple(mod.dilation) != (1, 1) or mod.padding_mode != "zeros":
+        return False
+    if isinstance(mod.padding, str) or mod.stride[0] != mod.stride[1]:
+        return False
+    w = mod.weight
+    if w.dtype != torch.float32 or not w.is_cuda:
+        return False
+    cin, kh, kw = w.shape[1], w.shape[2], w.shape[3]
+    if cin % 32 != 0 and -(-cin * kh * kw // 32) * 32 > MAX_FLAT_K:
+        return False
+    return kh < 256 and kw < 256
+
+
+class PackedConv:
+    """tf32 hi / lo planes of one Conv2d weight in the kernel's order; repacked when the weight tensor
+    changes (address or in-place version)."""
+
+    def __init__(self, mod):
+        self.mod = mod
+        self.packed = None
+        self.key = None
+        self.refresh()
+
+    def refresh(self):
+        w = self.mod.weight
+        key = (w.data_ptr(), w._version, tuple(w.shape))
+        if key == self.key:
+            return
+        cout, cin, kh, kw = w.shape
+        n = N.lib().plb_conv_packed_floats(cout, cin, kh, kw)
+        if self.packed is None or self.packed.numel() != n:
+            self.packed = torch.empty(n, dtype=torch.float32, device=w.device)
+        wc = w.detach().contiguous()
+        N.call("plb_conv_pack_weights", w.device, wc.data_ptr(), cout, cin, kh, kw, self.packed.data_ptr())
+        self.key = key
+
+
+def _ptr_array(ts):
+    return (ctypes.c_void_p * len(ts))(*[None if t is None else t.data_ptr() for t in ts])
+
+
+def conv2d_forward(xs, packs):
+    """Runs ``packs[i].mod`` on ``xs[i]`` (1 or 2 problems of identical geometry) in one launch; returns
+    the list of outputs.  Inputs must be fp32 CUDA NCHW-contiguous (the caller checks / falls back)."""
+    mod = packs[0].mod
+    w = mod.weight
+    cout, cin, kh, kw = w.shape
+    nb, _, ih, iw = xs[0].shape
+    stride, (ph, pw) = mod.stride[0], mod.padding
+    oh, ow = (ih + 2 * ph - kh) // stride + 1, (iw + 2 * pw - kw) // stride + 1
+    outs = [torch.empty((nb, cout, oh, ow), dtype=torch.float32, device=x.device) for x in xs]
+    biases = [pk.mod.bias.detach() if pk.mod.bias is not None else None for pk in packs]
+    if CONV_TIMER is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    N.call("plb_conv2d_forward", xs[0].device, _ptr_array(xs), _ptr_array([pk.packed for pk in packs]),
+           _ptr_array(biases), _ptr_array(outs), len(xs), nb, cin, ih, iw, cout, kh, kw, stride, ph, pw)
+    if CONV_TIMER is not None:
+        e1.record()
+        flops = 2.0 * len(xs) * nb * oh * ow * cout * cin * kh * kw
+        nbytes = 4.0 * len(xs) * (nb * cin * ih * iw + nb * cout * oh * ow)
+        CONV_TIMER.append((e0, e1, flops, nbytes, (cin, cout, kh, stride, ih)))
+    return outs
+
+
+def input_ok(x, mod):
+    return x.dim() == 4 and x.dtype == torch.float32 and x.is_cuda and x.is_contiguous() and \
+        x.shape[1] == mod.weight.shape[1] and x.numel() > 0 and x.shape[1] * x.shape[2] * x.shape[3] < 2 ** 31 and \
+        not (torch.is_grad_enabled() and (x.requires_grad or mod.weight.requires_grad))
+
+
+class ConvPair:
+    """The same convolution layer of the two source models: fx ``call_function`` target state."""
+
+    def __init__(self, mod_a, mod_b):
+        self.mods = (mod_a, mod_b)
+        self.packs = None
+
+    def same_geometry(self):
+        a, b = self.mods
+        return a.weight.shape == b.weight.shape and a.stride == b.stride and a.padding == b.padding and \
+            (a.bias is None) == (b.bias is None)
+
+    def __call__(self, xa, xb):
+        a, b = self.mods
+        if not (input_ok(xa, a) and input_ok(xb, b) and xa.shape == xb.shape):
+            return a(xa), b(xb)
+        if self.packs is None:
+            self.packs = (PackedConv(a), PackedConv(b))
+        else:
+            self.packs[0].refresh()
+            self.packs[1].refresh()
+        ya, yb = conv2d_forward([xa, xb], self.packs)
+        return ya, yb
+
+
+def conv2d(x, mod, pack=None):
+    """Single convolution through the library kernel (falls back to the module when not covered)."""
+    if not (eligible(mod) and input_ok(x, mod)):
+        return mod(x)
+    pack = pack or PackedConv(mod)
+    pack.refresh()
+    return conv2d_forward([x], [pack])[0]

@@ -1,0 +1,461 @@
+// Forward convolution of the source models as a 3xTF32 implicit GEMM on tcgen05 (include/pleas_b200.h,
+// plb_conv2d_forward).  Replaces the ATen / cuDNN fp32 convolutions the reference's loops run
+// (pleas/methods/activation_matching.py:123, pleas_merging.py:262-281) — SIMT kernels at ~38 TFLOP/s that
+// were 60 % of a calibration step.
+//
+// GEMM view (NCHW fp32, no layout change anywhere):
+//     D[p, co] = sum_k A[p, k] B[co, k]      p = (n, oh, ow) output position      -> M (tile 128 = TMEM lanes)
+//                                            co output channel                    -> N (tile TN = 64 / 128)
+//                                            k = (32-channel block, kh, kw)       -> K in boxes of 32
+// Positions are the M dimension because they are the contiguous dimension of both x and out: a warp's
+// loads (32 consecutive positions of one channel) and stores (32 consecutive positions of one output
+// channel) are 128-byte coalesced with no transposition.
+//
+//   A (activations) never touches shared memory: loader threads own one position each, read their
+//     32 channels of the current tap (predicated on the zero padding), split them in registers
+//     (hi = rna_tf32(x), lo = rna_tf32(x - hi)) and write both planes into TENSOR MEMORY with tcgen05.st —
+//     the MMA takes A from TMEM (tcgen05.mma [d], [a], b_desc).  That is the operand arrangement the
+//     shared-memory-bound Gram kernel's analysis asked for (profiles/r02_notes.md): shared memory carries
+//     the B operand only.
+//   B (weights) is packed ONCE per model (plb_conv_pack_weights: hi / lo planes, [tap][Cout][Cin]) and
+//     arrives by 4-D tensor-map TMA in the 128-byte-swizzled K-major layout.
+//   D: the tensor core's fp32 accumulator truncates, so K is cut into short chains; the MMA warp ping-pongs
+//     between two TMEM accumulators and the epilogue warps promote every finished chain into registers
+//     (same scheme as gemm.cu / gram_tma.cu), then store the tile (+ bias) straight into NCHW.
+//
+// TMEM columns: [0, 2 TN) accumulators, [2 TN, 2 TN + 4 x 64) four A stages (hi | lo, 32 k each).
+// Warp roles (576 threads, 1 CTA/SM, persistent over (position tile, model, channel tile) items):
+//   warp 0       TMA producer (weights)          warp 1        TMEM owner + MMA issuer
+//   warps 2-9    loaders: two sets of four warps (one per TMEM lane quadrant) alternate stages and
+//                prefetch their next stage into registers while converting the current one
+//   warps 10-17  promotion / epilogue (two per lane quadrant, half the channel tile each)
+#include "tma.cuh"
+
+namespace plb {
+
+constexpr int kConvStages = 4;
+constexpr int kConvThreads = 576;
+constexpr int kConvMaxFlatK = 1024;  // flat form: Cin*KH*KW (padded to 32) must fit the shared-memory k table
+
+struct ConvParams {
+  const float *x[2];
+  const float *bias[2];
+  float *out[2];
+  int nprob;
+  int NB, Cin, IH, IW, Cout, OH, OW, KH, KW, stride, pad_h, pad_w;
+  int P, OHW, IHW;
+  int m_tiles, n_tiles, total_items;
+  int taps;         // KH*KW (channel-block form) or 1 (flat form)
+  int nbox;         // K boxes of 32 per item
+  int flat;         // 1: k = ci*KH*KW + kh*KW + kw (any Cin), 0: k = 32-channel block x tap
+  int flat_k;       // Cin*KH*KW (flat form)
+  int chain_boxes;  // boxes chained into one TMEM accumulator before promotion
+};
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32 (A: lane = row, column = k)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, int c3,
+                                            uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], "
+      "[%6];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+
+struct ConvItem {
+  int prob, mt, nt;
+};
+__device__ __forceinline__ ConvItem conv_item(const ConvParams &p, int item) {
+  ConvItem it;
+  it.nt = item % p.n_tiles;
+  const int rest = item / p.n_tiles;
+  it.prob = rest % p.nprob;
+  it.mt = rest / p.nprob;
+  return it;
+}
+
+template <int TN>
+__global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __grid_constant__ CUtensorMap tmw0,
+                                                                      const __grid_constant__ CUtensorMap tmw1,
+                                                                      ConvParams p) {
+  constexpr int kPlaneBytes = TN * 128;          // one (TN rows x 32 k) weight box
+  constexpr int kStageBytes = 2 * kPlaneBytes;   // hi | lo
+  constexpr uint32_t kACol0 = 2 * TN;            // first TMEM column of the A stages
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_b_full[kConvStages];   // TMA -> MMA
+  __shared__ uint64_t bar_a_full[kConvStages];   // loaders -> MMA
+  __shared__ uint64_t bar_empty[kConvStages];    // MMA -> producer and loaders
+  __shared__ uint64_t bar_acc_full[2];           // MMA -> promotion warps
+  __shared__ uint64_t bar_acc_empty[2];          // promotion warps -> MMA
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int2 ktab[kConvMaxFlatK];           // flat form: k -> (ci*IHW + kh*IW + kw, kh << 16 | kw)
+
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta = (int)blockIdx.x, nctas = (int)gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < kConvStages; ++s) {
+      mbar_init(&bar_b_full[s], 1);
+      mbar_init(&bar_a_full[s], 4);
+      mbar_init(&bar_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bar_acc_full[b], 1);
+      mbar_init(&bar_acc_empty[b], 8);
+    }
+    fence_mbar_init();
+  } else if (warp == 1) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  if (p.flat) {
+    const int kk_total = p.nbox * 32, taps = p.KH * p.KW;
+    for (int k = (int)threadIdx.x; k < kk_total; k += kConvThreads) {
+      int2 e;
+      if (k < p.flat_k) {
+        const int ci = k / taps, t = k - ci * taps, kh = t / p.KW, kw = t - kh * p.KW;
+        e.x = ci * p.IHW + kh * p.IW + kw;
+        e.y = (kh << 16) | kw;
+      } else {
+        e.x = 0;
+        e.y = -1;  // padding k: always reads as zero
+      }
+      ktab[k] = e;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (weights)
+    uint32_t i = 0;
+    for (int item = cta; item < p.total_items; item += nctas) {
+      const ConvItem it = conv_item(p, item);
+      const CUtensorMap *map = it.prob ? &tmw1 : &tmw0;
+      const int n0 = it.nt * TN;
+      int cb = 0, tap = 0;
+      for (int b = 0; b < p.nbox; ++b, ++i) {
+        const uint32_t s = i & (kConvStages - 1), ph = (i / kConvStages) & 1u;
+        mbar_wait_wd(&bar_empty[s], ph ^ 1u);
+        if (elect_one()) {
+          uint8_t *st = smem + (size_t)s * kStageBytes;
+          mbar_arrive_expect_tx(&bar_b_full[s], kStageBytes);
+          tma_load_4d(st, map, cb * 32, n0, tap, 0, &bar_b_full[s]);
+          tma_load_4d(st + kPlaneBytes, map, cb * 32, n0, tap, 1, &bar_b_full[s]);
+        }
+        __syncwarp();
+        if (++tap == p.taps) {
+          tap = 0;
+          ++cb;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_tf32(128, TN);
+    const uint32_t smem_base = smem_u32(smem);
+    uint32_t i = 0, chain = 0;
+    for (int item = cta; item < p.total_items; item += nctas) {
+      for (int b0 = 0; b0 < p.nbox; b0 += p.chain_boxes, ++chain) {
+        const uint32_t buf = chain & 1u;
+        mbar_wait_wd(&bar_acc_empty[buf], ((chain >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * TN;
+        const int b1 = min(p.nbox, b0 + p.chain_boxes);
+        for (int b = b0; b < b1; ++b, ++i) {
+          const uint32_t s = i & (kConvStages - 1), ph = (i / kConvStages) & 1u;
+          mbar_wait_wd(&bar_a_full[s], ph);
+          mbar_wait_wd(&bar_b_full[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t bst = smem_base + s * kStageBytes;
+            const uint32_t a_hi0 = tmem_base + kACol0 + s * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint64_t b_hi = umma_desc_sw<128>(bst + 32 * j);
+              const uint64_t b_lo = umma_desc_sw<128>(bst + kPlaneBytes + 32 * j);
+              const uint32_t a_hi = a_hi0 + 8 * j, a_lo = a_hi + 32;
+              umma_tf32_ts(d_tmem, a_lo, b_hi, idesc, (b > b0 || j > 0) ? 1u : 0u);
+              umma_tf32_ts(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_tf32_ts(d_tmem, a_hi, b_hi, idesc, 1u);
+            }
+            umma_commit(&bar_empty[s]);
+            if (b == b1 - 1) umma_commit(&bar_acc_full[buf]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < 10) {
+    // ------------------------------------------------------------------ loaders (A operand -> TMEM)
+    const int set = (warp - 2) >> 2;
+    const int row = (warp & 3) * 32 + lane;  // TMEM lane = position inside the tile
+    const uint32_t a_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kACol0;
+    const int my_items = cta < p.total_items ? (p.total_items - cta + nctas - 1) / nctas : 0;
+    const int total = my_items * p.nbox;
+    float bufA[32], bufB[32];
+    int cur_it = -1, ih0 = 0, iw0 = 0;
+    bool pvalid = false;
+    const float *xn = nullptr;
+
+    auto issue = [&](int i, float(&buf)[32]) {
+      const int itx = i / p.nbox, box = i - itx * p.nbox;
+      if (itx != cur_it) {
+        cur_it = itx;
+        const ConvItem it = conv_item(p, cta + itx * nctas);
+        const int pos = it.mt * 128 + row;
+        pvalid = pos < p.P;
+        const int n = pos / p.OHW, r = pos - n * p.OHW, oh = r / p.OW, ow = r - oh * p.OW;
+        ih0 = oh * p.stride - p.pad_h;
+        iw0 = ow * p.stride - p.pad_w;
+        xn = p.x[it.prob] + (int64_t)n * p.Cin * p.IHW;
+      }
+      if (!p.flat) {
+        const int cb = box / p.taps, tap = box - cb * p.taps, kh = tap / p.KW, kw = tap - kh * p.KW;
+        const int ih = ih0 + kh, iw = iw0 + kw;
+        const bool ok = pvalid && (unsigned)ih < (unsigned)p.IH && (unsigned)iw < (unsigned)p.IW;
+        const float *src = xn + (int64_t)(cb * 32) * p.IHW + ih * p.IW + iw;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) buf[c] = ok ? __ldg(src + (int64_t)c * p.IHW) : 0.f;
+      } else {
+        const float *src = xn + ih0 * p.IW + iw0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const int2 e = ktab[box * 32 + c];
+          const int ih = ih0 + (e.y >> 16), iw = iw0 + (e.y & 0xffff);
+          const bool ok = pvalid && e.y >= 0 && (unsigned)ih < (unsigned)p.IH && (unsigned)iw < (unsigned)p.IW;
+          buf[c] = ok ? __ldg(src + e.x) : 0.f;
+        }
+      }
+    };
+    auto process = [&](int i, float(&buf)[32]) {
+      const uint32_t s = (uint32_t)i & (kConvStages - 1), ph = ((uint32_t)i / kConvStages) & 1u;
+      mbar_wait_wd(&bar_empty[s], ph ^ 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t hi[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) hi[c] = __float_as_uint(to_tf32(buf[16 * h + c]));
+        tmem_st16(a_base + s * 64 + 16 * h, hi);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) hi[c] = __float_as_uint(to_tf32(buf[16 * h + c] - __uint_as_float(hi[c])));
+        tmem_st16(a_base + s * 64 + 32 + 16 * h, hi);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_a_full[s]);
+    };
+
+    int i = set;
+    if (i < total) issue(i, bufA);
+    while (i < total) {
+      if (i + 2 < total) issue(i + 2, bufB);
+      process(i, bufA);
+      i += 2;
+      if (i >= total) break;
+      if (i + 2 < total) issue(i + 2, bufA);
+      process(i, bufB);
+      i += 2;
+    }
+  } else {
+    // ------------------------------------------------------------------ promotion / epilogue
+    constexpr int COLS = TN / 2;
+    const int q = warp & 3;
+    const int half = (warp - 10) >> 2;
+    uint32_t chain = 0;
+    for (int item = cta; item < p.total_items; item += nctas) {
+      const ConvItem it = conv_item(p, item);
+      float acc[COLS];
+#pragma unroll
+      for (int c = 0; c < COLS; ++c) acc[c] = 0.f;
+      for (int b0 = 0; b0 < p.nbox; b0 += p.chain_boxes, ++chain) {
+        const uint32_t buf = chain & 1u;
+        mbar_wait_wd(&bar_acc_full[buf], (chain >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TN + half * COLS;
+#pragma unroll
+        for (int c = 0; c < COLS / 16; ++c) {
+          uint32_t v[16];
+          tmem_ld16(t0 + c * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc[c * 16 + e] += __uint_as_float(v[e]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_acc_empty[buf]);
+      }
+      const int pos = it.mt * 128 + q * 32 + lane;
+      if (pos < p.P) {
+        const int n = pos / p.OHW, r = pos - n * p.OHW;
+        const int co0 = it.nt * TN + half * COLS;
+        float *o = p.out[it.prob] + ((int64_t)n * p.Cout + co0) * p.OHW + r;
+        const float *bias = p.bias[it.prob];
+#pragma unroll
+        for (int c = 0; c < COLS; ++c)
+          if (co0 + c < p.Cout) o[(int64_t)c * p.OHW] = acc[c] + (bias ? __ldg(bias + co0 + c) : 0.f);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// w[Cout][Cin][KH][KW] -> hi / lo planes [2][taps][Cout][Kc] (include/pleas_b200.h)
+__global__ void conv_pack_weights_kernel(const float *__restrict__ w, float *__restrict__ packed, int Cout, int Cin,
+                                         int KH, int KW, int taps, int Kc, int flat) {
+  const int64_t plane = (int64_t)taps * Cout * Kc;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < plane; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(idx % Kc);
+    const int co = (int)((idx / Kc) % Cout);
+    const int t = (int)(idx / ((int64_t)Kc * Cout));
+    float v = 0.f;
+    if (!flat) {
+      v = w[((int64_t)co * Cin + k) * (KH * KW) + t];
+    } else if (k < Cin * KH * KW) {
+      v = w[(int64_t)co * Cin * KH * KW + k];
+    }
+    const float hi = to_tf32(v);
+    packed[idx] = hi;
+    packed[plane + idx] = to_tf32(v - hi);
+  }
+}
+
+struct ConvGeometry {
+  int flat, taps, Kc;
+};
+static ConvGeometry conv_geometry(int64_t Cin, int KH, int KW) {
+  ConvGeometry g;
+  g.flat = (Cin % 32) != 0;
+  g.taps = g.flat ? 1 : KH * KW;
+  g.Kc = g.flat ? (int)(ceil_div(Cin * KH * KW, 32) * 32) : (int)Cin;
+  return g;
+}
+
+static int make_weight_map(CUtensorMap *m, const float *packed, int64_t Cout, const ConvGeometry &g, int tn) {
+  EncodeTiledFn enc = encode_tiled();
+  PLB_REQUIRE(enc != nullptr, PLB_EINVAL, "plb_conv2d_forward: cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[4] = {(cuuint64_t)g.Kc, (cuuint64_t)Cout, (cuuint64_t)g.taps, 2};
+  cuuint64_t gstride[3] = {(cuuint64_t)g.Kc * 4, (cuuint64_t)g.Kc * Cout * 4, (cuuint64_t)g.Kc * Cout * g.taps * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)tn, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)packed, gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PLB_REQUIRE(r == CUDA_SUCCESS, PLB_EINVAL, "plb_conv2d_forward: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return PLB_OK;
+}
+
+template <int TN>
+static int launch_conv(const CUtensorMap &m0, const CUtensorMap &m1, const ConvParams &p, cudaStream_t stream) {
+  constexpr int smem_bytes = kConvStages * 2 * TN * 128 + 1024;
+  if (int rc = ensure_dynamic_smem((const void *)conv3xtf32_kernel<TN>, smem_bytes, "conv3xtf32_kernel")) return rc;
+  const int grid = min(p.total_items, device_sm_count());
+  conv3xtf32_kernel<TN><<<grid, kConvThreads, smem_bytes, stream>>>(m0, m1, p);
+  return launch_status("conv3xtf32_kernel");
+}
+
+}  // namespace plb
+
+extern "C" int64_t plb_conv_packed_floats(int64_t Cout, int64_t Cin, int32_t KH, int32_t KW) {
+  if (Cout <= 0 || Cin <= 0 || KH <= 0 || KW <= 0) return 0;
+  const plb::ConvGeometry g = plb::conv_geometry(Cin, KH, KW);
+  return 2ll * g.taps * Cout * g.Kc;
+}
+
+extern "C" int plb_conv_pack_weights(const float *w, int64_t Cout, int64_t Cin, int32_t KH, int32_t KW, float *packed,
+                                     void *stream) {
+  using namespace plb;
+  PLB_REQUIRE(w && packed, PLB_EINVAL, "plb_conv_pack_weights: null pointer");
+  PLB_REQUIRE(Cout > 0 && Cin > 0 && KH > 0 && KW > 0, PLB_EINVAL, "plb_conv_pack_weights: empty weight");
+  const ConvGeometry g = conv_geometry(Cin, KH, KW);
+  PLB_REQUIRE(!g.flat || g.Kc <= kConvMaxFlatK, PLB_ESIZE,
+              "plb_conv_pack_weights: Cin %% 32 != 0 needs Cin*KH*KW <= %d", kConvMaxFlatK);
+  const int64_t plane = (int64_t)g.taps * Cout * g.Kc;
+  PLB_REQUIRE(plane < (1ll << 31), PLB_ESIZE, "plb_conv_pack_weights: weight too large");
+  const int64_t want = ceil_div(plane, 256);
+  const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
+  conv_pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, packed, (int)Cout, (int)Cin, KH, KW, g.taps,
+                                                                     g.Kc, g.flat);
+  return launch_status("conv_pack_weights_kernel");
+}
+
+extern "C" int plb_conv2d_forward(const float *const *x, const float *const *packed_w, const float *const *bias,
+                                  float *const *out, int32_t nprob, int64_t NB, int64_t Cin, int64_t IH, int64_t IW,
+                                  int64_t Cout, int32_t KH, int32_t KW, int32_t stride, int32_t pad_h, int32_t pad_w,
+                                  void *stream) {
+  using namespace plb;
+  PLB_REQUIRE(x && packed_w && out, PLB_EINVAL, "plb_conv2d_forward: null pointer table");
+  PLB_REQUIRE(nprob == 1 || nprob == 2, PLB_EINVAL, "plb_conv2d_forward: one or two problems per launch");
+  PLB_REQUIRE(NB > 0 && Cin > 0 && IH > 0 && IW > 0 && Cout > 0 && KH > 0 && KW > 0 && stride > 0 && pad_h >= 0 &&
+                  pad_w >= 0,
+              PLB_EINVAL, "plb_conv2d_forward: bad geometry");
+  const int64_t OH = (IH + 2 * pad_h - KH) / stride + 1, OW = (IW + 2 * pad_w - KW) / stride + 1;
+  PLB_REQUIRE(OH > 0 && OW > 0, PLB_EINVAL, "plb_conv2d_forward: empty output");
+  PLB_REQUIRE(NB * OH * OW < (1ll << 31) - 128 && NB * Cin * IH * IW < (1ll << 40) && Cin * IH * IW < (1ll << 31) &&
+                  KH < 256 && KW < 256,
+              PLB_ESIZE, "plb_conv2d_forward: extent too large");
+  const ConvGeometry g = conv_geometry(Cin, KH, KW);
+  PLB_REQUIRE(!g.flat || g.Kc <= kConvMaxFlatK, PLB_ESIZE,
+              "plb_conv2d_forward: Cin %% 32 != 0 needs Cin*KH*KW <= %d", kConvMaxFlatK);
+  ConvParams p = {};
+  for (int i = 0; i < nprob; ++i) {
+    PLB_REQUIRE(x[i] && packed_w[i] && out[i], PLB_EINVAL, "plb_conv2d_forward: null pointer");
+    PLB_REQUIRE(((uintptr_t)packed_w[i] & 15) == 0, PLB_EALIGN, "plb_conv2d_forward: packed weights must be 16-byte aligned");
+    p.x[i] = x[i];
+    p.out[i] = out[i];
+    p.bias[i] = bias ? bias[i] : nullptr;
+  }
+  p.nprob = nprob;
+  p.NB = (int)NB, p.Cin = (int)Cin, p.IH = (int)IH, p.IW = (int)IW, p.Cout = (int)Cout, p.OH = (int)OH, p.OW = (int)OW;
+  p.KH = KH, p.KW = KW, p.stride = stride, p.pad_h = pad_h, p.pad_w = pad_w;
+  p.P = (int)(NB * OH * OW), p.OHW = (int)(OH * OW), p.IHW = (int)(IH * IW);
+  p.flat = g.flat, p.taps = g.taps, p.flat_k = (int)(Cin * KH * KW);
+  p.nbox = g.taps * (g.Kc / 32);
+  p.chain_boxes = 8;  // 256 k = 96 chained MMAs per accumulator (the Gram kernels' MAX_CHAIN_KB = 16 blocks of 16 k)
+  const int tn = Cout <= 64 ? 64 : 128;
+  p.m_tiles = (int)ceil_div(p.P, 128);
+  p.n_tiles = (int)ceil_div(Cout, tn);
+  const int64_t items = (int64_t)p.m_tiles * p.n_tiles * nprob;
+  PLB_REQUIRE(items * p.nbox < (1ll << 31), PLB_ESIZE, "plb_conv2d_forward: too many work items");
+  p.total_items = (int)items;
+  CUtensorMap m0, m1;
+  if (int rc = make_weight_map(&m0, packed_w[0], Cout, g, tn)) return rc;
+  if (int rc = make_weight_map(&m1, packed_w[nprob - 1], Cout, g, tn)) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (tn == 64) return launch_conv<64>(m0, m1, p, s);
+  return launch_conv<128>(m0, m1, p, s);
+}
