@@ -276,6 +276,8 @@ int plb_wm_progress(const float *A, int64_t ld, const int64_t *P, int32_t n, int
  * plane[0][co][ci*KH*KW + kh*KW + kw], zero padded.  plb_conv_packed_floats returns the number of
  * floats of the whole packed buffer (host-only helper).  Weights are constants of the source
  * models: pack once, reuse for every batch. */
+/* experiments only: per-box clock64 stamps of CTA 0 of later plb_conv2d_forward launches (NULL switches it off) */
+int plb_conv_debug_set_trace(unsigned long long *dev_buf);
 int64_t plb_conv_packed_floats(int64_t Cout, int64_t Cin, int32_t KH, int32_t KW);
 int plb_conv_pack_weights(const float *w, int64_t Cout, int64_t Cin, int32_t KH, int32_t KW, float *packed,
                           void *stream);

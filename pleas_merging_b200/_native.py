@@ -70,6 +70,7 @@ _SIGNATURES = {
     "plb_compose_perm": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_i64, c_ptr]),
     "plb_wm_progress": (ctypes.c_int, [c_ptr, c_i64, c_ptr, c_i32, c_ptr, c_ptr, c_ptr]),
     "plb_chol_solve": (ctypes.c_int, [c_ptr, c_i64, c_ptr, c_i64, c_f64, c_ptr, c_ptr]),
+    "plb_conv_debug_set_trace": (ctypes.c_int, [c_ptr]),
     "plb_conv_packed_floats": (c_i64, [c_i64, c_i64, c_i32, c_i32]),
     "plb_conv_pack_weights": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     "plb_conv2d_forward": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64,

@@ -17,7 +17,7 @@ import torch
 from . import _native as N
 
 ENABLED = os.environ.get("PLB_CONV", "1") == "1"
-MAX_FLAT_K = 1024
+MAX_FLAT_K = 512
 CONV_TIMER = None  # bench: list of (start event, end event, algorithmic flops, bytes)
 
 

@@ -11,12 +11,14 @@
 // loads (32 consecutive positions of one channel) and stores (32 consecutive positions of one output
 // channel) are 128-byte coalesced with no transposition.
 //
-//   A (activations) never touches shared memory: loader threads own one position each, read their
-//     32 channels of the current tap (predicated on the zero padding), split them in registers
-//     (hi = rna_tf32(x), lo = rna_tf32(x - hi)) and write both planes into TENSOR MEMORY with tcgen05.st —
-//     the MMA takes A from TMEM (tcgen05.mma [d], [a], b_desc).  That is the operand arrangement the
-//     shared-memory-bound Gram kernel's analysis asked for (profiles/r02_notes.md): shared memory carries
-//     the B operand only.
+//   A (activations): loader threads own one position each.  They gather their 32 channels of the current
+//     tap with 4-byte cp.async (zero padding = zero-size copies) into a private shared-memory ring that is
+//     several stages deep — the prefetch needs no registers and no cross-thread synchronisation, every
+//     thread reads back only what it copied — then split in registers (hi = rna_tf32(x),
+//     lo = rna_tf32(x - hi)) and write both planes into TENSOR MEMORY with tcgen05.st: the MMA takes A from
+//     TMEM (tcgen05.mma [d], [a], b_desc).  That is the operand arrangement the shared-memory-bound Gram
+//     kernel's analysis asked for (profiles/r02_notes.md): the MMAs read only the B operand from shared
+//     memory, the raw A stream crosses it once.
 //   B (weights) is packed ONCE per model (plb_conv_pack_weights: hi / lo planes, [tap][Cout][Cin]) and
 //     arrives by 4-D tensor-map TMA in the 128-byte-swizzled K-major layout.
 //   D: the tensor core's fp32 accumulator truncates, so K is cut into short chains; the MMA warp ping-pongs
@@ -26,8 +28,8 @@
 // TMEM columns: [0, 2 TN) accumulators, [2 TN, 2 TN + 4 x 64) four A stages (hi | lo, 32 k each).
 // Warp roles (576 threads, 1 CTA/SM, persistent over (position tile, model, channel tile) items):
 //   warp 0       TMA producer (weights)          warp 1        TMEM owner + MMA issuer
-//   warps 2-9    loaders: two sets of four warps (one per TMEM lane quadrant) alternate stages and
-//                prefetch their next stage into registers while converting the current one
+//   warps 2-9    loaders: two per TMEM lane quadrant, 16 of a box's 32 channels each (a single warp per
+//                quadrant was the critical path: ~630 instructions per stage, profiles/r02_notes.md)
 //   warps 10-17  promotion / epilogue (two per lane quadrant, half the channel tile each)
 #include "tma.cuh"
 
@@ -35,7 +37,7 @@ namespace plb {
 
 constexpr int kConvStages = 4;
 constexpr int kConvThreads = 576;
-constexpr int kConvMaxFlatK = 1024;  // flat form: Cin*KH*KW (padded to 32) must fit the shared-memory k table
+constexpr int kConvMaxFlatK = 512;  // flat form: Cin*KH*KW (padded to 32) must fit the shared-memory k table
 
 struct ConvParams {
   const float *x[2];
@@ -50,6 +52,8 @@ struct ConvParams {
   int flat;         // 1: k = ci*KH*KW + kh*KW + kw (any Cin), 0: k = 32-channel block x tap
   int flat_k;       // Cin*KH*KW (flat form)
   int chain_boxes;  // boxes chained into one TMEM accumulator before promotion
+  unsigned long long *trace;  // experiments only (plb_conv_debug_set_trace): 8 clock64 stamps per box of CTA 0
+  int debug;        // experiments only (PLB_CONV_DEBUG, WRONG results): 1 no gather, 2 one MMA of three, 4 no stores
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -88,6 +92,22 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m
       : "memory");
 }
 
+template <int TN>
+struct ConvCfg {
+  static constexpr int kBBytes = kConvStages * 2 * TN * 128;
+  static constexpr int kARing = TN == 128 ? 5 : 8;
+  static constexpr int kSmemBytes = kBBytes + kARing * 16384 + 1024;
+};
+
+__device__ __forceinline__ void cp_async4(uint32_t smem_dst, const float *src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 struct ConvItem {
   int prob, mt, nt;
 };
@@ -107,9 +127,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
   constexpr int kPlaneBytes = TN * 128;          // one (TN rows x 32 k) weight box
   constexpr int kStageBytes = 2 * kPlaneBytes;   // hi | lo
   constexpr uint32_t kACol0 = 2 * TN;            // first TMEM column of the A stages
+  constexpr int kARing = ConvCfg<TN>::kARing;    // depth of the loaders' cp.async ring ([c][row] fp32, 16 KB / stage)
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_b_full[kConvStages];   // TMA -> MMA
-  __shared__ uint64_t bar_a_full[kConvStages];   // loaders -> MMA
+  __shared__ uint64_t bar_full[kConvStages];     // TMA (weights, tx bytes) + the eight loader warps (A in TMEM) -> MMA
   __shared__ uint64_t bar_empty[kConvStages];    // MMA -> producer and loaders
   __shared__ uint64_t bar_acc_full[2];           // MMA -> promotion warps
   __shared__ uint64_t bar_acc_empty[2];          // promotion warps -> MMA
@@ -122,8 +142,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kConvStages; ++s) {
-      mbar_init(&bar_b_full[s], 1);
-      mbar_init(&bar_a_full[s], 4);
+      mbar_init(&bar_full[s], 1 + 8);
       mbar_init(&bar_empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -166,11 +185,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
       for (int b = 0; b < p.nbox; ++b, ++i) {
         const uint32_t s = i & (kConvStages - 1), ph = (i / kConvStages) & 1u;
         mbar_wait_wd(&bar_empty[s], ph ^ 1u);
+        if (p.trace && cta == 0 && lane == 0 && i < 512) p.trace[i * 8 + 0] = clock64();
         if (elect_one()) {
           uint8_t *st = smem + (size_t)s * kStageBytes;
-          mbar_arrive_expect_tx(&bar_b_full[s], kStageBytes);
-          tma_load_4d(st, map, cb * 32, n0, tap, 0, &bar_b_full[s]);
-          tma_load_4d(st + kPlaneBytes, map, cb * 32, n0, tap, 1, &bar_b_full[s]);
+          mbar_arrive_expect_tx(&bar_full[s], kStageBytes);
+          tma_load_4d(st, map, cb * 32, n0, tap, 0, &bar_full[s]);
+          tma_load_4d(st + kPlaneBytes, map, cb * 32, n0, tap, 1, &bar_full[s]);
         }
         __syncwarp();
         if (++tap == p.taps) {
@@ -183,19 +203,25 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_tf32(128, TN);
     const uint32_t smem_base = smem_u32(smem);
+    // tcgen05.mma issue is nearly synchronous with the tensor pipe (~65 clocks per 128 x 128 x 8 MMA, a shallow
+    // queue): every clock between the last MMA of a box and the first of the next is an idle tensor core.  So
+    // the next box's barrier is probed BEFORE the current box's MMAs are issued (its ~120-clock latency hides
+    // behind them) and A and B share one barrier per stage.
     uint32_t i = 0, chain = 0;
+    bool ready = false;  // box i's barrier was already seen complete
     for (int item = cta; item < p.total_items; item += nctas) {
       for (int b0 = 0; b0 < p.nbox; b0 += p.chain_boxes, ++chain) {
         const uint32_t buf = chain & 1u;
         mbar_wait_wd(&bar_acc_empty[buf], ((chain >> 1) & 1u) ^ 1u);
-        tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * TN;
         const int b1 = min(p.nbox, b0 + p.chain_boxes);
         for (int b = b0; b < b1; ++b, ++i) {
           const uint32_t s = i & (kConvStages - 1), ph = (i / kConvStages) & 1u;
-          mbar_wait_wd(&bar_a_full[s], ph);
-          mbar_wait_wd(&bar_b_full[s], ph);
+          if (!ready) mbar_wait_wd(&bar_full[s], ph);
+          if (p.trace && cta == 0 && lane == 0 && i < 512) p.trace[i * 8 + 4] = clock64();
           tc_fence_after();
+          const uint32_t s1 = (i + 1) & (kConvStages - 1), ph1 = ((i + 1) / kConvStages) & 1u;
+          const bool next_ready = mbar_try_wait(&bar_full[s1], ph1);
           if (elect_one()) {
             const uint32_t bst = smem_base + s * kStageBytes;
             const uint32_t a_hi0 = tmem_base + kACol0 + s * 64;
@@ -205,88 +231,116 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
               const uint64_t b_lo = umma_desc_sw<128>(bst + kPlaneBytes + 32 * j);
               const uint32_t a_hi = a_hi0 + 8 * j, a_lo = a_hi + 32;
               umma_tf32_ts(d_tmem, a_lo, b_hi, idesc, (b > b0 || j > 0) ? 1u : 0u);
-              umma_tf32_ts(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma_tf32_ts(d_tmem, a_hi, b_hi, idesc, 1u);
+              if (!(p.debug & 2)) {
+                umma_tf32_ts(d_tmem, a_hi, b_lo, idesc, 1u);
+                umma_tf32_ts(d_tmem, a_hi, b_hi, idesc, 1u);
+              }
             }
             umma_commit(&bar_empty[s]);
             if (b == b1 - 1) umma_commit(&bar_acc_full[buf]);
           }
-          __syncwarp();
+          ready = __all_sync(0xffffffffu, next_ready);
+          if (p.trace && cta == 0 && lane == 0 && i < 512) p.trace[i * 8 + 6] = clock64();
         }
       }
     }
   } else if (warp < 10) {
     // ------------------------------------------------------------------ loaders (A operand -> TMEM)
-    const int set = (warp - 2) >> 2;
+    const int hsel = (warp - 2) >> 2;        // which 16 channels of every 32-channel box
     const int row = (warp & 3) * 32 + lane;  // TMEM lane = position inside the tile
-    const uint32_t a_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kACol0;
+    const uint32_t a_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kACol0 + 16 * hsel;
+    // ring slot layout [c][row] fp32: + slot * 16 KB + c * 512
+    const uint32_t ring = smem_u32(smem) + ConvCfg<TN>::kBBytes + (uint32_t)(hsel * 16) * 512u + (uint32_t)row * 4u;
     const int my_items = cta < p.total_items ? (p.total_items - cta + nctas - 1) / nctas : 0;
     const int total = my_items * p.nbox;
-    float bufA[32], bufB[32];
-    int cur_it = -1, ih0 = 0, iw0 = 0;
+    // issue-side cursor: work item, channel block, tap
+    const int kh_n = p.flat ? 1 : p.KH, kw_n = p.flat ? 1 : p.KW, cb_n = p.nbox / (kh_n * kw_n);
+    int itx = 0, cb = 0, kh = 0, kw = 0, ih0 = 0, iw0 = 0;
     bool pvalid = false;
     const float *xn = nullptr;
+    auto locate = [&]() {  // position of this thread's row in work item itx
+      const ConvItem it = conv_item(p, cta + itx * nctas);
+      const int pos = it.mt * 128 + row;
+      pvalid = pos < p.P;
+      const int n = pvalid ? pos / p.OHW : 0, r = pos - n * p.OHW, oh = r / p.OW, ow = r - oh * p.OW;
+      ih0 = oh * p.stride - p.pad_h;
+      iw0 = ow * p.stride - p.pad_w;
+      xn = p.x[it.prob] + (int64_t)n * p.Cin * p.IHW;
+    };
+    if (total > 0) locate();
 
-    auto issue = [&](int i, float(&buf)[32]) {
-      const int itx = i / p.nbox, box = i - itx * p.nbox;
-      if (itx != cur_it) {
-        cur_it = itx;
-        const ConvItem it = conv_item(p, cta + itx * nctas);
-        const int pos = it.mt * 128 + row;
-        pvalid = pos < p.P;
-        const int n = pos / p.OHW, r = pos - n * p.OHW, oh = r / p.OW, ow = r - oh * p.OW;
-        ih0 = oh * p.stride - p.pad_h;
-        iw0 = ow * p.stride - p.pad_w;
-        xn = p.x[it.prob] + (int64_t)n * p.Cin * p.IHW;
-      }
+    // gathers this thread's 16 values of the cursor's box into ring slot `slot`, then advances the cursor
+    auto issue = [&](int slot) {
+      const uint32_t dst = ring + (uint32_t)slot * 16384u;
       if (!p.flat) {
-        const int cb = box / p.taps, tap = box - cb * p.taps, kh = tap / p.KW, kw = tap - kh * p.KW;
         const int ih = ih0 + kh, iw = iw0 + kw;
         const bool ok = pvalid && (unsigned)ih < (unsigned)p.IH && (unsigned)iw < (unsigned)p.IW;
-        const float *src = xn + (int64_t)(cb * 32) * p.IHW + ih * p.IW + iw;
+        const float *src = ok ? xn + (int64_t)(cb * 32 + hsel * 16) * p.IHW + ih * p.IW + iw : xn;
+        const int64_t cs = ok ? p.IHW : 0;
+        const uint32_t sz = ok ? 4u : 0u;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) buf[c] = ok ? __ldg(src + (int64_t)c * p.IHW) : 0.f;
+        for (int c = 0; c < 16; ++c) cp_async4(dst + c * 512, src + c * cs, sz);
       } else {
-        const float *src = xn + ih0 * p.IW + iw0;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int2 e = ktab[box * 32 + c];
+        for (int c = 0; c < 16; ++c) {
+          const int2 e = ktab[cb * 32 + hsel * 16 + c];
           const int ih = ih0 + (e.y >> 16), iw = iw0 + (e.y & 0xffff);
           const bool ok = pvalid && e.y >= 0 && (unsigned)ih < (unsigned)p.IH && (unsigned)iw < (unsigned)p.IW;
-          buf[c] = ok ? __ldg(src + e.x) : 0.f;
+          cp_async4(dst + c * 512, ok ? xn + ih0 * p.IW + iw0 + e.x : xn, ok ? 4u : 0u);
+        }
+      }
+      if (++kw == kw_n) {
+        kw = 0;
+        if (++kh == kh_n) {
+          kh = 0;
+          if (++cb == cb_n) {
+            cb = 0;
+            ++itx;
+            if (itx < my_items) locate();
+          }
         }
       }
     };
-    auto process = [&](int i, float(&buf)[32]) {
+
+    int slot_in = 0;
+#pragma unroll 1
+    for (int j = 0; j < kARing - 1; ++j) {
+      if (j < total && !(p.debug & 1)) issue(slot_in);
+      cp_async_commit();
+      if (++slot_in == kARing) slot_in = 0;
+    }
+    int slot_out = 0;
+#pragma unroll 1
+    for (int i = 0; i < total; ++i) {
+      if (i + kARing - 1 < total && !(p.debug & 1)) issue(slot_in);
+      cp_async_commit();
+      if (++slot_in == kARing) slot_in = 0;
+      cp_async_wait<kARing - 1>();  // this thread's copies of box i have landed
+      uint32_t v[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v[c]) : "r"(ring + (uint32_t)slot_out * 16384u + c * 512u) : "memory");
+      if (++slot_out == kARing) slot_out = 0;
       const uint32_t s = (uint32_t)i & (kConvStages - 1), ph = ((uint32_t)i / kConvStages) & 1u;
+      const bool tr = p.trace && cta == 0 && warp == 2 && lane == 0 && i < 512;
+      if (tr) p.trace[i * 8 + 1] = clock64();
       mbar_wait_wd(&bar_empty[s], ph ^ 1u);
+      if (tr) p.trace[i * 8 + 2] = clock64();
       tc_fence_after();
+      // hi = rna_tf32(x), lo = rna_tf32(x - hi) with integer rounding (add half an ulp, clear the 13 low bits)
+      uint32_t hi[16];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t hi[16];
+      for (int c = 0; c < 16; ++c) hi[c] = (v[c] + 0x1000u) & 0xffffe000u;
+      tmem_st16(a_base + s * 64, hi);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) hi[c] = __float_as_uint(to_tf32(buf[16 * h + c]));
-        tmem_st16(a_base + s * 64 + 16 * h, hi);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) hi[c] = __float_as_uint(to_tf32(buf[16 * h + c] - __uint_as_float(hi[c])));
-        tmem_st16(a_base + s * 64 + 32 + 16 * h, hi);
-      }
+      for (int c = 0; c < 16; ++c)
+        hi[c] = (__float_as_uint(__uint_as_float(v[c]) - __uint_as_float(hi[c])) + 0x1000u) & 0xffffe000u;
+      tmem_st16(a_base + s * 64 + 32, hi);
       tmem_st_wait();
+      if (tr) p.trace[i * 8 + 3] = clock64();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_a_full[s]);
-    };
-
-    int i = set;
-    if (i < total) issue(i, bufA);
-    while (i < total) {
-      if (i + 2 < total) issue(i + 2, bufB);
-      process(i, bufA);
-      i += 2;
-      if (i >= total) break;
-      if (i + 2 < total) issue(i + 2, bufA);
-      process(i, bufB);
-      i += 2;
+      if (lane == 0) mbar_arrive(&bar_full[s]);
     }
   } else {
     // ------------------------------------------------------------------ promotion / epilogue
@@ -317,7 +371,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
         if (lane == 0) mbar_arrive(&bar_acc_empty[buf]);
       }
       const int pos = it.mt * 128 + q * 32 + lane;
-      if (pos < p.P) {
+      if (pos < p.P && !(p.debug & 4)) {
         const int n = pos / p.OHW, r = pos - n * p.OHW;
         const int co0 = it.nt * TN + half * COLS;
         float *o = p.out[it.prob] + ((int64_t)n * p.Cout + co0) * p.OHW + r;
@@ -354,6 +408,8 @@ __global__ void conv_pack_weights_kernel(const float *__restrict__ w, float *__r
   }
 }
 
+static unsigned long long *g_conv_trace = nullptr;
+
 struct ConvGeometry {
   int flat, taps, Kc;
 };
@@ -381,7 +437,7 @@ static int make_weight_map(CUtensorMap *m, const float *packed, int64_t Cout, co
 
 template <int TN>
 static int launch_conv(const CUtensorMap &m0, const CUtensorMap &m1, const ConvParams &p, cudaStream_t stream) {
-  constexpr int smem_bytes = kConvStages * 2 * TN * 128 + 1024;
+  constexpr int smem_bytes = ConvCfg<TN>::kSmemBytes;
   if (int rc = ensure_dynamic_smem((const void *)conv3xtf32_kernel<TN>, smem_bytes, "conv3xtf32_kernel")) return rc;
   const int grid = min(p.total_items, device_sm_count());
   conv3xtf32_kernel<TN><<<grid, kConvThreads, smem_bytes, stream>>>(m0, m1, p);
@@ -389,6 +445,13 @@ static int launch_conv(const CUtensorMap &m0, const CUtensorMap &m1, const ConvP
 }
 
 }  // namespace plb
+
+// experiments only: CTA 0 of every later plb_conv2d_forward launch writes 8 clock64 stamps per box (first 512 boxes)
+// [TMA issue, loader data ready, loader slot free, loader stored, MMA sees A, MMA sees B, MMA issued, -]
+extern "C" int plb_conv_debug_set_trace(unsigned long long *dev_buf) {
+  plb::g_conv_trace = dev_buf;
+  return PLB_OK;
+}
 
 extern "C" int64_t plb_conv_packed_floats(int64_t Cout, int64_t Cin, int32_t KH, int32_t KW) {
   if (Cout <= 0 || Cin <= 0 || KH <= 0 || KW <= 0) return 0;
@@ -445,6 +508,13 @@ extern "C" int plb_conv2d_forward(const float *const *x, const float *const *pac
   p.P = (int)(NB * OH * OW), p.OHW = (int)(OH * OW), p.IHW = (int)(IH * IW);
   p.flat = g.flat, p.taps = g.taps, p.flat_k = (int)(Cin * KH * KW);
   p.nbox = g.taps * (g.Kc / 32);
+  static int debug = -1;
+  if (debug < 0) {
+    const char *d = getenv("PLB_CONV_DEBUG");
+    debug = d ? atoi(d) : 0;
+  }
+  p.debug = debug;
+  p.trace = g_conv_trace;
   p.chain_boxes = 8;  // 256 k = 96 chained MMAs per accumulator (the Gram kernels' MAX_CHAIN_KB = 16 blocks of 16 k)
   const int tn = Cout <= 64 ? 64 : 128;
   p.m_tiles = (int)ceil_div(p.P, 128);
