@@ -108,6 +108,62 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Barrier helpers on raw 32-bit shared addresses.  The kernel computes ONE opaque base (asm volatile, so the
+// compiler keeps it in a register) for all its barriers: re-deriving `&bar[s]` costs an S2R SR_CgaCtaId plus
+// address arithmetic at every use, and on the MMA-issuing warp every clock between two boxes is an idle
+// tensor core (profiles/r02_notes.md).
+__device__ __forceinline__ uint32_t opaque_smem_u32(const void *p) {
+  uint32_t a;
+  asm volatile("{\n\t.reg .u64 t;\n\tcvta.to.shared.u64 t, %1;\n\tcvt.u32.u64 %0, t;\n\t}" : "=r"(a) : "l"(p));
+  return a;
+}
+__device__ __forceinline__ void a32_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void a32_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool a32_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking probe (try_wait may suspend the thread for a while when the phase is still open)
+__device__ __forceinline__ bool a32_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void a32_wait_wd(uint32_t bar, uint32_t parity) {
+  if (a32_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!a32_try_wait(bar, parity))
+    if (clock64() - t0 > kWatchdogClocks) __trap();
+}
+__device__ __forceinline__ void a32_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void a32_tma_load_4d(uint32_t smem_dst, const CUtensorMap *map, int c0, int c1, int c2,
+                                                int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], "
+      "[%6];" ::"r"(smem_dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+
 struct ConvItem {
   int prob, mt, nt;
 };
@@ -129,25 +185,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
   constexpr uint32_t kACol0 = 2 * TN;            // first TMEM column of the A stages
   constexpr int kARing = ConvCfg<TN>::kARing;    // depth of the loaders' cp.async ring ([c][row] fp32, 16 KB / stage)
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_full[kConvStages];     // TMA (weights, tx bytes) + the eight loader warps (A in TMEM) -> MMA
-  __shared__ uint64_t bar_empty[kConvStages];    // MMA -> producer and loaders
-  __shared__ uint64_t bar_acc_full[2];           // MMA -> promotion warps
-  __shared__ uint64_t bar_acc_empty[2];          // promotion warps -> MMA
+  // [0,4) full: TMA (weights, tx bytes) + the eight loader warps (A in TMEM) -> MMA;  [4,8) empty: MMA -> producer
+  // and loaders;  [8,10) accumulator full: MMA -> promotion warps;  [10,12) accumulator empty: promotion -> MMA
+  __shared__ uint64_t bars[2 * kConvStages + 4];
   __shared__ uint32_t tmem_base_s;
   __shared__ int2 ktab[kConvMaxFlatK];           // flat form: k -> (ci*IHW + kh*IW + kw, kh << 16 | kw)
 
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = (int)blockIdx.x, nctas = (int)gridDim.x;
+  const uint32_t bars_a = opaque_smem_u32(bars), smem_a = opaque_smem_u32(smem);
+  const uint32_t bar_full = bars_a, bar_empty = bars_a + 8 * kConvStages, bar_acc_full = bars_a + 16 * kConvStages,
+                 bar_acc_empty = bar_acc_full + 16;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < kConvStages; ++s) {
-      mbar_init(&bar_full[s], 1 + 8);
-      mbar_init(&bar_empty[s], 1);
+      mbar_init(&bars[s], 1 + 8);
+      mbar_init(&bars[kConvStages + s], 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&bar_acc_full[b], 1);
-      mbar_init(&bar_acc_empty[b], 8);
+      mbar_init(&bars[2 * kConvStages + b], 1);
+      mbar_init(&bars[2 * kConvStages + 2 + b], 8);
     }
     fence_mbar_init();
   } else if (warp == 1) {
@@ -184,13 +242,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
       int cb = 0, tap = 0;
       for (int b = 0; b < p.nbox; ++b, ++i) {
         const uint32_t s = i & (kConvStages - 1), ph = (i / kConvStages) & 1u;
-        mbar_wait_wd(&bar_empty[s], ph ^ 1u);
+        a32_wait_wd(bar_empty + 8 * s, ph ^ 1u);
         if (p.trace && cta == 0 && lane == 0 && i < 512) p.trace[i * 8 + 0] = clock64();
         if (elect_one()) {
-          uint8_t *st = smem + (size_t)s * kStageBytes;
-          mbar_arrive_expect_tx(&bar_full[s], kStageBytes);
-          tma_load_4d(st, map, cb * 32, n0, tap, 0, &bar_full[s]);
-          tma_load_4d(st + kPlaneBytes, map, cb * 32, n0, tap, 1, &bar_full[s]);
+          const uint32_t st = smem_a + s * kStageBytes;
+          a32_expect_tx(bar_full + 8 * s, kStageBytes);
+          a32_tma_load_4d(st, map, cb * 32, n0, tap, 0, bar_full + 8 * s);
+          a32_tma_load_4d(st + kPlaneBytes, map, cb * 32, n0, tap, 1, bar_full + 8 * s);
         }
         __syncwarp();
         if (++tap == p.taps) {
@@ -202,44 +260,55 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_tf32(128, TN);
-    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t smem_base = smem_a;
     // tcgen05.mma issue is nearly synchronous with the tensor pipe (~65 clocks per 128 x 128 x 8 MMA, a shallow
     // queue): every clock between the last MMA of a box and the first of the next is an idle tensor core.  So
     // the next box's barrier is probed BEFORE the current box's MMAs are issued (its ~120-clock latency hides
     // behind them) and A and B share one barrier per stage.
     uint32_t i = 0, chain = 0;
-    bool ready = false;  // box i's barrier was already seen complete
+    bool ready = false;   // box i's barrier was already seen complete
+    bool acc_ok = false;  // the next chain's accumulator was already seen drained
     for (int item = cta; item < p.total_items; item += nctas) {
       for (int b0 = 0; b0 < p.nbox; b0 += p.chain_boxes, ++chain) {
         const uint32_t buf = chain & 1u;
-        mbar_wait_wd(&bar_acc_empty[buf], ((chain >> 1) & 1u) ^ 1u);
-        const uint32_t d_tmem = tmem_base + buf * TN;
+        if (!acc_ok && !(p.debug & 8)) a32_wait_wd(bar_acc_empty + 8 * buf, ((chain >> 1) & 1u) ^ 1u);
+        acc_ok = false;
+        const uint32_t d_tmem = tmem_base + ((p.debug & 32) ? 0u : buf * TN);
         const int b1 = min(p.nbox, b0 + p.chain_boxes);
         for (int b = b0; b < b1; ++b, ++i) {
           const uint32_t s = i & (kConvStages - 1), ph = (i / kConvStages) & 1u;
-          if (!ready) mbar_wait_wd(&bar_full[s], ph);
+          if (!ready) a32_wait_wd(bar_full + 8 * s, ph);
           if (p.trace && cta == 0 && lane == 0 && i < 512) p.trace[i * 8 + 4] = clock64();
           tc_fence_after();
           const uint32_t s1 = (i + 1) & (kConvStages - 1), ph1 = ((i + 1) / kConvStages) & 1u;
-          const bool next_ready = mbar_try_wait(&bar_full[s1], ph1);
+          const bool next_ready = a32_test_wait(bar_full + 8 * s1, ph1);
+          bool next_acc = false;
+          if (b == b1 - 1 && !(p.debug & 8))  // the next box (if any) opens chain + 1
+            next_acc = a32_test_wait(bar_acc_empty + 8 * ((chain + 1) & 1u), (((chain + 1) >> 1) & 1u) ^ 1u);
           if (elect_one()) {
             const uint32_t bst = smem_base + s * kStageBytes;
             const uint32_t a_hi0 = tmem_base + kACol0 + s * 64;
+            // The two small products first: while the accumulator only holds lo x hi terms (2^-11 of the final
+            // magnitude) the tensor core's truncating adds cost nothing; the four hi x hi MMAs of the box are then
+            // the only adds at full magnitude.
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint64_t b_hi = umma_desc_sw<128>(bst + 32 * j);
               const uint64_t b_lo = umma_desc_sw<128>(bst + kPlaneBytes + 32 * j);
               const uint32_t a_hi = a_hi0 + 8 * j, a_lo = a_hi + 32;
-              umma_tf32_ts(d_tmem, a_lo, b_hi, idesc, (b > b0 || j > 0) ? 1u : 0u);
-              if (!(p.debug & 2)) {
-                umma_tf32_ts(d_tmem, a_hi, b_lo, idesc, 1u);
-                umma_tf32_ts(d_tmem, a_hi, b_hi, idesc, 1u);
-              }
+              umma_tf32_ts(d_tmem, a_lo, b_hi, idesc, (b > b0 || j > 0 || (p.debug & 16)) ? 1u : 0u);
+              if (!(p.debug & 2)) umma_tf32_ts(d_tmem, a_hi, b_lo, idesc, 1u);
             }
-            umma_commit(&bar_empty[s]);
-            if (b == b1 - 1) umma_commit(&bar_acc_full[buf]);
+            if (!(p.debug & 2)) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                umma_tf32_ts(d_tmem, a_hi0 + 8 * j, umma_desc_sw<128>(bst + 32 * j), idesc, 1u);
+            }
+            a32_commit(bar_empty + 8 * s);
+            if (b == b1 - 1) a32_commit(bar_acc_full + 8 * buf);
           }
           ready = __all_sync(0xffffffffu, next_ready);
+          if (b == b1 - 1) acc_ok = __all_sync(0xffffffffu, next_acc);
           if (p.trace && cta == 0 && lane == 0 && i < 512) p.trace[i * 8 + 6] = clock64();
         }
       }
@@ -250,7 +319,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
     const int row = (warp & 3) * 32 + lane;  // TMEM lane = position inside the tile
     const uint32_t a_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kACol0 + 16 * hsel;
     // ring slot layout [c][row] fp32: + slot * 16 KB + c * 512
-    const uint32_t ring = smem_u32(smem) + ConvCfg<TN>::kBBytes + (uint32_t)(hsel * 16) * 512u + (uint32_t)row * 4u;
+    const uint32_t ring = smem_a + ConvCfg<TN>::kBBytes + (uint32_t)(hsel * 16) * 512u + (uint32_t)row * 4u;
     const int my_items = cta < p.total_items ? (p.total_items - cta + nctas - 1) / nctas : 0;
     const int total = my_items * p.nbox;
     // issue-side cursor: work item, channel block, tap
@@ -323,9 +392,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
       if (++slot_out == kARing) slot_out = 0;
       const uint32_t s = (uint32_t)i & (kConvStages - 1), ph = ((uint32_t)i / kConvStages) & 1u;
       const bool tr = p.trace && cta == 0 && warp == 2 && lane == 0 && i < 512;
-      if (tr) p.trace[i * 8 + 1] = clock64();
-      mbar_wait_wd(&bar_empty[s], ph ^ 1u);
-      if (tr) p.trace[i * 8 + 2] = clock64();
+      a32_wait_wd(bar_empty + 8 * s, ph ^ 1u);
       tc_fence_after();
       // hi = rna_tf32(x), lo = rna_tf32(x - hi) with integer rounding (add half an ulp, clear the 13 low bits)
       uint32_t hi[16];
@@ -340,7 +407,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
       if (tr) p.trace[i * 8 + 3] = clock64();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_full[s]);
+      if (lane == 0) a32_arrive(bar_full + 8 * s);
     }
   } else {
     // ------------------------------------------------------------------ promotion / epilogue
@@ -355,7 +422,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
       for (int c = 0; c < COLS; ++c) acc[c] = 0.f;
       for (int b0 = 0; b0 < p.nbox; b0 += p.chain_boxes, ++chain) {
         const uint32_t buf = chain & 1u;
-        mbar_wait_wd(&bar_acc_full[buf], (chain >> 1) & 1u);
+        a32_wait_wd(bar_acc_full + 8 * buf, (chain >> 1) & 1u);
+        const bool tr = p.trace && cta == 0 && warp == 10 && lane == 0 && chain < 512;
+        if (tr) p.trace[chain * 8 + 5] = clock64();
         tc_fence_after();
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TN + half * COLS;
 #pragma unroll
@@ -368,7 +437,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_acc_empty[buf]);
+        if (lane == 0) a32_arrive(bar_acc_empty + 8 * buf);
+        if (tr) p.trace[chain * 8 + 7] = clock64();
       }
       const int pos = it.mt * 128 + q * 32 + lane;
       if (pos < p.P && !(p.debug & 4)) {
@@ -376,9 +446,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
         const int co0 = it.nt * TN + half * COLS;
         float *o = p.out[it.prob] + ((int64_t)n * p.Cout + co0) * p.OHW + r;
         const float *bias = p.bias[it.prob];
+        const int ohw = p.OHW;
+        // one IMAD.WIDE + one STG per value on the common path (full channel tile, no bias): the store loop is
+        // what bounds the small-K layers, 64 values per thread and item
+        if (bias == nullptr && co0 + COLS <= p.Cout) {
 #pragma unroll
-        for (int c = 0; c < COLS; ++c)
-          if (co0 + c < p.Cout) o[(int64_t)c * p.OHW] = acc[c] + (bias ? __ldg(bias + co0 + c) : 0.f);
+          for (int c = 0; c < COLS; ++c) o[(int64_t)c * ohw] = acc[c];
+        } else {
+          const int nc = min(COLS, p.Cout - co0);
+#pragma unroll
+          for (int c = 0; c < COLS; ++c)
+            if (c < nc) o[(int64_t)c * ohw] = acc[c] + (bias ? __ldg(bias + co0 + c) : 0.f);
+        }
       }
     }
   }
@@ -515,7 +594,17 @@ extern "C" int plb_conv2d_forward(const float *const *x, const float *const *pac
   }
   p.debug = debug;
   p.trace = g_conv_trace;
-  p.chain_boxes = 8;  // 256 k = 96 chained MMAs per accumulator (the Gram kernels' MAX_CHAIN_KB = 16 blocks of 16 k)
+  // The tensor core truncates when it adds into its fp32 accumulator (about -1e-7 relative per 16 k, gemm.cu): a
+  // bias that compounds through the layers of a network (activations shrink a little in every layer).  Chains are
+  // therefore ONE box (32 k) and the promotion warps add every chain with round-to-nearest.  Measured on the
+  // ResNet-50 pair (tests/test_configs_gpu.py, worst deviation of a group's objective from the reference's):
+  // 8-box chains > 1.3e-5, 2 boxes 1.0e-5, 1 box 5.2e-6 (cuDNN fp32 forwards: ~4e-6).
+  static int chain = 0;
+  if (chain == 0) {
+    const char *c = getenv("PLB_CONV_CHAIN");  // experiments: boxes per accumulation chain
+    chain = (c && atoi(c) > 0) ? atoi(c) : 1;
+  }
+  p.chain_boxes = chain;
   const int tn = Cout <= 64 ? 64 : 128;
   p.m_tiles = (int)ceil_div(p.P, 128);
   p.n_tiles = (int)ceil_div(Cout, tn);

@@ -25,7 +25,7 @@ import torch
 import torch.fx
 from torch.nn import Module
 
-from .. import ops
+from .. import conv, ops
 from ..core.solvers import b200_solve_lsa, solve_lsa_batched
 from ..core.utils import Axis, Permutation, PermutationSpec
 from ..graphs import GraphedStep
@@ -80,13 +80,25 @@ def _mutates_inputs(node, root):
     return False
 
 
-def _dual_graph(model1: Module, model2: Module, axes: Collection, emit, emit_sync=None):
+_CONV_PAIRS = {}
+_conv_ids = itertools.count()
+
+
+def _conv_pair_dispatch(pair_id: int, xa, xb):
+    """fx ``call_function`` target: the same convolution layer of both models in one launch of the library's
+    3xTF32 tcgen05 kernel (conv.ConvPair; falls back to the modules for inputs it does not cover)."""
+    return _CONV_PAIRS[pair_id](xa, xb)
+
+
+def _dual_graph(model1: Module, model2: Module, axes: Collection, emit, emit_sync=None, conv_pairs=None):
     """Runs both models side by side in one fx graph (model2 must trace to model1's graph, as
     in the reference, :68).  After every tapped node ``emit(graph, name, axis, node_a, node_b)``
     inserts the tap consumer right behind its producers — torchvision's in-place ReLU
     overwrites the preceding tap's storage, so consumers must not be deferred.  ``emit_sync(graph)``
     (optional) is inserted before every node that may mutate an input: a consumer that reads taps
-    asynchronously gets the chance to finish first."""
+    asynchronously gets the chance to finish first.  ``conv_pairs`` (a list, optional): eligible Conv2d layers are
+    not called as modules but pairwise through ``_conv_pair_dispatch``; the ids registered in ``_CONV_PAIRS`` are
+    appended to the list for the caller to release."""
     traced = torch.fx.symbolic_trace(model1)
     taps = _tap_axes(axes)
     g = torch.fx.Graph()
@@ -104,6 +116,17 @@ def _dual_graph(model1: Module, model2: Module, axes: Collection, emit, emit_syn
             continue
         if emit_sync is not None and _mutates_inputs(node, traced):
             emit_sync(g)
+        pair = _conv_pair_for(node, model1, model2) if conv_pairs is not None else None
+        if pair is not None:
+            pid = next(_conv_ids)
+            _CONV_PAIRS[pid] = pair
+            conv_pairs.append(pid)
+            both = g.call_function(_conv_pair_dispatch, (pid, env[0][node.args[0]], env[1][node.args[0]]))
+            env[0][node] = g.call_function(operator.getitem, (both, 0))
+            env[1][node] = g.call_function(operator.getitem, (both, 1))
+            for a in taps.get(node.name, ()):
+                emitted[node.name, a] = emit(g, node.name, a, env[0][node], env[1][node])
+            continue
         for side in (0, 1):
             new = g.node_copy(node, lambda n, side=side: env[side][n])
             if node.op in ("call_module", "get_attr"):
@@ -115,6 +138,21 @@ def _dual_graph(model1: Module, model2: Module, axes: Collection, emit, emit_syn
     gm = torch.fx.GraphModule(torch.nn.ModuleList([model1, model2]), g)
     gm.graph.lint()
     return gm
+
+
+def _conv_pair_for(node, model1, model2):
+    """ConvPair for an fx ``call_module`` node that is the same eligible Conv2d in both models, else None."""
+    if node.op != "call_module" or len(node.args) != 1 or node.kwargs:
+        return None
+    try:
+        ma, mb = model1.get_submodule(node.target), model2.get_submodule(node.target)
+    except AttributeError:
+        return None
+    if not (conv.eligible(ma) and conv.eligible(mb)) or ma._forward_hooks or mb._forward_hooks or \
+            ma._forward_pre_hooks or mb._forward_pre_hooks:
+        return None
+    pair = conv.ConvPair(ma, mb)
+    return pair if pair.same_geometry() else None
 
 
 def build_cross_module(model1: Module, model2: Module, axes: Collection, cross_features):
@@ -565,13 +603,27 @@ class CalibrationRunner:
             overlap = os.environ.get("PLB_OVERLAP", "0") == "1"
         self.acc = CrossAccumulator(spec, mode, self.device, overlap=overlap)
         axes = [ax for pg in spec.values() for ax in pg.node]
-        self.gm = _dual_graph(model1, model2, axes, self.acc.emit, self.acc.emit_sync if overlap else None)
+        self.conv_pairs = []
+        self.gm = _dual_graph(model1, model2, axes, self.acc.emit, self.acc.emit_sync if overlap else None,
+                              conv_pairs=self.conv_pairs if conv.ENABLED else None)
         self.reset = accumulate == "reference"
         self.step = GraphedStep(self._eager, self.acc.rebind_stale, use_cuda_graph)
 
     def close(self):
         self.step.clear()
         self.acc.close()
+        for pid in self.conv_pairs:
+            _CONV_PAIRS.pop(pid, None)
+        self.conv_pairs = []
+
+    def refresh_weights(self):
+        """Re-splits convolution weights that changed since they were packed (a CUDA-graph replay runs no
+        Python: the packed planes it reads are brought up to date here, before the batches of a call)."""
+        for pid in self.conv_pairs:
+            pair = _CONV_PAIRS[pid]
+            if pair.packs is not None:
+                pair.packs[0].refresh()
+                pair.packs[1].refresh()
 
     def _eager(self, x):
         self.acc.begin_batch(reset_costs=self.reset)
@@ -640,6 +692,7 @@ def _fused_costs(spec, model1, model2, dataloader, num_batches, mode, accumulate
     runner = _get_runner(spec, model1, model2, mode, accumulate, use_cuda_graph)
     ok = False
     try:
+        runner.refresh_weights()
         sharder = BatchSharder(dataloader, num_batches, *(() if distributed else (0, 1)))
         with torch.inference_mode():
             for i, x in device_prefetch(sharder, runner.device):

@@ -22,12 +22,13 @@ more pack + GEMM pass with its own channel maps into the same accumulators.
 optimizer and schedule) for weight-level parity checks.  Gradient masks reproduce the
 reference's index order ``mask[si1, so2]``.
 """
+import os
 import time
 from copy import copy, deepcopy
 
 import torch
 
-from .. import ops
+from .. import conv, ops
 from ..core.utils import Axis, get_attr
 from ..graphs import GraphedStep
 from ..parallel import (BatchSharder, allreduce_sum_, assign_owners, device_prefetch, reduce_to_owners_,
@@ -368,6 +369,8 @@ class LstsqRunner:
         self.separate_classifier, self.model_type = separate_classifier, model_type
         self.acts1, self.acts2 = {}, {}
         self.hooks = capture_inputs(model1, self.acts1) + capture_inputs(model2, self.acts2)
+        # the source models' convolutions run on the library's 3xTF32 tcgen05 kernel (conv.py) while this runner lives
+        self.conv_patch = conv.patched_convs(model1, model2).open()
         self.layers3 = {n: m for n, m in model3.named_modules() if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear))}
         self.accs, self.flat, self.ws = None, None, _Workspace(self.device)
         self.step = GraphedStep(self._eager, self._rebind, use_cuda_graph)
@@ -376,6 +379,7 @@ class LstsqRunner:
 
     def close(self):
         self.step.clear()
+        self.conv_patch.close()
         for h in self.hooks:
             h.remove()
         self.acts1.clear()
@@ -468,15 +472,28 @@ def _train_lstsq(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, sep
     model1.eval()
     model2.eval()
     rank, wsize = world() if distributed else (0, 1)
+    dbg = os.environ.get("PLB_DEBUG_TIMING") == "1"
+    if dbg:
+        torch.cuda.synchronize()
+        t_dbg = time.perf_counter()
     runner = LstsqRunner(model1, model2, model3, perm_blocks, num_classes, separate_classifier, model_type,
                          use_cuda_graph, merging, wsize)
+    if dbg:
+        torch.cuda.synchronize()
+        print(f"[plb timing] LstsqRunner construction {time.perf_counter() - t_dbg:.3f}s", flush=True)
     t_start = time.perf_counter()
     try:
         # the reference's loop breaks when idx > MAX_STEPS, i.e. it consumes MAX_STEPS + 1 batches
         sharder = BatchSharder(((b[0], 0) for b in dataloader), MAX_STEPS + 1, rank, wsize)
         with torch.no_grad():
-            for _, x in device_prefetch(sharder, runner.device):
+            for bi_, x in device_prefetch(sharder, runner.device):
                 runner.run(x)
+                if dbg and bi_ < 4:
+                    torch.cuda.synchronize()
+                    print(f"[plb timing] PLeaS batch {bi_} done at +{time.perf_counter() - t_start:.3f}s", flush=True)
+            if dbg:
+                torch.cuda.synchronize()
+                print(f"[plb timing] PLeaS loop end +{time.perf_counter() - t_start:.3f}s", flush=True)
             if wsize > 1:  # collective decision: a rank without a batch has no layer shapes to reduce into
                 have = torch.tensor([int(runner.accs is not None)], device=runner.device)
                 torch.distributed.all_reduce(have, op=torch.distributed.ReduceOp.MIN)
@@ -537,7 +554,13 @@ def _train_lstsq(dataloader, model1, model2, model3, perm_blocks, MAX_STEPS, sep
                 torch.cuda.synchronize()
                 stats["_timing"]["solve_s"] = time.perf_counter() - t_solve
     finally:
+        if dbg:
+            torch.cuda.synchronize()
+            t_dbg = time.perf_counter()
         runner.close()
+        if dbg:
+            torch.cuda.synchronize()
+            print(f"[plb timing] runner.close {time.perf_counter() - t_dbg:.3f}s", flush=True)
     return model3
 
 
