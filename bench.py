@@ -42,7 +42,7 @@ def workload_of(model_name, batch=None):
     """The workload both arms run (identical `config.workload`): what differs is who executes it."""
     return (f"{model_name} pair (random init, eval), activation_matching cost accumulation over batches of "
             f"{BATCH if batch is None else batch}x3x{HW}x{HW}, -cdist statistic on all taps, accumulate=sum, "
-            f"exact-fp32 forwards")
+            f"fp32-accurate forwards (no TF32 / bf16 rounding of the products)")
 
 
 def num_classes_of(model_name):
@@ -353,6 +353,7 @@ def _run_b200(args):
 
     import pleas_merging_b200 as P
     from pleas_merging_b200 import _native, ops
+    from pleas_merging_b200 import conv as conv_mod
 
     AM = importlib.import_module("pleas_merging_b200.methods.activation_matching")
     PM = importlib.import_module("pleas_merging_b200.methods.pleas_merging")
@@ -424,6 +425,7 @@ def _run_b200(args):
         # (events cannot bracket nodes of a replay), so the same steps are re-run un-captured with
         # events around every launch on the launching stream
         ops.GEMM_TIMER, ops.PACK_TIMER, ops.DIRECT_TIMER = [], [], []
+        conv_mod.CONV_TIMER = []
         overlap_was, acc.overlap = acc.overlap, False  # time the kernel alone, not time-sliced with cuDNN
         n_eager = min(K, 5)
         torch.cuda.nvtx.range_push("plb_eager")
@@ -435,6 +437,7 @@ def _run_b200(args):
         timer, ops.GEMM_TIMER = ops.GEMM_TIMER, None
         pack_timer, ops.PACK_TIMER = ops.PACK_TIMER, None
         direct_timer, ops.DIRECT_TIMER = ops.DIRECT_TIMER, None
+        conv_timer, conv_mod.CONV_TIMER = conv_mod.CONV_TIMER, None
         launches = launches_per_step * K
     t = torch.tensor([ms], dtype=torch.float64, device=device)
     if world > 1:
@@ -447,9 +450,11 @@ def _run_b200(args):
            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": workload_of(args.model) if not args.tf32_convs else
-                      workload_of(args.model).replace("exact-fp32 forwards", "TF32 cuDNN forwards (secondary number)")},
-           "implementation": {"kernels": f"3xTF32 tcgen05 Gram kernels on {taps} taps, {K} batches per GPU replayed as one "
-                                         f"CUDA graph per batch",
+                      workload_of(args.model).replace("fp32-accurate forwards (no TF32 / bf16 rounding of the products)",
+                                                     "TF32 cuDNN forwards (secondary number)")},
+           "implementation": {"kernels": f"3xTF32 tcgen05 Gram kernels on {taps} taps, the source models' convolutions on the "
+                                         f"3xTF32 tcgen05 implicit-GEMM kernel (PLB_CONV=0: cuDNN fp32), {K} batches per GPU "
+                                         f"replayed as one CUDA graph per batch",
                               "parallelism": f"batch-sharded x{world}, one NCCL all-reduce of the cost matrices",
                               "l2": "inputs larger than L2: every step streams ~10 GB of activations"},
            "gpu_launches": launches, "launches_per_step": launch_mix}
@@ -533,6 +538,18 @@ def _run_b200(args):
                      "hi/lo planes); " + common)
     if r:
         out["roofline_pack"] = r
+    if conv_timer:
+        r = tensor_roofline(
+            "conv3xtf32_kernel", [(a, b, f) for a, b, f, _, _ in conv_timer],
+            "forward convolutions of BOTH source models (one launch per layer pair, plb_conv2d_forward): 3xTF32 implicit "
+            "GEMM, A operand split in registers and fed from TMEM, weights packed once + TMA; achieved = 3 x algorithmic "
+            "FLOPs (2*N*OH*OW*Cout*Cin*KH*KW per model) / summed launch time; the 1x1 layers with 64-256 input channels "
+            "are HBM-bound (see roofline_conv.hbm_gbs); " + common)
+        if r:
+            c_ms = sum(a.elapsed_time(b) for a, b, _, _, _ in conv_timer)
+            r["hbm_gbs"] = sum(n for _, _, _, n, _ in conv_timer) / (c_ms / 1e3) / 1e9
+            r["cudnn_fp32_ms_per_step"] = None
+            out["roofline_conv"] = r
     out["clocks"] = clocks
 
     # ---- e2e through the public API with pinned host batches (H2D + LAP + D2H of the perms inside)

@@ -99,8 +99,14 @@ struct ConvCfg {
   static constexpr int kSmemBytes = kBBytes + kARing * 16384 + 1024;
 };
 
-__device__ __forceinline__ void cp_async4(uint32_t smem_dst, const float *src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(src), "r"(src_bytes) : "memory");
+// 4-byte cp.async; `ignore` != 0 writes zeros instead of reading src (the convolution's zero padding)
+__device__ __forceinline__ void cp_async4(uint32_t smem_dst, const float *src, uint32_t ignore) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %2, 0;\n\t"
+      "cp.async.ca.shared.global [%0], [%1], 4, p;\n\t}" ::"r"(smem_dst),
+      "l"(src), "r"(ignore)
+      : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -176,7 +182,8 @@ __device__ __forceinline__ ConvItem conv_item(const ConvParams &p, int item) {
   return it;
 }
 
-template <int TN>
+// TN: output-channel tile; CH: boxes per accumulation chain; DBG: experiments build (trace stamps, PLB_CONV_DEBUG)
+template <int TN, int CH, bool DBG>
 __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __grid_constant__ CUtensorMap tmw0,
                                                                       const __grid_constant__ CUtensorMap tmw1,
                                                                       ConvParams p) {
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
       for (int b = 0; b < p.nbox; ++b, ++i) {
         const uint32_t s = i & (kConvStages - 1), ph = (i / kConvStages) & 1u;
         a32_wait_wd(bar_empty + 8 * s, ph ^ 1u);
-        if (p.trace && cta == 0 && lane == 0 && i < 512) p.trace[i * 8 + 0] = clock64();
+        if (DBG && p.trace && cta == 0 && lane == 0 && i < 512) p.trace[i * 16 + 0] = clock64();
         if (elect_one()) {
           const uint32_t st = smem_a + s * kStageBytes;
           a32_expect_tx(bar_full + 8 * s, kStageBytes);
@@ -261,56 +268,68 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_tf32(128, TN);
     const uint32_t smem_base = smem_a;
-    // tcgen05.mma issue is nearly synchronous with the tensor pipe (~65 clocks per 128 x 128 x 8 MMA, a shallow
-    // queue): every clock between the last MMA of a box and the first of the next is an idle tensor core.  So
-    // the next box's barrier is probed BEFORE the current box's MMAs are issued (its ~120-clock latency hides
-    // behind them) and A and B share one barrier per stage.
+    // Every clock this warp spends between the last MMA of a chain and the first of the next is an idle tensor
+    // core, and the SM's issue slots are contended by sixteen busy loader / promotion warps (a barrier probe
+    // costs 100-250 clocks here, profiles/r02_notes.md).  So: one barrier per stage for A and B, the next
+    // chain's barriers are probed (non-blocking test_wait) BEFORE this chain's MMAs are issued, and barrier
+    // addresses are plain registers.
+    // A chain = up to chain_boxes consecutive boxes into one accumulator.  All small products of the chain are
+    // issued first: while the accumulator only holds lo x hi terms (2^-11 of the final magnitude) the tensor
+    // core's truncating adds cost nothing, so only the hi x hi MMAs add at full magnitude.
     uint32_t i = 0, chain = 0;
-    bool ready = false;   // box i's barrier was already seen complete
+    uint32_t ready = 0;   // bit q: box i + q's barrier was already seen complete
     bool acc_ok = false;  // the next chain's accumulator was already seen drained
     for (int item = cta; item < p.total_items; item += nctas) {
-      for (int b0 = 0; b0 < p.nbox; b0 += p.chain_boxes, ++chain) {
+      for (int b0 = 0; b0 < p.nbox; b0 += CH, ++chain) {
         const uint32_t buf = chain & 1u;
-        if (!acc_ok && !(p.debug & 8)) a32_wait_wd(bar_acc_empty + 8 * buf, ((chain >> 1) & 1u) ^ 1u);
-        acc_ok = false;
-        const uint32_t d_tmem = tmem_base + ((p.debug & 32) ? 0u : buf * TN);
-        const int b1 = min(p.nbox, b0 + p.chain_boxes);
-        for (int b = b0; b < b1; ++b, ++i) {
-          const uint32_t s = i & (kConvStages - 1), ph = (i / kConvStages) & 1u;
-          if (!ready) a32_wait_wd(bar_full + 8 * s, ph);
-          if (p.trace && cta == 0 && lane == 0 && i < 512) p.trace[i * 8 + 4] = clock64();
-          tc_fence_after();
-          const uint32_t s1 = (i + 1) & (kConvStages - 1), ph1 = ((i + 1) / kConvStages) & 1u;
-          const bool next_ready = a32_test_wait(bar_full + 8 * s1, ph1);
-          bool next_acc = false;
-          if (b == b1 - 1 && !(p.debug & 8))  // the next box (if any) opens chain + 1
-            next_acc = a32_test_wait(bar_acc_empty + 8 * ((chain + 1) & 1u), (((chain + 1) >> 1) & 1u) ^ 1u);
-          if (elect_one()) {
-            const uint32_t bst = smem_base + s * kStageBytes;
-            const uint32_t a_hi0 = tmem_base + kACol0 + s * 64;
-            // The two small products first: while the accumulator only holds lo x hi terms (2^-11 of the final
-            // magnitude) the tensor core's truncating adds cost nothing; the four hi x hi MMAs of the box are then
-            // the only adds at full magnitude.
+        const int nb = min(CH, p.nbox - b0);
+        const bool trm = DBG && p.trace && cta == 0 && lane == 0 && i < 512;
+        if (trm) p.trace[i * 16 + 8] = clock64();
+        if (!acc_ok) a32_wait_wd(bar_acc_empty + 8 * buf, ((chain >> 1) & 1u) ^ 1u);
+        const uint32_t d_tmem = tmem_base + buf * TN;
+#pragma unroll
+        for (int q = 0; q < CH; ++q)
+          if (q < nb && !((ready >> q) & 1u)) a32_wait_wd(bar_full + 8 * ((i + q) & (kConvStages - 1)), ((i + q) / kConvStages) & 1u);
+        if (trm) p.trace[i * 16 + 4] = clock64();
+        tc_fence_after();
+        // probes for the next chain (harmless when there is none: they just report "not yet")
+        uint32_t nready = 0;
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+          const uint32_t in = i + nb + q;
+          if (a32_test_wait(bar_full + 8 * (in & (kConvStages - 1)), (in / kConvStages) & 1u)) nready |= 1u << q;
+        }
+        const bool next_acc = a32_test_wait(bar_acc_empty + 8 * ((chain + 1) & 1u), (((chain + 1) >> 1) & 1u) ^ 1u);
+        if (elect_one()) {
+#pragma unroll
+          for (int q = 0; q < CH; ++q) {
+            if (q >= nb) break;
+            const uint32_t s = (i + q) & (kConvStages - 1);
+            const uint32_t bst = smem_base + s * kStageBytes, a_hi0 = tmem_base + kACol0 + s * 64;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint64_t b_hi = umma_desc_sw<128>(bst + 32 * j);
-              const uint64_t b_lo = umma_desc_sw<128>(bst + kPlaneBytes + 32 * j);
-              const uint32_t a_hi = a_hi0 + 8 * j, a_lo = a_hi + 32;
-              umma_tf32_ts(d_tmem, a_lo, b_hi, idesc, (b > b0 || j > 0 || (p.debug & 16)) ? 1u : 0u);
-              if (!(p.debug & 2)) umma_tf32_ts(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_tf32_ts(d_tmem, a_hi0 + 32 + 8 * j, umma_desc_sw<128>(bst + 32 * j), idesc, (q > 0 || j > 0) ? 1u : 0u);
+              if (!(DBG && p.debug & 2))
+                umma_tf32_ts(d_tmem, a_hi0 + 8 * j, umma_desc_sw<128>(bst + kPlaneBytes + 32 * j), idesc, 1u);
             }
-            if (!(p.debug & 2)) {
+          }
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                umma_tf32_ts(d_tmem, a_hi0 + 8 * j, umma_desc_sw<128>(bst + 32 * j), idesc, 1u);
+          for (int q = 0; q < CH; ++q) {
+            if (q >= nb) break;
+            const uint32_t s = (i + q) & (kConvStages - 1);
+            const uint32_t bst = smem_base + s * kStageBytes, a_hi0 = tmem_base + kACol0 + s * 64;
+            if (!(DBG && p.debug & 2)) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_tf32_ts(d_tmem, a_hi0 + 8 * j, umma_desc_sw<128>(bst + 32 * j), idesc, 1u);
             }
             a32_commit(bar_empty + 8 * s);
-            if (b == b1 - 1) a32_commit(bar_acc_full + 8 * buf);
           }
-          ready = __all_sync(0xffffffffu, next_ready);
-          if (b == b1 - 1) acc_ok = __all_sync(0xffffffffu, next_acc);
-          if (p.trace && cta == 0 && lane == 0 && i < 512) p.trace[i * 8 + 6] = clock64();
+          a32_commit(bar_acc_full + 8 * buf);
         }
+        ready = __reduce_and_sync(0xffffffffu, nready);
+        acc_ok = __all_sync(0xffffffffu, next_acc);
+        if (trm) p.trace[i * 16 + 6] = clock64();
+        i += nb;
       }
     }
   } else if (warp < 10) {
@@ -345,17 +364,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
         const int ih = ih0 + kh, iw = iw0 + kw;
         const bool ok = pvalid && (unsigned)ih < (unsigned)p.IH && (unsigned)iw < (unsigned)p.IW;
         const float *src = ok ? xn + (int64_t)(cb * 32 + hsel * 16) * p.IHW + ih * p.IW + iw : xn;
-        const int64_t cs = ok ? p.IHW : 0;
-        const uint32_t sz = ok ? 4u : 0u;
+        const uint32_t cs = ok ? (uint32_t)p.IHW : 0u, ign = ok ? 0u : 1u;
 #pragma unroll
-        for (int c = 0; c < 16; ++c) cp_async4(dst + c * 512, src + c * cs, sz);
+        for (int c = 0; c < 16; ++c) cp_async4(dst + c * 512, src + (uint32_t)c * cs, ign);
       } else {
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           const int2 e = ktab[cb * 32 + hsel * 16 + c];
           const int ih = ih0 + (e.y >> 16), iw = iw0 + (e.y & 0xffff);
           const bool ok = pvalid && e.y >= 0 && (unsigned)ih < (unsigned)p.IH && (unsigned)iw < (unsigned)p.IW;
-          cp_async4(dst + c * 512, ok ? xn + ih0 * p.IW + iw0 + e.x : xn, ok ? 4u : 0u);
+          cp_async4(dst + c * 512, ok ? xn + ih0 * p.IW + iw0 + e.x : xn, ok ? 0u : 1u);
         }
       }
       if (++kw == kw_n) {
@@ -374,14 +392,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
     int slot_in = 0;
 #pragma unroll 1
     for (int j = 0; j < kARing - 1; ++j) {
-      if (j < total && !(p.debug & 1)) issue(slot_in);
+      if (j < total && !(DBG && p.debug & 1)) issue(slot_in);
       cp_async_commit();
       if (++slot_in == kARing) slot_in = 0;
     }
     int slot_out = 0;
 #pragma unroll 1
     for (int i = 0; i < total; ++i) {
-      if (i + kARing - 1 < total && !(p.debug & 1)) issue(slot_in);
+      if (i + kARing - 1 < total && !(DBG && p.debug & 1)) issue(slot_in);
       cp_async_commit();
       if (++slot_in == kARing) slot_in = 0;
       cp_async_wait<kARing - 1>();  // this thread's copies of box i have landed
@@ -391,20 +409,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
         asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v[c]) : "r"(ring + (uint32_t)slot_out * 16384u + c * 512u) : "memory");
       if (++slot_out == kARing) slot_out = 0;
       const uint32_t s = (uint32_t)i & (kConvStages - 1), ph = ((uint32_t)i / kConvStages) & 1u;
-      const bool tr = p.trace && cta == 0 && warp == 2 && lane == 0 && i < 512;
+      const bool tr = DBG && p.trace && cta == 0 && warp == 2 && lane == 0 && i < 512;
       a32_wait_wd(bar_empty + 8 * s, ph ^ 1u);
       tc_fence_after();
-      // hi = rna_tf32(x), lo = rna_tf32(x - hi) with integer rounding (add half an ulp, clear the 13 low bits)
+      // hi = rna_tf32(x), lo = rna_tf32(x - hi) with integer rounding: add half a tf32 ulp, clear the 13 low bits
+      // (for lo the tensor core's own truncation of the operand does the clearing, as in gram_tma.cu)
       uint32_t hi[16];
 #pragma unroll
       for (int c = 0; c < 16; ++c) hi[c] = (v[c] + 0x1000u) & 0xffffe000u;
       tmem_st16(a_base + s * 64, hi);
 #pragma unroll
       for (int c = 0; c < 16; ++c)
-        hi[c] = (__float_as_uint(__uint_as_float(v[c]) - __uint_as_float(hi[c])) + 0x1000u) & 0xffffe000u;
+        hi[c] = __float_as_uint(__uint_as_float(v[c]) - __uint_as_float(hi[c])) + 0x1000u;  // the core drops the low bits
       tmem_st16(a_base + s * 64 + 32, hi);
       tmem_st_wait();
-      if (tr) p.trace[i * 8 + 3] = clock64();
+      if (tr) p.trace[i * 16 + 3] = clock64();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) a32_arrive(bar_full + 8 * s);
@@ -417,14 +436,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
     uint32_t chain = 0;
     for (int item = cta; item < p.total_items; item += nctas) {
       const ConvItem it = conv_item(p, item);
-      float acc[COLS];
+      // promotion accumulators as fp32 pairs: one add.rn.f32x2 per two columns halves the issue slots this role
+      // takes from the MMA-issuing warp's scheduler
+      unsigned long long acc2[COLS / 2];
 #pragma unroll
-      for (int c = 0; c < COLS; ++c) acc[c] = 0.f;
-      for (int b0 = 0; b0 < p.nbox; b0 += p.chain_boxes, ++chain) {
+      for (int c = 0; c < COLS / 2; ++c) acc2[c] = 0ull;
+      for (int b0 = 0; b0 < p.nbox; b0 += CH, ++chain) {
         const uint32_t buf = chain & 1u;
         a32_wait_wd(bar_acc_full + 8 * buf, (chain >> 1) & 1u);
-        const bool tr = p.trace && cta == 0 && warp == 10 && lane == 0 && chain < 512;
-        if (tr) p.trace[chain * 8 + 5] = clock64();
+        const bool tr = DBG && p.trace && cta == 0 && warp == 10 && lane == 0 && chain < 512;
+        if (tr) p.trace[chain * 16 + 5] = clock64();
         tc_fence_after();
         const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + buf * TN + half * COLS;
 #pragma unroll
@@ -433,15 +454,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
           tmem_ld16(t0 + c * 16, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 16; ++e) acc[c * 16 + e] += __uint_as_float(v[e]);
+          for (int e = 0; e < 8; ++e) {
+            unsigned long long pr;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(pr) : "r"(v[2 * e]), "r"(v[2 * e + 1]));
+            asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc2[c * 8 + e]) : "l"(pr));
+          }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) a32_arrive(bar_acc_empty + 8 * buf);
-        if (tr) p.trace[chain * 8 + 7] = clock64();
+        if (tr) p.trace[chain * 16 + 7] = clock64();
+      }
+      float acc[COLS];
+#pragma unroll
+      for (int c = 0; c < COLS / 2; ++c) {
+        uint32_t lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(acc2[c]));
+        acc[2 * c] = __uint_as_float(lo);
+        acc[2 * c + 1] = __uint_as_float(hi);
       }
       const int pos = it.mt * 128 + q * 32 + lane;
-      if (pos < p.P && !(p.debug & 4)) {
+      if (pos < p.P && !(DBG && p.debug & 4)) {
         const int n = pos / p.OHW, r = pos - n * p.OHW;
         const int co0 = it.nt * TN + half * COLS;
         float *o = p.out[it.prob] + ((int64_t)n * p.Cout + co0) * p.OHW + r;
@@ -514,12 +547,13 @@ static int make_weight_map(CUtensorMap *m, const float *packed, int64_t Cout, co
   return PLB_OK;
 }
 
-template <int TN>
+template <int TN, int CH, bool DBG>
 static int launch_conv(const CUtensorMap &m0, const CUtensorMap &m1, const ConvParams &p, cudaStream_t stream) {
   constexpr int smem_bytes = ConvCfg<TN>::kSmemBytes;
-  if (int rc = ensure_dynamic_smem((const void *)conv3xtf32_kernel<TN>, smem_bytes, "conv3xtf32_kernel")) return rc;
+  if (int rc = ensure_dynamic_smem((const void *)conv3xtf32_kernel<TN, CH, DBG>, smem_bytes, "conv3xtf32_kernel"))
+    return rc;
   const int grid = min(p.total_items, device_sm_count());
-  conv3xtf32_kernel<TN><<<grid, kConvThreads, smem_bytes, stream>>>(m0, m1, p);
+  conv3xtf32_kernel<TN, CH, DBG><<<grid, kConvThreads, smem_bytes, stream>>>(m0, m1, p);
   return launch_status("conv3xtf32_kernel");
 }
 
@@ -602,7 +636,7 @@ extern "C" int plb_conv2d_forward(const float *const *x, const float *const *pac
   static int chain = 0;
   if (chain == 0) {
     const char *c = getenv("PLB_CONV_CHAIN");  // experiments: boxes per accumulation chain
-    chain = (c && atoi(c) > 0) ? atoi(c) : 1;
+    chain = (c && atoi(c) > 0 && atoi(c) <= kConvStages / 2) ? atoi(c) : 2;
   }
   p.chain_boxes = chain;
   const int tn = Cout <= 64 ? 64 : 128;
@@ -615,6 +649,10 @@ extern "C" int plb_conv2d_forward(const float *const *x, const float *const *pac
   if (int rc = make_weight_map(&m0, packed_w[0], Cout, g, tn)) return rc;
   if (int rc = make_weight_map(&m1, packed_w[nprob - 1], Cout, g, tn)) return rc;
   cudaStream_t s = (cudaStream_t)stream;
-  if (tn == 64) return launch_conv<64>(m0, m1, p, s);
-  return launch_conv<128>(m0, m1, p, s);
+  const bool dbg = p.debug != 0 || p.trace != nullptr;
+  if (dbg || chain != 2) {  // experiments: runtime switches compiled in
+    if (chain == 1) return tn == 64 ? launch_conv<64, 1, true>(m0, m1, p, s) : launch_conv<128, 1, true>(m0, m1, p, s);
+    return tn == 64 ? launch_conv<64, 2, true>(m0, m1, p, s) : launch_conv<128, 2, true>(m0, m1, p, s);
+  }
+  return tn == 64 ? launch_conv<64, 2, false>(m0, m1, p, s) : launch_conv<128, 2, false>(m0, m1, p, s);
 }

@@ -13,20 +13,21 @@ with torch.no_grad():
     pair = conv.ConvPair(ma, mb)
     pair(xa, xb)
     torch.cuda.synchronize()
-    buf = torch.zeros(4096, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(8192, dtype=torch.int64, device="cuda")
     N.lib().plb_conv_debug_set_trace(buf.data_ptr())
     pair(xa, xb)
     torch.cuda.synchronize()
     N.lib().plb_conv_debug_set_trace(None)
-t = buf.view(512, 8).cpu()
+t = buf.view(512, 16).cpu()
 n = int((t[:, 6] > 0).sum())
 t0 = int(t[0, 0])
 print(f"shape {SHAPES[idx]}: {n} boxes traced; clocks relative to the first TMA issue")
-print(" box | tma_issue | mma_top mma_acc_ok loader_stored | mma_sees issued | epi_sees epi_done (chain = box when PLB_CONV_CHAIN=1) | d_issued")
-prev = None
-rows = list(range(min(n, 20))) + list(range(max(20, n - 12), n))
+print(" box | top acc_ok full(sees) fenced peeked mmas_out commits_out synced | epi_sees epi_done | next_ready next_acc")
+rows = list(range(min(n, 12))) + list(range(max(12, n - 24), n))
 for i in rows:
-    flags = (0, 0)
-    v = [int(x) - t0 for x in t[i]]
-    print(f"{i:4d} | {v[0]:8d} | {v[1]:8d} {v[2]:8d} {v[3]:8d} | {v[4]:8d} {v[6]:8d} | {v[5]:8d} {v[7]:8d} | {'' if prev is None else v[6]-prev} acc_ok={flags[0]} ready={flags[1]}")
-    prev = v[6]
+    r = [int(x) for x in t[i]]
+    nr, na = r[11] & 1, r[13] & 1
+    r[11] //= 2
+    r[13] //= 2
+    v = [x - t0 for x in r]
+    print(f"{i:4d} | {v[8]:7d} {v[9]:7d} {v[4]:7d} {v[10]:7d} {v[11]:7d} {v[12]:7d} {v[13]:7d} {v[6]:7d} | {v[5]:7d} {v[7]:7d} | {nr} {na}")

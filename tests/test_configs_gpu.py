@@ -54,11 +54,11 @@ def _sample_index(n):  # oracle/make_golden_configs.py::sample_index
 
 
 # Largest relative deviation of a group's optimal objective from the reference's.  The forwards of the source
-# models run on the library's 3xTF32 tensor-core convolution (csrc/conv.cu): per layer it is as close to the fp64
-# convolution as cuDNN's fp32 kernels are (3e-6, tests/test_conv_gpu.py), but its residual is not independent
-# from layer to layer (the tensor core truncates when it accumulates), so the deepest groups of a 50-layer
-# network sit at ~1e-5 instead of the ~4e-6 of the cuDNN forwards; BASELINE.json's bar for the statistics is 1e-4.
-OBJ_TOL = 3e-5
+# models run on the library's 3xTF32 tensor-core convolution (csrc/conv.cu).  The tensor core truncates when it
+# accumulates, a bias that compounds from layer to layer, so the kernel promotes two-box (64 k) chains and issues
+# their small products first; measured worst deviation on the ResNet-50 pair: 4.2e-6 (one-box chains 3.2e-6,
+# eight-box chains in k order 1.3e-5; cuDNN fp32 forwards ~4e-6).
+OBJ_TOL = 1e-5
 
 
 def _check_fingerprint(cost, fp, name, tol=1e-5):
