@@ -272,8 +272,10 @@ int plb_wm_progress(const float *A, int64_t ld, const int64_t *P, int32_t n, int
  *
  * plb_conv_pack_weights splits w into tf32 hi / lo planes in the order the kernel's tensor map
  * reads: planes[2][taps][Cout][Kc].  Cin % 32 == 0: taps = KH*KW, Kc = Cin, plane[t][co][ci].
- * Otherwise ("flat" form, e.g. the 3-channel stem): taps = 1, Kc = ceil32(Cin*KH*KW),
- * plane[0][co][ci*KH*KW + kh*KW + kw], zero padded.  plb_conv_packed_floats returns the number of
+ * Otherwise ("flat" form, e.g. the 3-channel stem): taps = 1, KWP = KW rounded up to a power of two,
+ * Kc = ceil32(Cin*KH*KWP), plane[0][co][(ci*KH + kh)*KWP + kw], zero for kw >= KW and beyond Cin*KH rows: a
+ * kernel row's taps are consecutive k, so the kernel's gather resolves (ci, kh) once per row.  Needs
+ * Kc <= 512.  plb_conv_packed_floats returns the number of
  * floats of the whole packed buffer (host-only helper).  Weights are constants of the source
  * models: pack once, reuse for every batch. */
 /* experiments only: per-box clock64 stamps of CTA 0 of later plb_conv2d_forward launches (NULL switches it off) */

@@ -32,9 +32,10 @@ def eligible(mod) -> bool:
     if w.dtype != torch.float32 or not w.is_cuda:
         return False
     cin, kh, kw = w.shape[1], w.shape[2], w.shape[3]
-    if cin % 32 != 0 and -(-cin * kh * kw // 32) * 32 > MAX_FLAT_K:
+    kwp = 1 << max(kw - 1, 0).bit_length()  # flat form: kernel rows padded to a power of two of taps
+    if cin % 32 != 0 and -(-cin * kh * kwp // 32) * 32 > MAX_FLAT_K:
         return False
-    return kh < 256 and kw < 256
+    return kh < 256 and kw < 256 and (cin % 32 == 0 or kw <= 16)
 
 
 class PackedConv:

@@ -37,7 +37,7 @@ namespace plb {
 
 constexpr int kConvStages = 4;
 constexpr int kConvThreads = 576;
-constexpr int kConvMaxFlatK = 512;  // flat form: Cin*KH*KW (padded to 32) must fit the shared-memory k table
+constexpr int kConvMaxFlatK = 512;  // flat form: K = Cin*KH*pow2(KW) padded to 32; bounds the kernel-row table (KW <= 16)
 
 struct ConvParams {
   const float *x[2];
@@ -49,8 +49,9 @@ struct ConvParams {
   int m_tiles, n_tiles, total_items;
   int taps;         // KH*KW (channel-block form) or 1 (flat form)
   int nbox;         // K boxes of 32 per item
-  int flat;         // 1: k = ci*KH*KW + kh*KW + kw (any Cin), 0: k = 32-channel block x tap
-  int flat_k;       // Cin*KH*KW (flat form)
+  int flat;         // 1: k = (ci*KH + kh) * KWP + kw (any Cin; KWP = KW rounded up to a power of two), 0: k = 32-channel block x tap
+  int flat_groups;  // Cin*KH kernel rows (flat form)
+  int flat_lg;      // log2(KWP)
   int chain_boxes;  // boxes chained into one TMEM accumulator before promotion
   unsigned long long *trace;  // experiments only (plb_conv_debug_set_trace): 8 clock64 stamps per box of CTA 0
   int debug;        // experiments only (PLB_CONV_DEBUG, WRONG results): 1 no gather, 2 one MMA of three, 4 no stores
@@ -170,6 +171,24 @@ __device__ __forceinline__ void a32_tma_load_4d(uint32_t smem_dst, const CUtenso
       : "memory");
 }
 
+// flat-form gather of one loader thread: 16 >> LG kernel rows of (1 << LG) taps (see conv3xtf32_kernel)
+template <int LG>
+__device__ __forceinline__ void flat_rows(const int2 *rows, const float *origin, const float *safe, uint32_t dst,
+                                          bool pvalid, int ih0, int iw0, int IH, int IW, int KW) {
+  constexpr int TAPS = 1 << LG, ROWS = 16 >> LG;
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int2 e = rows[r];
+    const bool rowok = pvalid && e.y >= 0 && (unsigned)(ih0 + e.y) < (unsigned)IH;
+    const float *base = rowok ? origin + e.x : safe;
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t) {
+      const bool ok = rowok && t < KW && (unsigned)(iw0 + t) < (unsigned)IW;
+      cp_async4(dst + (r * TAPS + t) * 512, base + (ok ? t : 0), ok ? 0u : 1u);
+    }
+  }
+}
+
 struct ConvItem {
   int prob, mt, nt;
 };
@@ -196,7 +215,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
   // and loaders;  [8,10) accumulator full: MMA -> promotion warps;  [10,12) accumulator empty: promotion -> MMA
   __shared__ uint64_t bars[2 * kConvStages + 4];
   __shared__ uint32_t tmem_base_s;
-  __shared__ int2 ktab[kConvMaxFlatK];           // flat form: k -> (ci*IHW + kh*IW + kw, kh << 16 | kw)
+  __shared__ int2 ktab[kConvMaxFlatK];           // flat form: kernel row g = ci*KH + kh -> (ci*IHW + kh*IW, kh) or (0, -1)
 
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,18 +239,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
     tmem_relinquish();
   }
   if (p.flat) {
-    const int kk_total = p.nbox * 32, taps = p.KH * p.KW;
-    for (int k = (int)threadIdx.x; k < kk_total; k += kConvThreads) {
+    const int rows = (p.nbox * 32) >> p.flat_lg;  // kernel rows incl. the zero rows that pad K to a box multiple
+    for (int g = (int)threadIdx.x; g < rows; g += kConvThreads) {
       int2 e;
-      if (k < p.flat_k) {
-        const int ci = k / taps, t = k - ci * taps, kh = t / p.KW, kw = t - kh * p.KW;
-        e.x = ci * p.IHW + kh * p.IW + kw;
-        e.y = (kh << 16) | kw;
+      if (g < p.flat_groups) {
+        const int ci = g / p.KH, kh = g - ci * p.KH;
+        e.x = ci * p.IHW + kh * p.IW;
+        e.y = kh;
       } else {
         e.x = 0;
-        e.y = -1;  // padding k: always reads as zero
+        e.y = -1;  // padding rows always read as zero
       }
-      ktab[k] = e;
+      ktab[g] = e;
     }
   }
   tc_fence_before();
@@ -368,12 +387,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
 #pragma unroll
         for (int c = 0; c < 16; ++c) cp_async4(dst + c * 512, src + (uint32_t)c * cs, ign);
       } else {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const int2 e = ktab[cb * 32 + hsel * 16 + c];
-          const int ih = ih0 + (e.y >> 16), iw = iw0 + (e.y & 0xffff);
-          const bool ok = pvalid && e.y >= 0 && (unsigned)ih < (unsigned)p.IH && (unsigned)iw < (unsigned)p.IW;
-          cp_async4(dst + c * 512, ok ? xn + ih0 * p.IW + iw0 + e.x : xn, ok ? 0u : 1u);
+        // flat form: this thread's 16 k are 16 >> lg kernel rows of KWP = 1 << lg taps each; a row's (channel, kh)
+        // comes from the table once, its taps are consecutive addresses
+        const int row0 = (cb * 32 + hsel * 16) >> p.flat_lg;
+        const float *origin = xn + ih0 * p.IW + iw0;
+        switch (p.flat_lg) {
+          case 0: flat_rows<0>(ktab + row0, origin, xn, dst, pvalid, ih0, iw0, p.IH, p.IW, p.KW); break;
+          case 1: flat_rows<1>(ktab + row0, origin, xn, dst, pvalid, ih0, iw0, p.IH, p.IW, p.KW); break;
+          case 2: flat_rows<2>(ktab + row0, origin, xn, dst, pvalid, ih0, iw0, p.IH, p.IW, p.KW); break;
+          case 3: flat_rows<3>(ktab + row0, origin, xn, dst, pvalid, ih0, iw0, p.IH, p.IW, p.KW); break;
+          default: flat_rows<4>(ktab + row0, origin, xn, dst, pvalid, ih0, iw0, p.IH, p.IW, p.KW); break;
         }
       }
       if (++kw == kw_n) {
@@ -502,7 +525,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
 
 // w[Cout][Cin][KH][KW] -> hi / lo planes [2][taps][Cout][Kc] (include/pleas_b200.h)
 __global__ void conv_pack_weights_kernel(const float *__restrict__ w, float *__restrict__ packed, int Cout, int Cin,
-                                         int KH, int KW, int taps, int Kc, int flat) {
+                                         int KH, int KW, int taps, int Kc, int flat, int flat_lg) {
   const int64_t plane = (int64_t)taps * Cout * Kc;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < plane; idx += (int64_t)gridDim.x * blockDim.x) {
     const int k = (int)(idx % Kc);
@@ -511,8 +534,9 @@ __global__ void conv_pack_weights_kernel(const float *__restrict__ w, float *__r
     float v = 0.f;
     if (!flat) {
       v = w[((int64_t)co * Cin + k) * (KH * KW) + t];
-    } else if (k < Cin * KH * KW) {
-      v = w[(int64_t)co * Cin * KH * KW + k];
+    } else {
+      const int g = k >> flat_lg, kw = k & ((1 << flat_lg) - 1);  // kernel row (ci, kh) and tap inside it
+      if (g < Cin * KH && kw < KW) v = w[((int64_t)co * Cin * KH + g) * KW + kw];
     }
     const float hi = to_tf32(v);
     packed[idx] = hi;
@@ -523,13 +547,15 @@ __global__ void conv_pack_weights_kernel(const float *__restrict__ w, float *__r
 static unsigned long long *g_conv_trace = nullptr;
 
 struct ConvGeometry {
-  int flat, taps, Kc;
+  int flat, taps, Kc, flat_lg;
 };
 static ConvGeometry conv_geometry(int64_t Cin, int KH, int KW) {
   ConvGeometry g;
   g.flat = (Cin % 32) != 0;
   g.taps = g.flat ? 1 : KH * KW;
-  g.Kc = g.flat ? (int)(ceil_div(Cin * KH * KW, 32) * 32) : (int)Cin;
+  g.flat_lg = 0;
+  while ((1 << g.flat_lg) < KW) ++g.flat_lg;  // kernel rows padded to a power of two of taps (zero weights)
+  g.Kc = g.flat ? (int)(ceil_div((Cin * KH) << g.flat_lg, 32) * 32) : (int)Cin;
   return g;
 }
 
@@ -578,14 +604,15 @@ extern "C" int plb_conv_pack_weights(const float *w, int64_t Cout, int64_t Cin, 
   PLB_REQUIRE(w && packed, PLB_EINVAL, "plb_conv_pack_weights: null pointer");
   PLB_REQUIRE(Cout > 0 && Cin > 0 && KH > 0 && KW > 0, PLB_EINVAL, "plb_conv_pack_weights: empty weight");
   const ConvGeometry g = conv_geometry(Cin, KH, KW);
+  PLB_REQUIRE(!g.flat || KW <= 16, PLB_ESIZE, "plb_conv_pack_weights: Cin %% 32 != 0 needs KW <= 16");
   PLB_REQUIRE(!g.flat || g.Kc <= kConvMaxFlatK, PLB_ESIZE,
-              "plb_conv_pack_weights: Cin %% 32 != 0 needs Cin*KH*KW <= %d", kConvMaxFlatK);
+              "plb_conv_pack_weights: Cin %% 32 != 0 needs Cin*KH*pow2(KW) <= %d", kConvMaxFlatK);
   const int64_t plane = (int64_t)g.taps * Cout * g.Kc;
   PLB_REQUIRE(plane < (1ll << 31), PLB_ESIZE, "plb_conv_pack_weights: weight too large");
   const int64_t want = ceil_div(plane, 256);
   const int blocks = (int)(want < 148 * 8 ? want : 148 * 8);
   conv_pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, packed, (int)Cout, (int)Cin, KH, KW, g.taps,
-                                                                     g.Kc, g.flat);
+                                                                     g.Kc, g.flat, g.flat_lg);
   return launch_status("conv_pack_weights_kernel");
 }
 
@@ -605,8 +632,9 @@ extern "C" int plb_conv2d_forward(const float *const *x, const float *const *pac
                   KH < 256 && KW < 256,
               PLB_ESIZE, "plb_conv2d_forward: extent too large");
   const ConvGeometry g = conv_geometry(Cin, KH, KW);
+  PLB_REQUIRE(!g.flat || KW <= 16, PLB_ESIZE, "plb_conv2d_forward: Cin %% 32 != 0 needs KW <= 16");
   PLB_REQUIRE(!g.flat || g.Kc <= kConvMaxFlatK, PLB_ESIZE,
-              "plb_conv2d_forward: Cin %% 32 != 0 needs Cin*KH*KW <= %d", kConvMaxFlatK);
+              "plb_conv2d_forward: Cin %% 32 != 0 needs Cin*KH*pow2(KW) <= %d", kConvMaxFlatK);
   ConvParams p = {};
   for (int i = 0; i < nprob; ++i) {
     PLB_REQUIRE(x[i] && packed_w[i] && out[i], PLB_EINVAL, "plb_conv2d_forward: null pointer");
@@ -619,7 +647,7 @@ extern "C" int plb_conv2d_forward(const float *const *x, const float *const *pac
   p.NB = (int)NB, p.Cin = (int)Cin, p.IH = (int)IH, p.IW = (int)IW, p.Cout = (int)Cout, p.OH = (int)OH, p.OW = (int)OW;
   p.KH = KH, p.KW = KW, p.stride = stride, p.pad_h = pad_h, p.pad_w = pad_w;
   p.P = (int)(NB * OH * OW), p.OHW = (int)(OH * OW), p.IHW = (int)(IH * IW);
-  p.flat = g.flat, p.taps = g.taps, p.flat_k = (int)(Cin * KH * KW);
+  p.flat = g.flat, p.taps = g.taps, p.flat_groups = (int)(Cin * KH), p.flat_lg = g.flat_lg;
   p.nbox = g.taps * (g.Kc / 32);
   static int debug = -1;
   if (debug < 0) {

@@ -173,7 +173,12 @@ __global__ void __launch_bounds__(384, 1) gram_tma_kernel(const __grid_constant_
     if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(Cfg::kMmaM, Cfg::kMmaN);
       const uint32_t smem_base = smem_u32(smem);
+      // Every clock between the last MMA of a box and the first of the next is an idle tensor core, and a barrier
+      // probe costs 100-250 clocks on an SM whose issue slots are contended by the converter / promotion warps
+      // (conv.cu, profiles/r02_notes.md): the NEXT box's barrier (and the next chain's accumulator) is probed with a
+      // non-blocking test_wait BEFORE this box's MMAs are issued, so its latency hides behind them.
       uint32_t s = 0, ph = 0, chain = 0;
+      bool ready = false, acc_ok = false;
       for (int item = cluster_id; item < p.total_items; item += n_clusters) {
         const int split = item / tiles;
         const int box0 = (int)((int64_t)p.total_boxes * split / p.splits);
@@ -181,14 +186,20 @@ __global__ void __launch_bounds__(384, 1) gram_tma_kernel(const __grid_constant_
         int kb = box0 % p.boxes_per_image;
         for (int b0 = 0; b0 < nbox; b0 += p.chain_boxes, ++chain) {
           const uint32_t buf = chain & 1u;
-          mbar_wait_wd(&bar_acc_empty[buf], ((chain >> 1) & 1u) ^ 1u);  // both CTAs drained this buffer
+          if (!acc_ok) mbar_wait_wd(&bar_acc_empty[buf], ((chain >> 1) & 1u) ^ 1u);  // both CTAs drained this buffer
+          acc_ok = false;
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * Cfg::kMmaN;
           const int b1 = min(nbox, b0 + p.chain_boxes);
           for (int b = b0; b < b1; ++b) {
-            mbar_wait_wd(&bar_conv[s], ph);
+            if (!ready) mbar_wait_wd(&bar_conv[s], ph);
             tc_fence_after();
             if (p.trace && blockIdx.x == 0 && lane == 0 && b < 256) p.trace[b * 4 + 3] = clock64();
+            const uint32_t s1 = (s + 1 == Cfg::kStages) ? 0u : s + 1, ph1 = (s + 1 == Cfg::kStages) ? ph ^ 1u : ph;
+            const bool next_ready = mbar_test_wait(&bar_conv[s1], ph1);
+            bool next_acc = false;
+            if (b == b1 - 1)
+              next_acc = mbar_test_wait(&bar_acc_empty[(chain + 1) & 1u], (((chain + 1) >> 1) & 1u) ^ 1u);
             const int valid = min(kBoxK, p.inner - kb * kBoxK);  // k beyond the image's extent is TMA zero fill
             const int nk8 = (valid + 7) >> 3;
             if (elect_one()) {
@@ -212,7 +223,8 @@ __global__ void __launch_bounds__(384, 1) gram_tma_kernel(const __grid_constant_
               umma_commit_cg<CG>(&bar_empty[s]);
               if (b == b1 - 1) umma_commit_cg<CG>(&bar_acc_full[buf]);
             }
-            __syncwarp();
+            ready = __all_sync(0xffffffffu, next_ready);
+            if (b == b1 - 1) acc_ok = __all_sync(0xffffffffu, next_acc);
             if (++kb == p.boxes_per_image) kb = 0;
             if (++s == Cfg::kStages) {
               s = 0;

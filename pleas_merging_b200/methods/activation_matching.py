@@ -155,11 +155,24 @@ def _conv_pair_for(node, model1, model2):
     return pair if pair.same_geometry() else None
 
 
+def _release_conv_pairs(ids):
+    for pid in ids:
+        _CONV_PAIRS.pop(pid, None)
+
+
 def build_cross_module(model1: Module, model2: Module, axes: Collection, cross_features):
     """GraphModule returning ``([out1, out2], {(node_name, axis): cross_features(a, b, axis)})``
-    (reference :49-100)."""
-    return _dual_graph(model1, model2, axes,
-                       lambda g, name, a, na, nb: g.call_function(cross_features, (na, nb, a)))
+    (reference :49-100).  On CUDA models the eligible convolutions run pairwise on the library kernel, exactly
+    as in the fused loop, so both paths see the same activations."""
+    import weakref
+
+    on_gpu = all(p.is_cuda for p in itertools.chain(model1.parameters(), model2.parameters()))
+    pairs = [] if (conv.ENABLED and on_gpu) else None
+    gm = _dual_graph(model1, model2, axes,
+                     lambda g, name, a, na, nb: g.call_function(cross_features, (na, nb, a)), conv_pairs=pairs)
+    if pairs:
+        weakref.finalize(gm, _release_conv_pairs, pairs)
+    return gm
 
 
 # ------------------------------------------------------------------ fused accumulation

@@ -461,6 +461,49 @@ def test_built_library_is_sm100a_native_sass():
     assert pair and all("UTCHMMA.2CTA" in b and "UTCBAR.2CTA.MULTICAST" in b for b in pair)
 
 
+def test_conv_kernel_sass_and_packed_geometry():
+    """The convolution kernel (csrc/conv.cu) is what its header says: tensor-map TMA for the weights (UTMALDG),
+    4-byte cp.async gathers (zero padding = ignore-src copies) for the activations (LDGSTS), the A operand written to tensor
+    memory (STTM) and MMAs that take it from there (UTCHMMA with a tmem A operand), packed f32x2 promotion adds in
+    the production instantiation; and the packed-weight size helper (host-only) follows include/pleas_b200.h."""
+    import ctypes
+    import shutil
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    from pleas_merging_b200 import _native, build
+
+    lib = build.build()
+    sass = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True, timeout=300).stdout
+    bodies, name = {}, None
+    for line in sass.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+            bodies[name] = []
+        elif name is not None:
+            bodies[name].append(line)
+    conv = {n: "\n".join(b) for n, b in bodies.items() if "conv3xtf32_kernel" in n}
+    assert len(conv) >= 4  # TN 64 / 128 x production / experiments builds
+    for n, b in conv.items():
+        assert "UTMALDG" in b and "STTM" in b and "LDTM" in b and "LDGSTS" in b, n
+        mma = [l for l in b.splitlines() if "UTCHMMA" in l]
+        assert len(mma) >= 12 and all(l.split("UTCHMMA")[1].strip().startswith("tmem[") for l in mma), n
+        assert "MEMBAR.ALL.GPU" not in b, n
+    assert any("FADD2" in b for b in conv.values())
+    h = _native.lib()
+    # channel-block form: [2][KH*KW][Cout][Cin]
+    assert h.plb_conv_packed_floats(256, 128, 3, 3) == 2 * 9 * 256 * 128
+    # flat form (Cin % 32 != 0): kernel rows padded to 8 taps, K = 3*7*8 = 168 -> 192
+    assert h.plb_conv_packed_floats(64, 3, 7, 7) == 2 * 64 * 192
+    assert h.plb_conv_packed_floats(0, 3, 7, 7) == 0
+    import torch
+    from pleas_merging_b200 import conv as C
+
+    assert not C.eligible(torch.nn.Conv2d(64, 64, 3))            # CPU weights: the module keeps its own forward
+    assert not C.eligible(torch.nn.Conv2d(64, 64, 3, groups=2))
+
+
 def test_parallel_helpers_single_process_edges():
     """No process group: the collectives are no-ops, every item belongs to rank 0, and a sharder
     over an empty / short loader yields what exists."""
