@@ -181,7 +181,11 @@ typedef struct PlbFinalizeTap {
   const double *qa, *qb;       /* row sums of squares */
   const double *sa, *sb;       /* row sums */
   int64_t ld_m, ld_n, K;
-  int32_t splits, reserved;
+  int32_t splits;
+  int32_t n_affine;            /* derived taps: the statistic of (s_a x + t_a, s_b y + t_b) per unit, e.g. the
+                                  output of an eval-mode BatchNorm behind this tap, formed from the SAME Gram, row
+                                  sums and sums of squares (needs sa / sb) — no second contraction */
+  const double *affine;        /* n_affine x [s_a (n) | t_a (n) | s_b (n) | t_b (n)], n = the group's size */
 } PlbFinalizeTap;
 typedef struct PlbFinalizeGroup {
   float *cost;                 /* [n][ldc] fp32 */

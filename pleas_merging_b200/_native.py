@@ -25,7 +25,8 @@ class GemmProblem(ctypes.Structure):
 class FinalizeTap(ctypes.Structure):
     """Mirror of PlbFinalizeTap (include/pleas_b200.h)."""
     _fields_ = [("partial", c_ptr), ("qa", c_ptr), ("qb", c_ptr), ("sa", c_ptr), ("sb", c_ptr),
-                ("ld_m", c_i64), ("ld_n", c_i64), ("K", c_i64), ("splits", c_i32), ("reserved", c_i32)]
+                ("ld_m", c_i64), ("ld_n", c_i64), ("K", c_i64), ("splits", c_i32), ("n_affine", c_i32),
+                ("affine", c_ptr)]
 
 
 class FinalizeGroup(ctypes.Structure):

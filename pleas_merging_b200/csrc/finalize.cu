@@ -273,6 +273,29 @@ __global__ void __launch_bounds__(256) cross_finalize_grouped_kernel(const PlbFi
           v = (float)gs[r][c];
         }
         total[r][c] += v;
+        // derived taps: the same statistic of the per-unit affine images s_a x_i + t_a, s_b y_j + t_b (an eval-mode
+        // BatchNorm behind this tap) from the Gram entry, the row sums S and the sums of squares q, in fp64:
+        //   <x', y'>  = s_a s_b G + s_a t_b S_a + t_a s_b S_b + K t_a t_b
+        //   |x'-y'|^2 = s_a^2 q_a + s_b^2 q_b - 2 s_a s_b G + K (t_a - t_b)^2 + 2 (t_a - t_b)(s_a S_a - s_b S_b)
+        //   corr(x', y') = sign(s_a s_b) corr(x, y)
+        for (int a = 0; a < tp.n_affine; ++a) {
+          const double *av = tp.affine + (int64_t)a * 4 * g.n;
+          const double s_a = av[i], t_a = av[g.n + i], s_b = av[2 * g.n + j + c], t_b = av[3 * (int64_t)g.n + j + c];
+          float w;
+          if (mode == PLB_MODE_NEG_CDIST) {
+            const double dt = t_a - t_b;
+            const double d2 = s_a * s_a * tp.qa[i] + s_b * s_b * tp.qb[j + c] - 2.0 * s_a * s_b * gs[r][c] +
+                              (double)tp.K * dt * dt + 2.0 * dt * (s_a * tp.sa[i] - s_b * tp.sb[j + c]);
+            w = -sqrtf(fmaxf((float)d2, 0.f));
+          } else if (mode == PLB_MODE_CORR) {
+            const double sg = s_a * s_b;
+            w = sg > 0.0 ? v : (sg < 0.0 ? -v : 0.f);
+          } else {
+            w = (float)(s_a * s_b * gs[r][c] + s_a * t_b * tp.sa[i] + t_a * s_b * tp.sb[j + c] +
+                        (double)tp.K * t_a * t_b);
+          }
+          total[r][c] += w;
+        }
       }
     }
   }

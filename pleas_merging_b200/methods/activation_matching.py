@@ -90,7 +90,8 @@ def _conv_pair_dispatch(pair_id: int, xa, xb):
     return _CONV_PAIRS[pair_id](xa, xb)
 
 
-def _dual_graph(model1: Module, model2: Module, axes: Collection, emit, emit_sync=None, conv_pairs=None):
+def _dual_graph(model1: Module, model2: Module, axes: Collection, emit, emit_sync=None, conv_pairs=None,
+                emit_affine=None):
     """Runs both models side by side in one fx graph (model2 must trace to model1's graph, as
     in the reference, :68).  After every tapped node ``emit(graph, name, axis, node_a, node_b)``
     inserts the tap consumer right behind its producers — torchvision's in-place ReLU
@@ -98,7 +99,8 @@ def _dual_graph(model1: Module, model2: Module, axes: Collection, emit, emit_syn
     (optional) is inserted before every node that may mutate an input: a consumer that reads taps
     asynchronously gets the chance to finish first.  ``conv_pairs`` (a list, optional): eligible Conv2d layers are
     not called as modules but pairwise through ``_conv_pair_dispatch``; the ids registered in ``_CONV_PAIRS`` are
-    appended to the list for the caller to release."""
+    appended to the list for the caller to release.  ``emit_affine(node, axis, model1, model2)`` (optional) may claim a
+    tap as a per-unit affine image of an earlier tap (returns True): no consumer is inserted for it."""
     traced = torch.fx.symbolic_trace(model1)
     taps = _tap_axes(axes)
     g = torch.fx.Graph()
@@ -133,6 +135,9 @@ def _dual_graph(model1: Module, model2: Module, axes: Collection, emit, emit_syn
                 new.target = f"{side}.{node.target}"
             env[side][node] = new
         for a in taps.get(node.name, ()):
+            if emit_affine is not None and emit_affine(node, a, model1, model2):
+                emitted[node.name, a] = None
+                continue
             emitted[node.name, a] = emit(g, node.name, a, env[0][node], env[1][node])
     g.output(([out_a, out_b], emitted))
     gm = torch.fx.GraphModule(torch.nn.ModuleList([model1, model2]), g)
@@ -261,11 +266,34 @@ FINALIZE_FLUSH_BYTES = int(float(os.environ.get("PLB_FINALIZE_FLUSH_MB", "1e9"))
 
 class _TapState:
     """Geometry, row-norm buffer and GEMM plan of one tap for one pair of activation shapes."""
-    __slots__ = ("ra", "rb", "kb", "K", "q", "plan", "version", "pa", "pb", "deferred", "group", "slot", "direct")
+    __slots__ = ("ra", "rb", "kb", "K", "q", "plan", "version", "pa", "pb", "deferred", "group", "slot", "direct",
+                 "tap")
 
 
 class _Tap:
-    __slots__ = ("name", "axis", "group", "states")
+    __slots__ = ("name", "axis", "group", "states", "affine", "aff_vec", "aff_key")
+
+
+# Eval-mode BatchNorm taps are not contracted: per unit the layer is y = s x + t, so its cross statistic follows from
+# the Gram, row sums and sums of squares of the tap in front of it (plb_cross_finalize_grouped, n_affine).  On a
+# ResNet-50 pair that is 53 of the 174 taps.  PLB_BN_AFFINE=0 contracts every tap.
+BN_AFFINE = os.environ.get("PLB_BN_AFFINE", "1") == "1"
+
+
+def _bn_scale_shift(bn):
+    """(s, t) in float64 with bn(x) = s x + t per channel (eval mode, running statistics)."""
+    s = (bn.running_var.detach().double() + bn.eps).rsqrt()
+    if bn.weight is not None:
+        s = s * bn.weight.detach().double()
+    t = -bn.running_mean.detach().double() * s
+    if bn.bias is not None:
+        t = t + bn.bias.detach().double()
+    return s, t
+
+
+def _bn_key(bn):
+    ts = (bn.running_mean, bn.running_var, bn.weight, bn.bias)
+    return tuple(None if x is None else (x.data_ptr(), x._version) for x in ts)
 
 
 class CrossAccumulator:
@@ -296,6 +324,7 @@ class CrossAccumulator:
             for ax in spec[k].node:
                 self.group_of[ax.key, ax.axis] = gi
         self.taps = []
+        self.tap_index = {}  # (node name, axis) -> index into self.taps
         self.arena = _Arena(device, slots=4 if overlap else 1)
         self._retired = []  # plans replaced by a rebind; captured graphs may still point at them
         self._pending = []  # deferred (small) taps of the batch in flight
@@ -326,8 +355,55 @@ class CrossAccumulator:
     def emit(self, g, name, axis, na, nb):
         t = _Tap()
         t.name, t.axis, t.group, t.states = name, axis, self.group_of[name, axis], {}
+        t.affine, t.aff_vec, t.aff_key = [], None, None
         self.taps.append(t)
+        self.tap_index[name, axis] = len(self.taps) - 1
         return g.call_function(_tap_dispatch, (self.sink_id, len(self.taps) - 1, na, nb))
+
+    def emit_affine(self, node, axis, model1, model2):
+        """Claims the tap of an eval-mode BatchNorm whose input is itself tapped (same axis, same permutation
+        group): it becomes a derived tap of that one.  True when claimed."""
+        if not BN_AFFINE or self.overlap or node.op != "call_module" or len(node.args) != 1 or node.kwargs or axis != 1:
+            return False
+        parent = node.args[0]
+        if not isinstance(parent, torch.fx.Node) or (parent.name, axis) not in self.tap_index:
+            return False
+        try:
+            mods = (model1.get_submodule(node.target), model2.get_submodule(node.target))
+        except AttributeError:
+            return False
+        for m in mods:
+            if not isinstance(m, torch.nn.modules.batchnorm._BatchNorm) or m.training or \
+                    not m.track_running_stats or m.running_mean is None or m.running_var is None:
+                return False
+        if self.group_of.get((node.name, axis)) != self.group_of.get((parent.name, axis)):
+            return False
+        n = self.costs[self.group_of[node.name, axis]].shape[0]
+        if mods[0].num_features != n or mods[1].num_features != n:
+            return False
+        self.taps[self.tap_index[parent.name, axis]].affine.append(mods)
+        return True
+
+    def refresh_affines(self):
+        """(Re)computes the derived taps' scale / shift vectors when the BatchNorm tensors changed (in place:
+        captured graphs and epilogue tables keep pointing at the same buffer)."""
+        for t in self.taps:
+            if not t.affine:
+                continue
+            key = tuple((_bn_key(a), _bn_key(b)) for a, b in t.affine)
+            if key == t.aff_key:
+                continue
+            parts = []
+            for a, b in t.affine:
+                sa, ta = _bn_scale_shift(a)
+                sb, tb = _bn_scale_shift(b)
+                parts += [sa, ta, sb, tb]
+            vec = torch.cat(parts).to(self.device)
+            if t.aff_vec is None:
+                t.aff_vec = vec.contiguous()
+            else:
+                t.aff_vec.copy_(vec)
+            t.aff_key = key
 
     def begin_batch(self, reset_costs):
         self._pending, self._pack_events, self._live, self._final, self._final_bytes = [], [], [], [], 0
@@ -347,10 +423,13 @@ class CrossAccumulator:
         if (ra, rb) != (n, n):
             raise ValueError(f"tap {t.name}:{t.axis} has {ra}x{rb} units but its group has {n}")
         st = _TapState()
+        st.tap = t
         st.ra, st.rb, st.K, st.kb = ra, rb, oa * ia, (oa * ia + 15) // 16
         # fp64 row norms live in the slab too (zeroed by begin_batch before the first use)
         # [qa | qb] sums of squares, [sa | sb] sums for the correlation statistic
         nq = {ops.MODE_INNER: 0, ops.MODE_NEG_CDIST: ra + rb, ops.MODE_CORR: 2 * (ra + rb)}[self.mode]
+        if t.affine:  # derived taps are formed from the row sums as well
+            nq = 2 * (ra + rb)
         st.q = self.pool.empty(2 * nq).view(torch.float64).zero_() if nq else None
         st.plan, st.version, st.group, st.slot = None, -1, t.group, None
         # narrow taps (C <= 128) are HBM-bound: the fused kernel reads the activations once, in place,
@@ -362,7 +441,7 @@ class CrossAccumulator:
             st.direct, st.deferred, st.pa, st.pb, st.version = True, False, None, None, None
             st.plan = ops.TmaGramPlan(ra, oa, ia, self.device, pool=self.pool)
             return st
-        st.direct = (not self.overlap) and fp32 and self.mode != ops.MODE_CORR and \
+        st.direct = (not self.overlap) and fp32 and self.mode != ops.MODE_CORR and not t.affine and \
             ops.direct_gram_eligible(xa, xb, t.axis)
         if st.direct:
             st.deferred, st.pa, st.pb, st.version = False, None, None, None
@@ -546,9 +625,12 @@ class CrossAccumulator:
                 for st in members:
                     qa, qb, sa, sb = self._moments(st)
                     pl = st.plan
+                    aff = st.tap.affine
+                    if aff and st.tap.aff_vec is None:
+                        self.refresh_affines()
                     taps_raw += bytes(ops.N.FinalizeTap(pl.partial.data_ptr(), ops.N.ptr(qa), ops.N.ptr(qb),
                                                         ops.N.ptr(sa), ops.N.ptr(sb), pl.ld_m, pl.ld_n, st.K,
-                                                        pl.splits, 0))
+                                                        pl.splits, len(aff), ops.N.ptr(st.tap.aff_vec) if aff else None))
                 groups_raw += bytes(ops.N.FinalizeGroup(self.costs[gi].data_ptr(), self.costs[gi].stride(0), n, ntaps,
                                                         ntaps + len(members), blocks))
                 ntaps += len(members)
@@ -618,7 +700,8 @@ class CalibrationRunner:
         axes = [ax for pg in spec.values() for ax in pg.node]
         self.conv_pairs = []
         self.gm = _dual_graph(model1, model2, axes, self.acc.emit, self.acc.emit_sync if overlap else None,
-                              conv_pairs=self.conv_pairs if conv.ENABLED else None)
+                              conv_pairs=self.conv_pairs if conv.ENABLED else None, emit_affine=self.acc.emit_affine)
+        self.acc.refresh_affines()
         self.reset = accumulate == "reference"
         self.step = GraphedStep(self._eager, self.acc.rebind_stale, use_cuda_graph)
 
@@ -637,6 +720,7 @@ class CalibrationRunner:
             if pair.packs is not None:
                 pair.packs[0].refresh()
                 pair.packs[1].refresh()
+        self.acc.refresh_affines()
 
     def _eager(self, x):
         self.acc.begin_batch(reset_costs=self.reset)

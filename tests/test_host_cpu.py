@@ -577,9 +577,9 @@ def test_tma_planning_helpers_and_struct_mirrors():
     # grouped epilogue: 256-column x 16-row tiles from 256 units up, 64 x 64 below
     assert ops.finalize_grouped_blocks(64) == 1 and ops.finalize_grouped_blocks(65) == 4
     assert ops.finalize_grouped_blocks(256) == 16 and ops.finalize_grouped_blocks(2048) == 8 * 128
-    assert ctypes.sizeof(_native.FinalizeTap) == 72 and ctypes.sizeof(_native.FinalizeGroup) == 32
+    assert ctypes.sizeof(_native.FinalizeTap) == 80 and ctypes.sizeof(_native.FinalizeGroup) == 32
     header = open(os.path.join(ROOT, "include", "pleas_b200.h")).read()
-    for field in ("partial", "qa", "qb", "sa", "sb", "ld_m", "ld_n", "K", "splits"):
+    for field in ("partial", "qa", "qb", "sa", "sb", "ld_m", "ld_n", "K", "splits", "n_affine", "affine"):
         assert re.search(r"typedef struct PlbFinalizeTap \{[^}]*\b%s\b" % field, header, re.S), field
     for field in ("cost", "ldc", "n", "tap_begin", "tap_end", "block_begin"):
         assert re.search(r"typedef struct PlbFinalizeGroup \{[^}]*\b%s\b" % field, header, re.S), field
