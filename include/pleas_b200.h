@@ -295,6 +295,18 @@ int plb_conv2d_forward(const float *const *x, const float *const *packed_w, cons
                        int64_t Cout, int32_t KH, int32_t KW, int32_t stride, int32_t pad_h, int32_t pad_w,
                        void *stream);
 
+/* Same, with the per-channel affine layer behind the convolution fused into the epilogue: besides out, the
+ * kernel writes out2[n, co, oh, ow] = f(scale[co] * out + shift[co]), f = ReLU when `relu`, else identity — an
+ * eval-mode BatchNorm (scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale) with its ReLU,
+ * i.e. the `conv -> bn -> relu` chain of the source models in one pass over the activation instead of three.
+ * scale_shift / out2 are HOST arrays of nprob device pointers; scale_shift[i] is Cout interleaved (scale, shift)
+ * fp32 pairs.  Both NULL: plain convolution. */
+int plb_conv2d_affine_forward(const float *const *x, const float *const *packed_w, const float *const *bias,
+                              float *const *out, const float *const *scale_shift, float *const *out2,
+                              int32_t relu, int32_t nprob, int64_t NB, int64_t Cin, int64_t IH, int64_t IW,
+                              int64_t Cout, int32_t KH, int32_t KW, int32_t stride, int32_t pad_h, int32_t pad_w,
+                              void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * PLeaS closed form: solve (G + ridge*I) X = B for symmetric positive definite G (fp64,
  * column/row symmetric so layout-agnostic), in place: G is overwritten by its Cholesky

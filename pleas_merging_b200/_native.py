@@ -76,6 +76,8 @@ _SIGNATURES = {
     "plb_conv_pack_weights": (ctypes.c_int, [c_ptr, c_i64, c_i64, c_i32, c_i32, c_ptr, c_ptr]),
     "plb_conv2d_forward": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i64, c_i64, c_i64, c_i64, c_i64,
                                           c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
+    "plb_conv2d_affine_forward": (ctypes.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_i32, c_i32, c_i64, c_i64,
+                                                 c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_ptr]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

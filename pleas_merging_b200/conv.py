@@ -70,9 +70,46 @@ def _ptr_array(ts):
     return (ctypes.c_void_p * len(ts))(*[None if t is None else t.data_ptr() for t in ts])
 
 
-def conv2d_forward(xs, packs):
+def bn_foldable(bn) -> bool:
+    """Eval-mode BatchNorm2d with running statistics: a per-channel affine map the convolution's epilogue can apply."""
+    return type(bn) is torch.nn.BatchNorm2d and not bn.training and bn.track_running_stats and \
+        bn.running_mean is not None and bn.running_var is not None and bn.running_mean.dtype == torch.float32 and \
+        bn.running_mean.is_cuda
+
+
+class FoldedBN:
+    """Interleaved fp32 (scale, shift) of an eval-mode BatchNorm: bn(x) = scale x + shift per channel (formed in
+    float64); refreshed when one of the module's tensors changes."""
+
+    def __init__(self, bn):
+        self.bn, self.vec, self.key = bn, None, None
+        self.refresh()
+
+    def refresh(self):
+        bn = self.bn
+        ts = (bn.running_mean, bn.running_var, bn.weight, bn.bias)
+        key = tuple(None if t is None else (t.data_ptr(), t._version) for t in ts)
+        if key == self.key:
+            return
+        s = (bn.running_var.detach().double() + bn.eps).rsqrt()
+        if bn.weight is not None:
+            s = s * bn.weight.detach().double()
+        t = -bn.running_mean.detach().double() * s
+        if bn.bias is not None:
+            t = t + bn.bias.detach().double()
+        vec = torch.stack([s, t], dim=1).float().contiguous()
+        if self.vec is None:
+            self.vec = vec
+        else:
+            self.vec.copy_(vec)
+        self.key = key
+
+
+def conv2d_forward(xs, packs, folded=None, relu=False):
     """Runs ``packs[i].mod`` on ``xs[i]`` (1 or 2 problems of identical geometry) in one launch; returns
-    the list of outputs.  Inputs must be fp32 CUDA NCHW-contiguous (the caller checks / falls back)."""
+    the list of outputs.  Inputs must be fp32 CUDA NCHW-contiguous (the caller checks / falls back).
+    ``folded`` (one FoldedBN per problem): the launch also writes relu?(bn(conv(x))) and the result is
+    ``(outs, outs2)``."""
     mod = packs[0].mod
     w = mod.weight
     cout, cin, kh, kw = w.shape
@@ -80,18 +117,21 @@ def conv2d_forward(xs, packs):
     stride, (ph, pw) = mod.stride[0], mod.padding
     oh, ow = (ih + 2 * ph - kh) // stride + 1, (iw + 2 * pw - kw) // stride + 1
     outs = [torch.empty((nb, cout, oh, ow), dtype=torch.float32, device=x.device) for x in xs]
+    outs2 = [torch.empty_like(o) for o in outs] if folded is not None else None
     biases = [pk.mod.bias.detach() if pk.mod.bias is not None else None for pk in packs]
     if CONV_TIMER is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    N.call("plb_conv2d_forward", xs[0].device, _ptr_array(xs), _ptr_array([pk.packed for pk in packs]),
-           _ptr_array(biases), _ptr_array(outs), len(xs), nb, cin, ih, iw, cout, kh, kw, stride, ph, pw)
+    N.call("plb_conv2d_affine_forward", xs[0].device, _ptr_array(xs), _ptr_array([pk.packed for pk in packs]),
+           _ptr_array(biases), _ptr_array(outs), None if folded is None else _ptr_array([f.vec for f in folded]),
+           None if folded is None else _ptr_array(outs2), int(bool(relu)), len(xs), nb, cin, ih, iw, cout, kh, kw,
+           stride, ph, pw)
     if CONV_TIMER is not None:
         e1.record()
         flops = 2.0 * len(xs) * nb * oh * ow * cout * cin * kh * kw
-        nbytes = 4.0 * len(xs) * (nb * cin * ih * iw + nb * cout * oh * ow)
+        nbytes = 4.0 * len(xs) * (nb * cin * ih * iw + (1 if folded is None else 2) * nb * cout * oh * ow)
         CONV_TIMER.append((e0, e1, flops, nbytes, (cin, cout, kh, stride, ih)))
-    return outs
+    return outs if folded is None else (outs, outs2)
 
 
 def input_ok(x, mod):
@@ -101,28 +141,54 @@ def input_ok(x, mod):
 
 
 class ConvPair:
-    """The same convolution layer of the two source models: fx ``call_function`` target state."""
+    """The same convolution layer of the two source models: fx ``call_function`` target state.  With ``bns``
+    (the eval-mode BatchNorm modules behind the convolutions) the call returns four tensors: the convolution
+    outputs and relu?(bn(.)) of them, written by the same launch."""
 
-    def __init__(self, mod_a, mod_b):
+    def __init__(self, mod_a, mod_b, bns=None, relu=False):
         self.mods = (mod_a, mod_b)
+        self.bns, self.relu = bns, relu
         self.packs = None
+        self.folded = None
 
     def same_geometry(self):
         a, b = self.mods
         return a.weight.shape == b.weight.shape and a.stride == b.stride and a.padding == b.padding and \
             (a.bias is None) == (b.bias is None)
 
+    def refresh(self):
+        if self.packs is not None:
+            self.packs[0].refresh()
+            self.packs[1].refresh()
+        if self.folded is not None:
+            self.folded[0].refresh()
+            self.folded[1].refresh()
+
+    def _fallback(self, xa, xb):
+        a, b = self.mods
+        ya, yb = a(xa), b(xb)
+        if self.bns is None:
+            return ya, yb
+        za, zb = self.bns[0](ya), self.bns[1](yb)
+        if self.relu:
+            za, zb = torch.relu(za), torch.relu(zb)
+        return ya, yb, za, zb
+
     def __call__(self, xa, xb):
         a, b = self.mods
         if not (input_ok(xa, a) and input_ok(xb, b) and xa.shape == xb.shape):
-            return a(xa), b(xb)
+            return self._fallback(xa, xb)
         if self.packs is None:
             self.packs = (PackedConv(a), PackedConv(b))
+            if self.bns is not None:
+                self.folded = (FoldedBN(self.bns[0]), FoldedBN(self.bns[1]))
         else:
-            self.packs[0].refresh()
-            self.packs[1].refresh()
-        ya, yb = conv2d_forward([xa, xb], self.packs)
-        return ya, yb
+            self.refresh()
+        if self.bns is None:
+            ya, yb = conv2d_forward([xa, xb], self.packs)
+            return ya, yb
+        (ya, yb), (za, zb) = conv2d_forward([xa, xb], self.packs, self.folded, self.relu)
+        return ya, yb, za, zb
 
 
 def conv2d(x, mod, pack=None):

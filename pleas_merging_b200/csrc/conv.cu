@@ -43,6 +43,9 @@ struct ConvParams {
   const float *x[2];
   const float *bias[2];
   float *out[2];
+  const float2 *post[2];  // per output channel (scale, shift) of the fused per-channel affine, or nullptr
+  float *out2[2];         // second output: relu?(scale * out + shift)
+  int post_relu;
   int nprob;
   int NB, Cin, IH, IW, Cout, OH, OW, KH, KW, stride, pad_h, pad_w;
   int P, OHW, IHW;
@@ -185,6 +188,37 @@ __device__ __forceinline__ void flat_rows(const int2 *rows, const float *origin,
     for (int t = 0; t < TAPS; ++t) {
       const bool ok = rowok && t < KW && (unsigned)(iw0 + t) < (unsigned)IW;
       cp_async4(dst + (r * TAPS + t) * 512, base + (ok ? t : 0), ok ? 0u : 1u);
+    }
+  }
+}
+
+// epilogue stores of one thread: its position's COLS channel values (stride ohw between channels)
+template <int COLS, bool BIAS, bool POST>
+__device__ __forceinline__ void store_tile(const float (&acc)[COLS], float *o, float *o2, int ohw, const float *bias,
+                                           const float2 *ss, bool relu, int) {
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) {
+    const float v = acc[c];
+    o[(int64_t)c * ohw] = v;
+    if (POST) {
+      const float2 a = __ldg(ss + c);
+      const float w = fmaf(v, a.x, a.y);
+      o2[(int64_t)c * ohw] = relu ? fmaxf(w, 0.f) : w;
+    }
+  }
+}
+template <int COLS>
+__device__ __noinline__ void store_tile_ragged(const float (&acc)[COLS], float *o, float *o2, int ohw, const float *bias,
+                                               const float2 *ss, bool relu, int nc) {
+#pragma unroll 4
+  for (int c = 0; c < COLS; ++c) {
+    if (c >= nc) break;
+    const float v = acc[c] + (bias ? __ldg(bias + c) : 0.f);
+    o[(int64_t)c * ohw] = v;
+    if (o2 != nullptr) {
+      const float2 a = __ldg(ss + c);
+      const float w = fmaf(v, a.x, a.y);
+      o2[(int64_t)c * ohw] = relu ? fmaxf(w, 0.f) : w;
     }
   }
 }
@@ -503,16 +537,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
         float *o = p.out[it.prob] + ((int64_t)n * p.Cout + co0) * p.OHW + r;
         const float *bias = p.bias[it.prob];
         const int ohw = p.OHW;
-        // one IMAD.WIDE + one STG per value on the common path (full channel tile, no bias): the store loop is
-        // what bounds the small-K layers, 64 values per thread and item
-        if (bias == nullptr && co0 + COLS <= p.Cout) {
-#pragma unroll
-          for (int c = 0; c < COLS; ++c) o[(int64_t)c * ohw] = acc[c];
+        const int nc = min(COLS, p.Cout - co0);
+        float *o2 = p.out2[it.prob] ? p.out2[it.prob] + ((int64_t)n * p.Cout + co0) * p.OHW + r : nullptr;
+        const float2 *ss = p.post[it.prob] ? p.post[it.prob] + co0 : nullptr;
+        const bool relu = p.post_relu != 0;
+        // one IMAD.WIDE + one STG per value on the common paths (full channel tile): the store loop is what bounds
+        // the small-K layers, 64 values per thread and item.  The fused eval-mode BatchNorm (+ ReLU) behind the
+        // convolution is a second output from the same registers instead of two more passes over the activation.
+        if (nc == COLS && bias == nullptr && o2 == nullptr) {
+          store_tile<COLS, false, false>(acc, o, o2, ohw, bias, ss, relu, nc);
+        } else if (nc == COLS && bias == nullptr) {
+          store_tile<COLS, false, true>(acc, o, o2, ohw, bias, ss, relu, nc);
         } else {
-          const int nc = min(COLS, p.Cout - co0);
-#pragma unroll
-          for (int c = 0; c < COLS; ++c)
-            if (c < nc) o[(int64_t)c * ohw] = acc[c] + (bias ? __ldg(bias + co0 + c) : 0.f);
+          store_tile_ragged<COLS>(acc, o, o2, ohw, bias ? bias + co0 : nullptr, ss, relu, nc);
         }
       }
     }
@@ -620,6 +657,16 @@ extern "C" int plb_conv2d_forward(const float *const *x, const float *const *pac
                                   float *const *out, int32_t nprob, int64_t NB, int64_t Cin, int64_t IH, int64_t IW,
                                   int64_t Cout, int32_t KH, int32_t KW, int32_t stride, int32_t pad_h, int32_t pad_w,
                                   void *stream) {
+  return plb_conv2d_affine_forward(x, packed_w, bias, out, nullptr, nullptr, 0, nprob, NB, Cin, IH, IW, Cout, KH, KW,
+                                   stride, pad_h, pad_w, stream);
+}
+
+extern "C" int plb_conv2d_affine_forward(const float *const *x, const float *const *packed_w,
+                                         const float *const *bias, float *const *out,
+                                         const float *const *scale_shift, float *const *out2, int32_t relu,
+                                         int32_t nprob, int64_t NB, int64_t Cin, int64_t IH, int64_t IW, int64_t Cout,
+                                         int32_t KH, int32_t KW, int32_t stride, int32_t pad_h, int32_t pad_w,
+                                         void *stream) {
   using namespace plb;
   PLB_REQUIRE(x && packed_w && out, PLB_EINVAL, "plb_conv2d_forward: null pointer table");
   PLB_REQUIRE(nprob == 1 || nprob == 2, PLB_EINVAL, "plb_conv2d_forward: one or two problems per launch");
@@ -642,8 +689,16 @@ extern "C" int plb_conv2d_forward(const float *const *x, const float *const *pac
     p.x[i] = x[i];
     p.out[i] = out[i];
     p.bias[i] = bias ? bias[i] : nullptr;
+    PLB_REQUIRE((scale_shift == nullptr) == (out2 == nullptr) &&
+                    (out2 == nullptr || ((scale_shift[i] != nullptr) && (out2[i] != nullptr))),
+                PLB_EINVAL, "plb_conv2d_affine_forward: scale_shift and out2 go together");
+    PLB_REQUIRE(scale_shift == nullptr || ((uintptr_t)scale_shift[i] & 7) == 0, PLB_EALIGN,
+                "plb_conv2d_affine_forward: scale_shift must be 8-byte aligned");
+    p.post[i] = scale_shift ? reinterpret_cast<const float2 *>(scale_shift[i]) : nullptr;
+    p.out2[i] = out2 ? out2[i] : nullptr;
   }
   p.nprob = nprob;
+  p.post_relu = relu;
   p.NB = (int)NB, p.Cin = (int)Cin, p.IH = (int)IH, p.IW = (int)IW, p.Cout = (int)Cout, p.OH = (int)OH, p.OW = (int)OW;
   p.KH = KH, p.KW = KW, p.stride = stride, p.pad_h = pad_h, p.pad_w = pad_w;
   p.P = (int)(NB * OH * OW), p.OHW = (int)(OH * OW), p.IHW = (int)(IH * IW);

@@ -107,7 +107,17 @@ def _dual_graph(model1: Module, model2: Module, axes: Collection, emit, emit_syn
     env = ({}, {})
     emitted = {}
     out_a = out_b = None
+    fused = {}  # BatchNorm / ReLU node -> (value_a, value_b) written by the convolution launch in front (None: never stored)
     for node in traced.graph.nodes:
+        if node in fused:
+            vals = fused[node]
+            env[0][node], env[1][node] = vals if vals is not None else (None, None)
+            for a in taps.get(node.name, ()):
+                if emit_affine is not None and emit_affine(node, a, model1, model2):
+                    emitted[node.name, a] = None
+                else:  # _conv_fusion only leaves taps here that a value exists for
+                    emitted[node.name, a] = emit(g, node.name, a, env[0][node], env[1][node])
+            continue
         if node.op == "placeholder":
             ph = g.node_copy(node)
             env[0][node] = env[1][node] = ph
@@ -120,12 +130,22 @@ def _dual_graph(model1: Module, model2: Module, axes: Collection, emit, emit_syn
             emit_sync(g)
         pair = _conv_pair_for(node, model1, model2) if conv_pairs is not None else None
         if pair is not None:
+            plan = _conv_fusion(node, model1, model2, taps, emit_affine) if CONV_BN_FUSION else None
+            if plan is not None:
+                bn_node, relu_node, bns = plan
+                pair.bns, pair.relu = bns, relu_node is not None
             pid = next(_conv_ids)
             _CONV_PAIRS[pid] = pair
             conv_pairs.append(pid)
             both = g.call_function(_conv_pair_dispatch, (pid, env[0][node.args[0]], env[1][node.args[0]]))
             env[0][node] = g.call_function(operator.getitem, (both, 0))
             env[1][node] = g.call_function(operator.getitem, (both, 1))
+            if plan is not None:
+                second = (g.call_function(operator.getitem, (both, 2)), g.call_function(operator.getitem, (both, 3)))
+                if relu_node is not None:
+                    fused[bn_node], fused[relu_node] = None, second
+                else:
+                    fused[bn_node] = second
             for a in taps.get(node.name, ()):
                 emitted[node.name, a] = emit(g, node.name, a, env[0][node], env[1][node])
             continue
@@ -143,6 +163,54 @@ def _dual_graph(model1: Module, model2: Module, axes: Collection, emit, emit_syn
     gm = torch.fx.GraphModule(torch.nn.ModuleList([model1, model2]), g)
     gm.graph.lint()
     return gm
+
+
+# conv -> eval-mode BatchNorm (-> ReLU) chains of the source models run as ONE launch of the convolution kernel with
+# two outputs (plb_conv2d_affine_forward) when the BatchNorm's own tap, if any, is derived from the convolution's
+# (CrossAccumulator.emit_affine) — three passes over the activation less.  PLB_CONV_BN_FUSION=0 keeps the modules.
+CONV_BN_FUSION = os.environ.get("PLB_CONV_BN_FUSION", "1") == "1"
+
+
+def _is_relu_of(node, src, model1, model2):
+    if node.kwargs and set(node.kwargs) - {"inplace"}:
+        return False
+    if node.op == "call_module":
+        try:
+            ms = (model1.get_submodule(node.target), model2.get_submodule(node.target))
+        except AttributeError:
+            return False
+        return all(type(m) is torch.nn.ReLU and not m._forward_hooks and not m._forward_pre_hooks for m in ms) and \
+            tuple(node.args) == (src,)
+    if node.op == "call_function":
+        return node.target in (torch.relu, torch.relu_, torch.nn.functional.relu) and tuple(node.args) == (src,)
+    return False
+
+
+def _conv_fusion(node, model1, model2, taps, emit_affine):
+    """(bn_node, relu_node or None, (bn_a, bn_b)) when the convolution ``node`` feeds exactly one foldable BatchNorm
+    whose taps can all be derived from the convolution's tap, else None."""
+    if len(node.users) != 1:
+        return None
+    bn = next(iter(node.users))
+    if bn.op != "call_module" or tuple(bn.args) != (node,) or bn.kwargs:
+        return None
+    try:
+        bns = (model1.get_submodule(bn.target), model2.get_submodule(bn.target))
+    except AttributeError:
+        return None
+    if not all(conv.bn_foldable(m) and not m._forward_hooks and not m._forward_pre_hooks for m in bns):
+        return None
+    if bns[0].num_features != bns[1].num_features:
+        return None
+    for a in taps.get(bn.name, ()):  # a tapped BatchNorm output must be derivable: it is never read
+        if emit_affine is None or not emit_affine(bn, a, model1, model2, check_only=True):
+            return None
+    relu = None
+    if len(bn.users) == 1:
+        cand = next(iter(bn.users))
+        if _is_relu_of(cand, bn, model1, model2):
+            relu = cand
+    return bn, relu, bns
 
 
 def _conv_pair_for(node, model1, model2):
@@ -360,13 +428,16 @@ class CrossAccumulator:
         self.tap_index[name, axis] = len(self.taps) - 1
         return g.call_function(_tap_dispatch, (self.sink_id, len(self.taps) - 1, na, nb))
 
-    def emit_affine(self, node, axis, model1, model2):
+    def emit_affine(self, node, axis, model1, model2, check_only=False):
         """Claims the tap of an eval-mode BatchNorm whose input is itself tapped (same axis, same permutation
-        group): it becomes a derived tap of that one.  True when claimed."""
+        group): it becomes a derived tap of that one.  True when claimed.  ``check_only``: asks ahead, while the
+        parent's own tap is still to be emitted."""
         if not BN_AFFINE or self.overlap or node.op != "call_module" or len(node.args) != 1 or node.kwargs or axis != 1:
             return False
         parent = node.args[0]
-        if not isinstance(parent, torch.fx.Node) or (parent.name, axis) not in self.tap_index:
+        if not isinstance(parent, torch.fx.Node):
+            return False
+        if (parent.name, axis) not in (self.group_of if check_only else self.tap_index):
             return False
         try:
             mods = (model1.get_submodule(node.target), model2.get_submodule(node.target))
@@ -381,7 +452,8 @@ class CrossAccumulator:
         n = self.costs[self.group_of[node.name, axis]].shape[0]
         if mods[0].num_features != n or mods[1].num_features != n:
             return False
-        self.taps[self.tap_index[parent.name, axis]].affine.append(mods)
+        if not check_only:
+            self.taps[self.tap_index[parent.name, axis]].affine.append(mods)
         return True
 
     def refresh_affines(self):
@@ -716,10 +788,7 @@ class CalibrationRunner:
         """Re-splits convolution weights that changed since they were packed (a CUDA-graph replay runs no
         Python: the packed planes it reads are brought up to date here, before the batches of a call)."""
         for pid in self.conv_pairs:
-            pair = _CONV_PAIRS[pid]
-            if pair.packs is not None:
-                pair.packs[0].refresh()
-                pair.packs[1].refresh()
+            _CONV_PAIRS[pid].refresh()
         self.acc.refresh_affines()
 
     def _eager(self, x):

@@ -76,3 +76,45 @@ def test_conv_ineligible_falls_back_to_module():
     x = torch.randn(1, 64, 8, 8, device="cuda")
     with torch.no_grad():
         assert torch.equal(conv.conv2d(x, m), m(x))
+
+
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("case", [(2, 64, 28, 28, 256, 1, 1, 0), (3, 64, 14, 14, 72, 3, 1, 1), (2, 3, 32, 32, 24, 7, 2, 3)],
+                         ids=["1x1", "3x3-ragged", "stem"])
+def test_conv_with_fused_batchnorm_relu_output(case, relu):
+    """plb_conv2d_affine_forward: the eval-mode BatchNorm (+ ReLU) behind a convolution as a second output of the same
+    launch, against the fp64 modules; the first output stays the plain convolution."""
+    from pleas_merging_b200 import conv
+
+    nb, cin, h, w, cout, k, stride, pad = case
+    mods, bns = [], []
+    for seed in (1, 2):
+        torch.manual_seed(seed)
+        mods.append(torch.nn.Conv2d(cin, cout, k, stride, pad, bias=(seed == 2 and k == 3)).cuda())
+        bn = torch.nn.BatchNorm2d(cout).cuda().eval()
+        with torch.no_grad():
+            bn.weight.copy_(torch.randn(cout).cuda())        # negative scales included
+            bn.bias.copy_(0.3 * torch.randn(cout).cuda())
+            bn.running_mean.copy_(0.2 * torch.randn(cout).cuda())
+            bn.running_var.copy_(0.5 + torch.rand(cout).cuda())
+        bns.append(bn)
+    same_bias = (mods[0].bias is None) == (mods[1].bias is None)
+    if not same_bias:  # a pair needs the same geometry
+        mods[0] = torch.nn.Conv2d(cin, cout, k, stride, pad, bias=True).cuda()
+    xa, xb = torch.randn(nb, cin, h, w, device="cuda"), torch.randn(nb, cin, h, w, device="cuda")
+    pair = conv.ConvPair(mods[0], mods[1], bns=tuple(bns), relu=relu)
+    with torch.no_grad():
+        ya, yb, za, zb = pair(xa, xb)
+        for y, z, m, bn, x in ((ya, za, mods[0], bns[0], xa), (yb, zb, mods[1], bns[1], xb)):
+            ref = torch.nn.functional.conv2d(x.double(), m.weight.double(), None if m.bias is None else m.bias.double(),
+                                             stride, pad)
+            ref2 = torch.nn.functional.batch_norm(ref, bn.running_mean.double(), bn.running_var.double(),
+                                                  bn.weight.double(), bn.bias.double(), False, 0.0, bn.eps)
+            if relu:
+                ref2 = torch.relu(ref2)
+            assert (y.double() - ref).abs().max().item() <= 3e-6 * ref.abs().max().item()
+            assert (z.double() - ref2).abs().max().item() <= 4e-6 * max(ref2.abs().max().item(), 1.0)
+        # a BatchNorm update is seen by the next call
+        bns[0].running_mean.add_(1.0)
+        _, _, za2, _ = pair(xa, xb)
+        assert not torch.equal(za2, za)

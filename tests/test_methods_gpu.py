@@ -585,9 +585,10 @@ def test_activation_matching_correlation_statistic(accumulate):
         oc = ocosts[(k.key, k.axis)]
         assert np.abs(costs[k].cpu().numpy() - oc).max() <= 1e-3, k
         assert np.abs(costs2[k].cpu().numpy() - oc).max() <= 1e-3, k
-        # fused loop == generic plug-in path, up to the BatchNorm taps: the fused loop derives them from the tap in front
-        # (sign(s_a s_b) corr, exact), the plug-in contracts the shifted fp32 outputs (variance by cancellation)
-        assert (costs[k] - costs2[k]).abs().max() <= 1e-4, k
+        # fused loop == generic plug-in path, up to the BatchNorm layers: the fused loop folds them into the convolution
+        # launch and derives their taps from the tap in front (sign(s_a s_b) corr, exact), the plug-in runs the modules
+        # and contracts the shifted fp32 outputs (variance by cancellation); both are within 1e-3 of the fp64 oracle
+        assert (costs[k] - costs2[k]).abs().max() <= 5e-4, k
         assert_perm_or_objective(perm[k].numpy(), operm[(k.key, k.axis)], oc, str(k))
         assert_perm_or_objective(perm2[k].numpy(), operm[(k.key, k.axis)], oc, str(k))
 
