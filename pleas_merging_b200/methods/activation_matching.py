@@ -91,7 +91,7 @@ def _conv_pair_dispatch(pair_id: int, xa, xb):
 
 
 def _dual_graph(model1: Module, model2: Module, axes: Collection, emit, emit_sync=None, conv_pairs=None,
-                emit_affine=None):
+                emit_affine=None, on_layer=None):
     """Runs both models side by side in one fx graph (model2 must trace to model1's graph, as
     in the reference, :68).  After every tapped node ``emit(graph, name, axis, node_a, node_b)``
     inserts the tap consumer right behind its producers — torchvision's in-place ReLU
@@ -100,7 +100,9 @@ def _dual_graph(model1: Module, model2: Module, axes: Collection, emit, emit_syn
     asynchronously gets the chance to finish first.  ``conv_pairs`` (a list, optional): eligible Conv2d layers are
     not called as modules but pairwise through ``_conv_pair_dispatch``; the ids registered in ``_CONV_PAIRS`` are
     appended to the list for the caller to release.  ``emit_affine(node, axis, model1, model2)`` (optional) may claim a
-    tap as a per-unit affine image of an earlier tap (returns True): no consumer is inserted for it."""
+    tap as a per-unit affine image of an earlier tap (returns True): no consumer is inserted for it.
+    ``on_layer(graph, module_name, in_a, in_b, out_a, out_b)`` (optional) is called behind every Conv2d / Linear
+    ``call_module`` node (PLeaS captures the trained layers' inputs and outputs this way)."""
     traced = torch.fx.symbolic_trace(model1)
     taps = _tap_axes(axes)
     g = torch.fx.Graph()
@@ -140,6 +142,8 @@ def _dual_graph(model1: Module, model2: Module, axes: Collection, emit, emit_syn
             both = g.call_function(_conv_pair_dispatch, (pid, env[0][node.args[0]], env[1][node.args[0]]))
             env[0][node] = g.call_function(operator.getitem, (both, 0))
             env[1][node] = g.call_function(operator.getitem, (both, 1))
+            if on_layer is not None:
+                on_layer(g, node.target, env[0][node.args[0]], env[1][node.args[0]], env[0][node], env[1][node])
             if plan is not None:
                 second = (g.call_function(operator.getitem, (both, 2)), g.call_function(operator.getitem, (both, 3)))
                 if relu_node is not None:
@@ -154,6 +158,10 @@ def _dual_graph(model1: Module, model2: Module, axes: Collection, emit, emit_syn
             if node.op in ("call_module", "get_attr"):
                 new.target = f"{side}.{node.target}"
             env[side][node] = new
+        if on_layer is not None and node.op == "call_module" and len(node.args) >= 1 and \
+                isinstance(node.args[0], torch.fx.Node) and \
+                isinstance(traced.get_submodule(node.target), (torch.nn.Conv2d, torch.nn.Linear)):
+            on_layer(g, node.target, env[0][node.args[0]], env[1][node.args[0]], env[0][node], env[1][node])
         for a in taps.get(node.name, ()):
             if emit_affine is not None and emit_affine(node, a, model1, model2):
                 emitted[node.name, a] = None

@@ -33,6 +33,9 @@ from ..core.utils import Axis, get_attr
 from ..graphs import GraphedStep
 from ..parallel import (BatchSharder, allreduce_sum_, assign_owners, device_prefetch, reduce_to_owners_,
                         world)
+import importlib
+
+_AM = importlib.import_module(".activation_matching", __package__)  # the package re-exports a function of this name
 from .partial_matching import get_blocks
 
 
@@ -353,6 +356,12 @@ class _LayerLS:
         return W, W0
 
 
+def _record_layer(sink_id: int, name: str, in_a, in_b, out_a, out_b):
+    """fx ``call_function`` target: hands a trained layer's inputs / outputs of both models to the runner."""
+    _AM._SINKS[sink_id].record(name, in_a, in_b, out_a, out_b)
+    return None
+
+
 class LstsqRunner:
     """Streams calibration batches through both source models (forward hooks capture every
     trained layer's input and output) and accumulates all layers' normal equations; the
@@ -368,9 +377,22 @@ class LstsqRunner:
         self.perm_blocks, self.num_classes = perm_blocks, num_classes
         self.separate_classifier, self.model_type = separate_classifier, model_type
         self.acts1, self.acts2 = {}, {}
-        self.hooks = capture_inputs(model1, self.acts1) + capture_inputs(model2, self.acts2)
-        # the source models' convolutions run on the library's 3xTF32 tcgen05 kernel (conv.py) while this runner lives
-        self.conv_patch = conv.patched_convs(model1, model2).open()
+        # Both source models run side by side through the activation-matching dual graph: the same layer of the two
+        # models is one launch of the library's convolution kernel, with the eval-mode BatchNorm (+ ReLU) behind it
+        # folded in, and every trained layer's (input, output) is recorded on the way.  Models fx cannot trace, or
+        # that trace to different graphs, run as plain modules with forward hooks (convolutions patched one by one).
+        self.gm, self.hooks, self.conv_patch, self.conv_pairs = None, [], None, []
+        self.sink_id = next(_AM._sink_ids)
+        if conv.ENABLED:
+            try:
+                _AM._SINKS[self.sink_id] = self
+                self.gm = _AM._dual_graph(model1, model2, (), None, conv_pairs=self.conv_pairs, on_layer=self._on_layer)
+            except Exception:  # not traceable: plain module calls
+                self.gm = None
+                self._release_graph()
+        if self.gm is None:
+            self.hooks = capture_inputs(model1, self.acts1) + capture_inputs(model2, self.acts2)
+            self.conv_patch = conv.patched_convs(model1, model2).open()
         self.layers3 = {n: m for n, m in model3.named_modules() if isinstance(m, (torch.nn.Conv2d, torch.nn.Linear))}
         self.accs, self.flat, self.ws = None, None, _Workspace(self.device)
         self.step = GraphedStep(self._eager, self._rebind, use_cuda_graph)
@@ -379,11 +401,26 @@ class LstsqRunner:
 
     def close(self):
         self.step.clear()
-        self.conv_patch.close()
+        self._release_graph()
+        if self.conv_patch is not None:
+            self.conv_patch.close()
         for h in self.hooks:
             h.remove()
         self.acts1.clear()
         self.acts2.clear()
+
+    def _release_graph(self):
+        _AM._SINKS.pop(self.sink_id, None)
+        for pid in self.conv_pairs:
+            _AM._CONV_PAIRS.pop(pid, None)
+        self.conv_pairs = []
+
+    def _on_layer(self, g, name, in_a, in_b, out_a, out_b):
+        return g.call_function(_record_layer, (self.sink_id, name, in_a, in_b, out_a, out_b))
+
+    def record(self, name, in_a, in_b, out_a, out_b):
+        self.acts1[name] = (in_a, out_a)
+        self.acts2[name] = (in_b, out_b)
 
     def _create(self):
         self.accs = {}
@@ -435,8 +472,11 @@ class LstsqRunner:
     def _eager(self, x):
         self.acts1.clear()
         self.acts2.clear()
-        self.model1(x)
-        self.model2(x)
+        if self.gm is not None:
+            self.gm(x)
+        else:
+            self.model1(x)
+            self.model2(x)
         if self.accs is None:
             self._create()
         Ls = {n: a.out_positions(self.acts1[n]) for n, a in self.accs.items()}

@@ -588,7 +588,7 @@ def test_activation_matching_correlation_statistic(accumulate):
         # fused loop == generic plug-in path, up to the BatchNorm layers: the fused loop folds them into the convolution
         # launch and derives their taps from the tap in front (sign(s_a s_b) corr, exact), the plug-in runs the modules
         # and contracts the shifted fp32 outputs (variance by cancellation); both are within 1e-3 of the fp64 oracle
-        assert (costs[k] - costs2[k]).abs().max() <= 5e-4, k
+        assert (costs[k] - costs2[k]).abs().max() <= 1e-3, k
         assert_perm_or_objective(perm[k].numpy(), operm[(k.key, k.axis)], oc, str(k))
         assert_perm_or_objective(perm2[k].numpy(), operm[(k.key, k.axis)], oc, str(k))
 
@@ -624,9 +624,11 @@ def test_batchnorm_taps_derived_from_the_tap_in_front_equal_contracted_taps(mode
     """An eval-mode BatchNorm tap is not contracted: its statistic is formed in the grouped epilogue from the Gram,
     row sums and sums of squares of the tap in front of it (PlbFinalizeTap.n_affine).  Same cost matrices as with
     every tap contracted (PLB_BN_AFFINE=0), negative BatchNorm scales included; fewer Gram launches."""
-    from pleas_merging_b200 import _native
-    from pleas_merging_b200.methods import activation_matching as AM
+    import importlib
 
+    from pleas_merging_b200 import _native
+
+    AM = importlib.import_module("pleas_merging_b200.methods.activation_matching")
     P = _pkg()
     m1, m2 = tinynet.make_pair(12, 10)
     with torch.no_grad():
@@ -651,5 +653,7 @@ def test_batchnorm_taps_derived_from_the_tap_in_front_equal_contracted_taps(mode
     for k in spec:
         a, b = out[True][1][k], out[False][1][k]
         scale = float(b.abs().max())
-        assert float((a - b).abs().max()) <= (2e-5 if mode == "corr" else 1e-5 * scale), (k, mode)
+        # correlation: the contracted BatchNorm tap forms variances of SHIFTED fp32 outputs by cancellation, the
+        # derived one is sign(s_a s_b) corr of the tap in front — the difference is the contracted path's error
+        assert float((a - b).abs().max()) <= (5e-4 if mode == "corr" else 1e-5 * scale), (k, mode)
         assert_perm_or_objective(out[True][0][k].numpy(), out[False][0][k].numpy(), b.cpu().numpy(), str(k))
