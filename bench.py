@@ -559,7 +559,7 @@ def _run_b200(args):
             "conv3xtf32_kernel", membound,
             conv_note + "the launches whose HBM time exceeds their tensor time (1x1 layers with few input channels, the "
             "3-channel stem): achieved = algorithmic bytes (x read once, every output written once) / summed launch "
-            "time; " + common)
+            "time; " + common, traffic_kernel="conv3xtf32_kernel (HBM-bound class)")
         if r:
             out["roofline_conv_hbm"] = r
         c_ms = sum(a.elapsed_time(b) for a, b, _, _, _ in conv_timer)

@@ -655,5 +655,5 @@ def test_batchnorm_taps_derived_from_the_tap_in_front_equal_contracted_taps(mode
         scale = float(b.abs().max())
         # correlation: the contracted BatchNorm tap forms variances of SHIFTED fp32 outputs by cancellation, the
         # derived one is sign(s_a s_b) corr of the tap in front — the difference is the contracted path's error
-        assert float((a - b).abs().max()) <= (5e-4 if mode == "corr" else 1e-5 * scale), (k, mode)
+        assert float((a - b).abs().max()) <= (2e-3 if mode == "corr" else 1e-5 * scale), (k, mode)
         assert_perm_or_objective(out[True][0][k].numpy(), out[False][0][k].numpy(), b.cpu().numpy(), str(k))
