@@ -345,14 +345,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
           if (q < nb && !((ready >> q) & 1u)) a32_wait_wd(bar_full + 8 * ((i + q) & (kConvStages - 1)), ((i + q) / kConvStages) & 1u);
         if (trm) p.trace[i * 16 + 4] = clock64();
         tc_fence_after();
-        // probes for the next chain (harmless when there is none: they just report "not yet")
-        uint32_t nready = 0;
-#pragma unroll
-        for (int q = 0; q < CH; ++q) {
-          const uint32_t in = i + nb + q;
-          if (a32_test_wait(bar_full + 8 * (in & (kConvStages - 1)), (in / kConvStages) & 1u)) nready |= 1u << q;
-        }
-        const bool next_acc = a32_test_wait(bar_acc_empty + 8 * ((chain + 1) & 1u), (((chain + 1) >> 1) & 1u) ^ 1u);
         if (elect_one()) {
 #pragma unroll
           for (int q = 0; q < CH; ++q) {
@@ -366,6 +358,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv3xtf32_kernel(const __gri
                 umma_tf32_ts(d_tmem, a_hi0 + 8 * j, umma_desc_sw<128>(bst + kPlaneBytes + 32 * j), idesc, 1u);
             }
           }
+        }
+        __syncwarp();
+        // Probes for the next chain, issued BETWEEN the chain's two MMA phases: the stages of the next chain are
+        // the ones the previous chain released when this one started executing, so at the top of the chain the
+        // loaders have not refilled them yet (the probe would always fail and the blocking wait after the issue
+        // loop would cost 100-250 clocks per barrier); two thirds of the chain's MMAs later they have, and the
+        // tensor pipe keeps draining its queue while the probes are in flight.  Harmless when there is no next
+        // chain: they just report "not yet".
+        uint32_t nready = 0;
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+          const uint32_t in = i + nb + q;
+          if (a32_test_wait(bar_full + 8 * (in & (kConvStages - 1)), (in / kConvStages) & 1u)) nready |= 1u << q;
+        }
+        const bool next_acc = a32_test_wait(bar_acc_empty + 8 * ((chain + 1) & 1u), (((chain + 1) >> 1) & 1u) ^ 1u);
+        if (elect_one()) {
 #pragma unroll
           for (int q = 0; q < CH; ++q) {
             if (q >= nb) break;
