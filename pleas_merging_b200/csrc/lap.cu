@@ -541,6 +541,385 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v2(const float *const *__r
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// v3 (product path): the same algorithm and selection rules again, with the per-column solver
+// state in REGISTERS.  v2 keeps v, dist, row4col and the todo list in shared memory and gathers
+// four of them per column per step (49 KB of shared-memory traffic per step at n = 2048 — the
+// step was bound by the shared-memory pipe, not by the L2 latency of the cost row).  Here a
+// thread owns fixed columns j = tid + c * nthr: its column dual, tentative distance and
+// row4col live in registers, and SciPy's `remaining` list is kept implicitly as the list
+// POSITION of each owned column (the list is filled in reverse: column j starts at position
+// n-1-j; removing position t moves the column at the last position into t — the owner of that
+// column notices `pos == last` and takes t).  The cost row is read coalesced (fixed columns), a
+// step touches shared memory only for u[row], the predecessor store and the 32 warp winners.
+// The dual update runs from registers (the owner of a scanned column j updates v_j and the
+// dual of the row matched to j); only the path flip walks shared memory.
+// Shared memory: u, a column-dual scratch for the warm start, pred, row4col, col4row (28 B/col).
+// ------------------------------------------------------------------------------------------
+#ifdef PLB_LAP_TRACE  // profiles/experiments/lap_trace.cu: per-phase clock sums of problem 0 (first and last thread)
+__device__ uint32_t plb_lap_trace[2][10];
+#define LAP_STAMP(k, dep)                                                                      \
+  do {                                                                                         \
+    uint32_t _t;                                                                               \
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(_t) : "r"((uint32_t)(dep)) : "memory");         \
+    tr_acc[k] += _t - tr_last;                                                                 \
+    tr_last = _t;                                                                              \
+  } while (0)
+#else
+#define LAP_STAMP(k, dep) \
+  do {                    \
+  } while (0)
+#endif
+static inline size_t lap_v3_smem_bytes(int n) { return 1024 + (size_t)n * (2 * 8 + 3 * 4) + 64; }
+
+// order_key on the two 32-bit halves (b ^ ((b >> 63) | sign bit)): pure integer instructions — the compiler
+// turns the 64-bit form into an fp64 -|x| DADD on the long-latency pipe.
+__device__ __forceinline__ uint64_t order_key_i(double d) {
+  const int hi = __double2hiint(d);
+  const uint32_t lo = (uint32_t)__double2loint(d);
+  const uint32_t m = (uint32_t)(hi >> 31);
+  return ((uint64_t)((uint32_t)hi ^ (m | 0x80000000u)) << 32) | (uint64_t)(lo ^ m);
+}
+// Shared-memory accesses of the step loop by 32-bit shared address held in a register: with C++ pointers the
+// compiler re-derives the shared window base (S2UR SR_CgaCtaId + ULEA) inside the dependent chain of every step.
+__device__ __forceinline__ uint64_t lds_u64(uint32_t a) {
+  uint64_t v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u64(uint32_t a, uint64_t v) {
+  asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
+template <int CPT>
+__global__ void __launch_bounds__(1024, 1) lap_kernel_v3(const float *const *__restrict__ costs,
+                                                        const int32_t *__restrict__ ns,
+                                                        const int32_t *__restrict__ lds,
+                                                        int64_t *const *__restrict__ outs,
+                                                        double *__restrict__ objective, int32_t *__restrict__ status,
+                                                        int maximize, const double *const *__restrict__ v_in,
+                                                        double v_scale, double *const *__restrict__ v_out) {
+  extern __shared__ __align__(16) uint8_t lap_smem[];
+  // warp-winner slots (double-buffered by step parity) at the front of the dynamic allocation:
+  // keys u64 [2][32] at +0, rank << 13 | (row4col + 1) u32 [2][32] at +512
+  // sink column of the finished search at +768.  The base goes through an opaque asm so that it stays a register.
+  uint32_t sm_base;
+  asm volatile("mov.u32 %0, %1;" : "=r"(sm_base) : "r"(smem_u32(lap_smem)));
+  __shared__ double red[32];
+  __shared__ int sh_bad;
+
+  const int prob = blockIdx.x;
+  const int n = ns[prob];
+  const int64_t ld = lds[prob];
+  const float *__restrict__ C = costs[prob];
+  const int need = max(32, (((n + CPT - 1) / CPT + 31) / 32) * 32);
+  const int tid = threadIdx.x, nthr = min((int)blockDim.x, need), lane = tid & 31, warp = tid >> 5;
+  if (tid >= nthr) return;  // warps this problem's columns do not need (block sized for the batch's largest n)
+  const int nwarps = nthr >> 5;
+  const double sgn = maximize ? -1.0 : 1.0;
+  const uint32_t smask = maximize ? 0x80000000u : 0u;  // costs are negated by flipping the float's sign bit
+  double *__restrict__ u = (double *)(lap_smem + 1024);
+  double *__restrict__ vtmp = u + n;
+  int *__restrict__ pred = (int *)(vtmp + n);
+  int *__restrict__ row4col = pred + n;
+  int *__restrict__ col4row = row4col + n;
+
+  if (tid == 0) sh_bad = 0;
+  for (int k = tid; k < n; k += nthr) {
+    u[k] = 0.0;
+    pred[k] = -1;
+    row4col[k] = -1;
+    col4row[k] = -1;
+  }
+  __syncthreads();
+  {  // NaN / -inf screen (SciPy returns an error for those); rows of 4 GB and more are not addressed (32-bit
+    // row offsets in the step loop) and reported the same way
+    int bad = (ld >= (int64_t)(1 << 30)) ? 1 : 0;
+    for (int i = 0; i < n; ++i) {
+      const float *__restrict__ crow = C + (int64_t)i * ld;
+      for (int j = tid; j < n; j += nthr) {
+        const double x = sgn * (double)__ldg(crow + j);
+        if (x != x || x == -INFINITY) bad = 1;
+      }
+    }
+    if (bad) sh_bad = 1;
+  }
+  __syncthreads();
+  if (sh_bad) {
+    if (tid == 0) {
+      status[prob] = 2;
+      objective[prob] = 0.0;
+    }
+    return;
+  }
+
+  // Tentative distances are kept as their order-preserving integer image: fp64 compares sit on a long-latency pipe
+  // (a DSETP costs as much as a DADD), the integer compares of the relaxation and of the arg-min do not.  The
+  // image is exact and monotonic for every value that occurs (no NaN after the screen, and -0.0 cannot arise:
+  // min_val starts at +0.0 and x - x rounds to +0.0).
+  double v[CPT];
+  uint64_t dkey[CPT];
+  int pos[CPT], r4c[CPT];  // pos: list position; -1 = scanned in this search; -2 = no such column
+  // candidate word rank << 13 | (row4col + 1) = kb + ks * pos: an unassigned column ranks n-1-pos (the LAST list
+  // position wins), an assigned one n+pos (the first wins, after every unassigned column)
+  uint32_t kb[CPT];
+  int ks[CPT];
+  const float *Cj[CPT];  // &C[0][j] of the owned columns: the cost address is one IMAD.WIDE per column
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) v[c] = 0.0;
+
+  // Warm start (optional), as in v2: any column duals v are feasible with u_i = min_j (c_ij - v_j); a row keeps
+  // its arg-min column when no smaller row claimed it, the others are inserted by the search below.
+  const double *vin = (v_in != nullptr) ? v_in[prob] : nullptr;
+  if (vin != nullptr) {
+    for (int k = tid; k < n; k += nthr) vtmp[k] = v_scale * vin[k];
+    __syncthreads();
+    for (int i = warp; i < n; i += nwarps) {
+      const float *__restrict__ crow = C + (int64_t)i * ld;
+      double best = INFINITY;
+      int bj = n;
+      for (int j = lane; j < n; j += 32) {
+        const double r = __dsub_rn(sgn * (double)__ldg(crow + j), vtmp[j]);
+        if (r < best) {
+          best = r;
+          bj = j;
+        }
+      }
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, m);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, m);
+        if (ob < best || (ob == best && oj < bj)) {
+          best = ob;
+          bj = oj;
+        }
+      }
+      if (lane == 0) {
+        u[i] = best;
+        pred[i] = bj;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int i = 0; i < n; ++i) {
+        const int j = pred[i];
+        if (j < n && row4col[j] < 0) {
+          row4col[j] = i;
+          col4row[i] = j;
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int j = tid + c * nthr;
+      if (j < n) v[c] = vtmp[j];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    const int j = tid + c * nthr;
+    r4c[c] = (j < n) ? row4col[j] : -1;
+    kb[c] = (r4c[c] < 0) ? ((uint32_t)(n - 1) << 13) : (((uint32_t)n << 13) | (uint32_t)(r4c[c] + 1));
+    ks[c] = (r4c[c] < 0) ? -8192 : 8192;
+    Cj[c] = C + (j < n ? j : 0);
+  }
+  const uint32_t ld4 = (uint32_t)ld * 4u;  // bytes per cost row (the host checks ld < 2^30)
+
+  const uint32_t sm_u = sm_base + 1024u, sm_pred = sm_u + 16u * (uint32_t)n;
+  const uint32_t sm_wkey = sm_base + 8u * (uint32_t)warp, sm_wrank = sm_base + 512u + 4u * (uint32_t)warp;
+  const uint32_t sm_gkey = sm_base + 8u * (uint32_t)lane, sm_grank = sm_base + 512u + 4u * (uint32_t)lane;
+  int result = 0;
+  uint32_t step = 0;  // parity selects the warp-winner buffer
+#ifdef PLB_LAP_TRACE
+  uint32_t tr_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tr_last;
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(tr_last)::"memory");
+#endif
+  for (int cur = 0; cur < n; ++cur) {
+    if (col4row[cur] >= 0) continue;  // matched by the warm start (uniform: written only between barriers)
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int j = tid + c * nthr;
+      dkey[c] = 0xfff0000000000000ull;  // +inf
+      pos[c] = (j < n) ? (n - 1 - j) : -2;
+    }
+    int row = cur, ntodo = n, sink = -1;
+    double min_val = 0.0;
+    LAP_STAMP(7, ntodo);
+
+    while (true) {
+      const double u_row = lds_f64(sm_u + 8u * (uint32_t)row);
+      float cf[CPT];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)
+        cf[c] = (pos[c] >= 0) ? __ldg((const float *)((const char *)Cj[c] + (uint64_t)(uint32_t)row * ld4)) : 0.f;
+      LAP_STAMP(0, __float_as_uint(cf[0]));
+      // candidate = (distance key, rank << 13 | row4col + 1): rank < 2n <= 8192 is unique, so the third reduction
+      // word also carries the row matched to the winning column
+      uint64_t bkey = 0xffffffffffffffffull;
+      uint32_t bpk = 0xffffffffu;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        if (pos[c] >= 0) {
+          const double cst = (double)__uint_as_float(__float_as_uint(cf[c]) ^ smask);
+          const double r = __dsub_rn(__dsub_rn(__dadd_rn(min_val, cst), u_row), v[c]);
+          const uint64_t rk = order_key_i(r);
+          if (rk < dkey[c]) {
+            dkey[c] = rk;
+            sts_u32(sm_pred + 4u * (uint32_t)(tid + c * nthr), (uint32_t)row);
+          }
+          const uint32_t pk = kb[c] + (uint32_t)(ks[c] * pos[c]);
+          if (dkey[c] < bkey || (dkey[c] == bkey && pk < bpk)) {
+            bkey = dkey[c];
+            bpk = pk;
+          }
+        }
+      }
+      const uint32_t buf = step & 1u;
+      ++step;
+      LAP_STAMP(1, (uint32_t)bkey);
+      {
+        const Win w = warp_argmin(bkey, bpk);
+        LAP_STAMP(2, w.rank);
+        if (lane == 0) {  // all-ones when the warp has no candidate
+          sts_u64(sm_wkey + 256u * buf, w.key);
+          sts_u32(sm_wrank + 128u * buf, w.rank);
+        }
+      }
+      __syncthreads();
+      LAP_STAMP(3, 0);
+      const bool have = lane < nwarps;
+      const uint64_t gk = have ? lds_u64(sm_gkey + 256u * buf) : 0xffffffffffffffffull;
+      const uint32_t gr = have ? lds_u32(sm_grank + 128u * buf) : 0xffffffffu;
+      LAP_STAMP(4, gr ^ (uint32_t)gk);
+      const Win g = warp_argmin(gk, gr);
+      LAP_STAMP(5, g.rank);
+      if (g.key >= 0xfff0000000000000ull) {  // no candidate, or the nearest column is at +inf: infeasible
+        sink = -2;
+        break;
+      }
+      const uint32_t grank = g.rank >> 13;
+      const int next_row = (int)(g.rank & 0x1fffu) - 1;
+      const int t = (grank < (uint32_t)n) ? (n - 1 - (int)grank) : ((int)grank - n);
+      min_val = key_value(g.key);
+      const int last = ntodo - 1;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)  // scanned; SciPy moves the last list element into the freed slot
+        pos[c] = (pos[c] == t) ? -1 : ((pos[c] == last) ? t : pos[c]);
+      ntodo = last;
+      LAP_STAMP(6, next_row ^ pos[0]);
+      if (next_row < 0) {
+        sink = 0;
+        break;
+      }
+      row = next_row;
+    }
+    if (sink == -2) {
+      result = 1;
+      break;
+    }
+
+    // dual update from registers: the owner of a scanned column j updates v_j and the dual of the row matched to
+    // j (that row was reached through j: col4row[row] == j before the flip); the inserted row gets + min_val.
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      if (pos[c] == -1 && r4c[c] < 0) sts_u32(sm_base + 768u, (uint32_t)(tid + c * nthr));  // the sink: the only
+      if (pos[c] == -1) {                                                        // scanned unassigned column
+        const double dv = __dsub_rn(min_val, key_value(dkey[c]));
+        v[c] = __dsub_rn(v[c], dv);
+        if (r4c[c] >= 0) u[r4c[c]] = __dadd_rn(u[r4c[c]], dv);
+      }
+    }
+    if (tid == 0) u[cur] = __dadd_rn(u[cur], min_val);
+    __syncthreads();  // pred / sh_sink of the last step are visible
+    if (tid == 0) {   // flip the augmenting path
+      int j = (int)lds_u32(sm_base + 768u);
+      while (true) {
+        const int i = pred[j];
+        row4col[j] = i;
+        const int prev = col4row[i];
+        col4row[i] = j;
+        j = prev;
+        if (i == cur) break;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int j = tid + c * nthr;
+      if (j < n) {
+        r4c[c] = row4col[j];
+        kb[c] = (r4c[c] < 0) ? ((uint32_t)(n - 1) << 13) : (((uint32_t)n << 13) | (uint32_t)(r4c[c] + 1));
+        ks[c] = (r4c[c] < 0) ? -8192 : 8192;
+      }
+    }
+  }
+
+#ifdef PLB_LAP_TRACE
+  if (prob == 0 && (tid == 0 || tid == nthr - 1)) {
+    tr_acc[8] = step;
+    for (int k = 0; k < 10; ++k) plb_lap_trace[tid == 0 ? 0 : 1][k] = tr_acc[k];
+  }
+#endif
+  if (result != 0) {
+    if (tid == 0) {
+      status[prob] = result;
+      objective[prob] = 0.0;
+    }
+    return;
+  }
+  if (v_out != nullptr && v_out[prob] != nullptr) {
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int j = tid + c * nthr;
+      if (j < n) v_out[prob][j] = v[c];
+    }
+  }
+  int64_t *out = outs[prob];
+  double part = 0.0;
+  for (int i = tid; i < n; i += nthr) {
+    const int j = col4row[i];
+    out[i] = (int64_t)j;
+    part += (double)C[(int64_t)i * ld + j];
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+  if (lane == 0) red[warp] = part;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int wq = 0; wq < nwarps; ++wq) tot += red[wq];
+    objective[prob] = tot;
+    status[prob] = 0;
+  }
+}
+
+template <int CPT>
+static int launch_lap_v3(const float *const *cost, const int32_t *n, const int32_t *ld, int64_t *const *col4row,
+                         double *objective, int32_t *status, int n_problems, int max_n, int maximize,
+                         const double *const *v_in, double v_scale, double *const *v_out, cudaStream_t stream) {
+  const size_t smem = lap_v3_smem_bytes(max_n);
+  if (int rc = ensure_dynamic_smem((const void *)lap_kernel_v3<CPT>, (int)smem, "lap_kernel_v3")) return rc;
+  int threads = (int)(ceil_div(max_n, 32 * CPT) * 32);
+  threads = threads < 32 ? 32 : threads;  // <= 1024 by the caller's choice of CPT
+  lap_kernel_v3<CPT><<<n_problems, threads, smem, stream>>>(cost, n, ld, col4row, objective, status, maximize, v_in,
+                                                            v_scale, v_out);
+  return launch_status("lap_kernel_v3");
+}
+
 template <int CPT>
 static int launch_lap_v2(const float *const *cost, const int32_t *n, const int32_t *ld, int64_t *const *col4row,
                          double *objective, int32_t *status, int n_problems, int max_n, int maximize, size_t smem,
@@ -564,14 +943,30 @@ static int lap_solve_impl(const float *const *cost, const int32_t *n, const int3
   PLB_REQUIRE(max_n <= 4096, PLB_ESIZE, "plb_lap_solve_batched: n > 4096 exceeds the shared-memory working set");
   const size_t smem = lap_smem_bytes(max_n);
   if (int rc = ensure_dynamic_smem((const void *)lap_kernel, (int)smem, "lap_kernel")) return rc;
-  // PLB_LAP_IMPL=v1 selects the first kernel (one column per thread, two barriers per step) for A/B
-  // runs; PLB_LAP_COLS_PER_THREAD overrides the columns per thread of either kernel.
+  // PLB_LAP_IMPL=v1 / v2 select the earlier kernels (v1: one column per thread, two barriers per step; v2: solver
+  // state in shared memory) for A/B runs; PLB_LAP_COLS_PER_THREAD overrides the columns per thread.
   static int impl = 0, cols_override = -1;
   if (impl == 0) {
     const char *e = getenv("PLB_LAP_IMPL");
-    impl = (e && e[0] == 'v' && e[1] == '1') ? 1 : 2;
+    impl = (e && e[0] == 'v' && e[1] == '1') ? 1 : ((e && e[0] == 'v' && e[1] == '2') ? 2 : 3);
     const char *c = getenv("PLB_LAP_COLS_PER_THREAD");
     cols_override = c ? atoi(c) : 0;
+  }
+  if (impl == 3) {
+    // register-resident column state (product path); columns per thread as for v2, PLB_LAP_COLS_PER_THREAD overrides
+    int cpt = cols_override > 0 ? cols_override : (max_n <= 512 ? 1 : (max_n <= 2048 ? 2 : 4));
+    while (cpt < 8 && (int64_t)cpt * 1024 < max_n) cpt *= 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (cpt) {
+      case 1: return launch_lap_v3<1>(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, v_in,
+                                       v_scale, v_out, st);
+      case 2: return launch_lap_v3<2>(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, v_in,
+                                       v_scale, v_out, st);
+      case 4: return launch_lap_v3<4>(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, v_in,
+                                       v_scale, v_out, st);
+      default: return launch_lap_v3<8>(cost, n, ld, col4row, objective, status, n_problems, max_n, maximize, v_in,
+                                       v_scale, v_out, st);
+    }
   }
   if (impl == 2) {
     // columns per thread, measured on B200 (profiles/experiments/lap_cpt_sweep.py, N(0,1) costs, ms at

@@ -17,4 +17,4 @@ for n in (256, 512, 1024, 2048, 4096):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); ops.lap_solve_batched([Ad], True); e1.record(); torch.cuda.synchronize()
         out.append("%s n=%d: %.2f ms" % (kind, n, e0.elapsed_time(e1)))
-print("cpt=%s impl=%s | " % (os.environ.get("PLB_LAP_COLS_PER_THREAD", "auto"), os.environ.get("PLB_LAP_IMPL", "v2")) + " | ".join(out))
+print("cpt=%s impl=%s | " % (os.environ.get("PLB_LAP_COLS_PER_THREAD", "auto"), os.environ.get("PLB_LAP_IMPL", "v3")) + " | ".join(out))
