@@ -684,12 +684,13 @@ def _run_b200(args):
         gbs = lap_bytes / (lap_ms / 1e3) / 1e9
         out["roofline_lap"] = {
             "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-            "traffic": None, "kernel": "lap_kernel_v2", "ms": lap_ms, "problems": len(mats),
+            "traffic": None, "kernel": "lap_kernel_v3", "ms": lap_ms, "problems": len(mats),
             "sizes": sorted({m.shape[0] for m in mats}),
             "note": "all permutation groups of the pair in ONE launch (one CTA per problem), real -cdist cost matrices of "
                     "this run; algorithmic bytes = sum n^2 * 4 (each matrix read once).  The solve is a chain of dependent "
-                    "augmenting-path steps (latency-bound by construction): the fraction of the HBM rate is reported because "
-                    "the contract asks for it, the time is what matters"}
+                    "augmenting-path steps (latency-bound by construction; ~125 k steps of ~0.75 us for the n = 2048 group, "
+                    "instruction-issue bound at 32 warps: profiles/r02_notes.md): the fraction of the HBM rate is reported "
+                    "because the contract asks for it, the time is what matters"}
         # ---- K5: blocked fp64 Cholesky + triangular solves, the largest layer shape of the pair
         n_ch, nrhs = 4608, 512
         A = torch.randn(n_ch, n_ch + 64, dtype=torch.float64, device=device)

@@ -558,19 +558,22 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v2(const float *const *__r
 // ------------------------------------------------------------------------------------------
 #ifdef PLB_LAP_TRACE  // profiles/experiments/lap_trace.cu: per-phase clock sums of problem 0 (first and last thread)
 __device__ uint32_t plb_lap_trace[2][10];
-#define LAP_STAMP(k, dep)                                                                      \
-  do {                                                                                         \
-    uint32_t _t;                                                                               \
-    asm volatile("mov.u32 %0, %%clock;" : "=r"(_t) : "r"((uint32_t)(dep)) : "memory");         \
-    tr_acc[k] += _t - tr_last;                                                                 \
-    tr_last = _t;                                                                              \
+#define LAP_STAMP(k, dep)                                                                                      \
+  do { /* the volatile store consumes `dep` first: in-order issue makes the clock read wait for the value */   \
+    uint32_t _t;                                                                                               \
+    asm volatile("st.volatile.shared.u32 [%1], %2;\n\tmov.u32 %0, %%clock;"                                     \
+                 : "=r"(_t)                                                                                    \
+                 : "r"(sm_base + 1028u + 0u * (uint32_t)(k)), "r"((uint32_t)(dep))                             \
+                 : "memory");                                                                                  \
+    tr_acc[k] += _t - tr_last;                                                                                 \
+    tr_last = _t;                                                                                              \
   } while (0)
 #else
 #define LAP_STAMP(k, dep) \
   do {                    \
   } while (0)
 #endif
-static inline size_t lap_v3_smem_bytes(int n) { return 1024 + (size_t)n * (2 * 8 + 3 * 4) + 64; }
+static inline size_t lap_v3_smem_bytes(int n) { return 1088 + (size_t)n * (2 * 8 + 3 * 4) + 64; }
 
 // order_key on the two 32-bit halves (b ^ ((b >> 63) | sign bit)): pure integer instructions — the compiler
 // turns the 64-bit form into an fp64 -|x| DADD on the long-latency pipe.
@@ -597,6 +600,17 @@ __device__ __forceinline__ double lds_f64(uint32_t a) {
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
   return v;
 }
+__device__ __forceinline__ void sts_slot(uint32_t a, uint64_t key, uint32_t word) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"((uint32_t)key), "r"((uint32_t)(key >> 32)),
+               "r"(word), "r"(0u)
+               : "memory");
+}
+__device__ __forceinline__ void lds_slot(uint32_t a, uint64_t &key, uint32_t &word) {
+  uint32_t lo, hi;
+  [[maybe_unused]] uint32_t pad;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(hi), "=r"(word), "=r"(pad) : "r"(a) : "memory");
+  key = ((uint64_t)hi << 32) | lo;
+}
 __device__ __forceinline__ void sts_u64(uint32_t a, uint64_t v) {
   asm volatile("st.shared.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
 }
@@ -613,9 +627,9 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v3(const float *const *__r
                                                         int maximize, const double *const *__restrict__ v_in,
                                                         double v_scale, double *const *__restrict__ v_out) {
   extern __shared__ __align__(16) uint8_t lap_smem[];
-  // warp-winner slots (double-buffered by step parity) at the front of the dynamic allocation:
-  // keys u64 [2][32] at +0, rank << 13 | (row4col + 1) u32 [2][32] at +512
-  // sink column of the finished search at +768.  The base goes through an opaque asm so that it stays a register.
+  // warp-winner slots (double-buffered by step parity) at the front of the dynamic allocation: [2][32] slots of
+  // 16 B {u64 distance key, u32 rank << 13 | (row4col + 1), pad} — one 128-bit store / load per step and thread;
+  // sink column of the finished search at +1024.  The base goes through an opaque asm so that it stays a register.
   uint32_t sm_base;
   asm volatile("mov.u32 %0, %1;" : "=r"(sm_base) : "r"(smem_u32(lap_smem)));
   __shared__ double red[32];
@@ -631,7 +645,7 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v3(const float *const *__r
   const int nwarps = nthr >> 5;
   const double sgn = maximize ? -1.0 : 1.0;
   const uint32_t smask = maximize ? 0x80000000u : 0u;  // costs are negated by flipping the float's sign bit
-  double *__restrict__ u = (double *)(lap_smem + 1024);
+  double *__restrict__ u = (double *)(lap_smem + 1088);
   double *__restrict__ vtmp = u + n;
   int *__restrict__ pred = (int *)(vtmp + n);
   int *__restrict__ row4col = pred + n;
@@ -739,9 +753,11 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v3(const float *const *__r
   }
   const uint32_t ld4 = (uint32_t)ld * 4u;  // bytes per cost row (the host checks ld < 2^30)
 
-  const uint32_t sm_u = sm_base + 1024u, sm_pred = sm_u + 16u * (uint32_t)n;
-  const uint32_t sm_wkey = sm_base + 8u * (uint32_t)warp, sm_wrank = sm_base + 512u + 4u * (uint32_t)warp;
-  const uint32_t sm_gkey = sm_base + 8u * (uint32_t)lane, sm_grank = sm_base + 512u + 4u * (uint32_t)lane;
+  const uint32_t sm_u = sm_base + 1088u, sm_pred = sm_u + 16u * (uint32_t)n;
+  uint32_t sm_wslot = sm_base + 16u * (uint32_t)warp, sm_gslot = sm_base + 16u * (uint32_t)lane;  // ^= 512 per step
+  uint32_t pa[CPT <= 2 ? CPT : 1];  // shared address of pred[j] of the owned columns (recomputed when CPT > 2:
+#pragma unroll                      // registers)
+  for (int c = 0; c < (CPT <= 2 ? CPT : 1); ++c) pa[c] = sm_pred + 4u * (uint32_t)(tid + c * nthr);
   int result = 0;
   uint32_t step = 0;  // parity selects the warp-winner buffer
 #ifdef PLB_LAP_TRACE
@@ -766,7 +782,7 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v3(const float *const *__r
 #pragma unroll
       for (int c = 0; c < CPT; ++c)
         cf[c] = (pos[c] >= 0) ? __ldg((const float *)((const char *)Cj[c] + (uint64_t)(uint32_t)row * ld4)) : 0.f;
-      LAP_STAMP(0, __float_as_uint(cf[0]));
+      LAP_STAMP(0, __float_as_uint(cf[CPT - 1]) ^ __float_as_uint(cf[0]));
       // candidate = (distance key, rank << 13 | row4col + 1): rank < 2n <= 8192 is unique, so the third reduction
       // word also carries the row matched to the winning column
       uint64_t bkey = 0xffffffffffffffffull;
@@ -779,31 +795,30 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v3(const float *const *__r
           const uint64_t rk = order_key_i(r);
           if (rk < dkey[c]) {
             dkey[c] = rk;
-            sts_u32(sm_pred + 4u * (uint32_t)(tid + c * nthr), (uint32_t)row);
+            sts_u32(CPT <= 2 ? pa[CPT <= 2 ? c : 0] : sm_pred + 4u * (uint32_t)(tid + c * nthr), (uint32_t)row);
           }
           const uint32_t pk = kb[c] + (uint32_t)(ks[c] * pos[c]);
-          if (dkey[c] < bkey || (dkey[c] == bkey && pk < bpk)) {
+          if (c == 0 || dkey[c] < bkey || (dkey[c] == bkey && pk < bpk)) {
             bkey = dkey[c];
             bpk = pk;
           }
         }
       }
-      const uint32_t buf = step & 1u;
       ++step;
       LAP_STAMP(1, (uint32_t)bkey);
       {
         const Win w = warp_argmin(bkey, bpk);
         LAP_STAMP(2, w.rank);
-        if (lane == 0) {  // all-ones when the warp has no candidate
-          sts_u64(sm_wkey + 256u * buf, w.key);
-          sts_u32(sm_wrank + 128u * buf, w.rank);
-        }
+        if (lane == 0) sts_slot(sm_wslot, w.key, w.rank);  // all-ones when the warp has no candidate
       }
       __syncthreads();
       LAP_STAMP(3, 0);
       const bool have = lane < nwarps;
-      const uint64_t gk = have ? lds_u64(sm_gkey + 256u * buf) : 0xffffffffffffffffull;
-      const uint32_t gr = have ? lds_u32(sm_grank + 128u * buf) : 0xffffffffu;
+      uint64_t gk = 0xffffffffffffffffull;
+      uint32_t gr = 0xffffffffu;
+      if (have) lds_slot(sm_gslot, gk, gr);
+      sm_wslot ^= 512u;
+      sm_gslot ^= 512u;
       LAP_STAMP(4, gr ^ (uint32_t)gk);
       const Win g = warp_argmin(gk, gr);
       LAP_STAMP(5, g.rank);
@@ -836,7 +851,7 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v3(const float *const *__r
     // j (that row was reached through j: col4row[row] == j before the flip); the inserted row gets + min_val.
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
-      if (pos[c] == -1 && r4c[c] < 0) sts_u32(sm_base + 768u, (uint32_t)(tid + c * nthr));  // the sink: the only
+      if (pos[c] == -1 && r4c[c] < 0) sts_u32(sm_base + 1024u, (uint32_t)(tid + c * nthr));  // the sink: the only
       if (pos[c] == -1) {                                                        // scanned unassigned column
         const double dv = __dsub_rn(min_val, key_value(dkey[c]));
         v[c] = __dsub_rn(v[c], dv);
@@ -846,7 +861,7 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v3(const float *const *__r
     if (tid == 0) u[cur] = __dadd_rn(u[cur], min_val);
     __syncthreads();  // pred / sh_sink of the last step are visible
     if (tid == 0) {   // flip the augmenting path
-      int j = (int)lds_u32(sm_base + 768u);
+      int j = (int)lds_u32(sm_base + 1024u);
       while (true) {
         const int i = pred[j];
         row4col[j] = i;

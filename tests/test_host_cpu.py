@@ -449,6 +449,12 @@ def test_built_library_is_sm100a_native_sass():
     for n, b in body("gram_direct_kernel").items():
         assert "UTCHMMA" in b and "LDTM" in b and "LDGSTS" in b, n
     assert all("REDUX" in b for b in body("lap_kernel_v2").values())
+    # v3 (product path): warp arg-min by redux, and the shared window base is not re-derived per step
+    # (at most the handful of S2R/S2UR SR_CgaCtaId outside the step loop)
+    for n, b in body("lap_kernel_v3").items():
+        assert "REDUX" in b, n
+        if "ILi1E" in n or "ILi2E" in n:  # every group of a ResNet pair (n <= 2048)
+            assert "STL" not in b and "LDL" not in b, n  # column state stays in registers
     # round 2: the TMA-fed Gram kernel — tensor-map loads (UTMALDG), TMEM loads, and for the CTA-pair
     # instantiation 2-CTA MMAs with a multicast commit
     tma = body("gram_tma_kernel")
