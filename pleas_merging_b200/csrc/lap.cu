@@ -775,13 +775,15 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v3(const float *const *__r
     int row = cur, ntodo = n, sink = -1;
     double min_val = 0.0;
     LAP_STAMP(7, ntodo);
+    // The cost row and u[row] of a step are requested as soon as the row is known — for the next step right after
+    // the cross-warp arg-min, ahead of the list bookkeeping — and unconditionally (a scanned or padding column
+    // reads a valid address and ignores the value): the L2 round trip overlaps the tail of the previous step.
+    double u_row = lds_f64(sm_u + 8u * (uint32_t)row);
+    float cf[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) cf[c] = __ldg((const float *)((const char *)Cj[c] + (uint64_t)(uint32_t)row * ld4));
 
     while (true) {
-      const double u_row = lds_f64(sm_u + 8u * (uint32_t)row);
-      float cf[CPT];
-#pragma unroll
-      for (int c = 0; c < CPT; ++c)
-        cf[c] = (pos[c] >= 0) ? __ldg((const float *)((const char *)Cj[c] + (uint64_t)(uint32_t)row * ld4)) : 0.f;
       LAP_STAMP(0, __float_as_uint(cf[CPT - 1]) ^ __float_as_uint(cf[0]));
       // candidate = (distance key, rank << 13 | row4col + 1): rank < 2n <= 8192 is unique, so the third reduction
       // word also carries the row matched to the winning column
@@ -828,6 +830,11 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v3(const float *const *__r
       }
       const uint32_t grank = g.rank >> 13;
       const int next_row = (int)(g.rank & 0x1fffu) - 1;
+      const uint32_t row_req = (uint32_t)(next_row < 0 ? row : next_row);  // the last step re-requests its own row
+      const double u_next = lds_f64(sm_u + 8u * row_req);
+      float cfn[CPT];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) cfn[c] = __ldg((const float *)((const char *)Cj[c] + (uint64_t)row_req * ld4));
       const int t = (grank < (uint32_t)n) ? (n - 1 - (int)grank) : ((int)grank - n);
       min_val = key_value(g.key);
       const int last = ntodo - 1;
@@ -841,6 +848,9 @@ __global__ void __launch_bounds__(1024, 1) lap_kernel_v3(const float *const *__r
         break;
       }
       row = next_row;
+      u_row = u_next;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) cf[c] = cfn[c];
     }
     if (sink == -2) {
       result = 1;
