@@ -130,6 +130,10 @@ struct Im2colGeom {
   int kh, kw, sh, sw, ph, pw, dh, dw, ones_row;
 };
 
+// FAST1X1: 1x1 kernel, stride 1, no padding, Ho*Wo % 4 == 0, 16-byte aligned sources — the four k of a thread are
+// four consecutive positions of one image: one 128-bit load per source instead of four decoded scalar gathers
+// (36 of the 53 convolution inputs of a ResNet-50 and all 54 target packs: 57 % of the bytes this kernel writes).
+template <bool FAST1X1>
 __global__ void __launch_bounds__(256) pack_im2col_kernel(const float *__restrict__ x1, const float *__restrict__ x2,
                                                           const int32_t *__restrict__ chan1,
                                                           const int32_t *__restrict__ chan2,
@@ -172,6 +176,17 @@ __global__ void __launch_bounds__(256) pack_im2col_kernel(const float *__restric
 #pragma unroll
         for (int e = 0; e < 4; ++e) v[e] = (k + e < K) ? 1.f : 0.f;
       } else {
+        if constexpr (FAST1X1) {
+          const uint32_t n = k / HoWo;
+          const int64_t off = (int64_t)n * img + (int64_t)(k - n * HoWo);
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 a = b1 ? __ldg(reinterpret_cast<const float4 *>(b1 + off)) : z;
+          const float4 b = b2 ? __ldg(reinterpret_cast<const float4 *>(b2 + off)) : z;
+          v[0] = fmaf(w1, a.x, w2 * b.x);  // same rounding as the generic path below
+          v[1] = fmaf(w1, a.y, w2 * b.y);
+          v[2] = fmaf(w1, a.z, w2 * b.z);
+          v[3] = fmaf(w1, a.w, w2 * b.w);
+        } else {
         // decode (n, ho, wo) once, then step along the output row
         uint32_t n = k / HoWo;
         const uint32_t p = k - n * HoWo;
@@ -194,6 +209,7 @@ __global__ void __launch_bounds__(256) pack_im2col_kernel(const float *__restric
               ++n;
             }
           }
+        }
         }
       }
     }
@@ -286,7 +302,15 @@ extern "C" int plb_pack_im2col(const float *x1, const float *x2, int64_t N, int6
   const int k_blocks = (int)ceil_div(K, kPackK);
   dim3 grid((unsigned)ceil_div(k_blocks, kKbPerBlock), (unsigned)ceil_div(rows, 8));
   PLB_REQUIRE(grid.y <= 65535, PLB_ESIZE, "plb_pack_im2col: too many rows");
-  pack_im2col_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x1, x2, chan1, chan2, scale1, scale2, gm, (int)rows,
-                                                            (uint32_t)K, hi, lo, row_groups, kb_offset, k_blocks);
+  const bool fast = kh == 1 && kw == 1 && stride_h == 1 && stride_w == 1 && pad_h == 0 && pad_w == 0 && Ho == H &&
+                    Wo == W && (H * W) % 4 == 0 && ((uintptr_t)x1 % 16) == 0 && ((uintptr_t)x2 % 16) == 0;
+  if (fast)
+    pack_im2col_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x1, x2, chan1, chan2, scale1, scale2, gm,
+                                                                    (int)rows, (uint32_t)K, hi, lo, row_groups,
+                                                                    kb_offset, k_blocks);
+  else
+    pack_im2col_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x1, x2, chan1, chan2, scale1, scale2, gm,
+                                                                     (int)rows, (uint32_t)K, hi, lo, row_groups,
+                                                                     kb_offset, k_blocks);
   return launch_status("pack_im2col_kernel");
 }

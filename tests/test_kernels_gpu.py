@@ -480,8 +480,11 @@ def test_pack_im2col_vs_unfold():
     b1c = torch.tensor([i for i in range(10) if i not in b1.tolist()])
     b2c = torch.tensor([i for i in range(10) if i not in b2.tolist()])
     xbar = torch.cat([(x1[:, b1] + x2[:, b2]) / 2, x1[:, b1c], x2[:, b2c]], 1)  # pleas_merging.py:146
+    # the fourth and fifth cases take the kernel's 1x1 / stride-1 fast path (H * W = 72 is a multiple of 4:
+    # 128-bit loads), with and without the bias row
     for kernel, stride, pad, dil, bias in (((3, 3), (1, 1), (1, 1), (1, 1), False), ((1, 1), (2, 2), (0, 0), (1, 1), True),
-                                           ((3, 2), (2, 1), (0, 1), (1, 2), True)):
+                                           ((3, 2), (2, 1), (0, 1), (1, 2), True), ((1, 1), (1, 1), (0, 0), (1, 1), True),
+                                           ((1, 1), (1, 1), (0, 0), (1, 1), False)):
         U = F.unfold(xbar, kernel, dil, pad, stride)  # [B, K, L']
         Ho = (9 + 2 * pad[0] - dil[0] * (kernel[0] - 1) - 1) // stride[0] + 1
         Wo = (8 + 2 * pad[1] - dil[1] * (kernel[1] - 1) - 1) // stride[1] + 1
