@@ -209,7 +209,8 @@ int plb_cross_finalize_corr(const float *partial, int32_t splits, int64_t ld_m, 
  * SciPy's Crouse shortest-augmenting-path in float64) including its tie-breaking rules, so
  * the returned assignment is identical to SciPy's.  One CTA per problem.
  * cost[p]: [n_p, n_p] fp32 row-major with leading dimension ld_p; col4row[p]: int64[n_p];
- * objective[p]: sum_i cost[i, col4row[i]] in fp64; status[p]: 0 ok, 1 infeasible, 2 NaN/-inf.
+ * objective[p]: sum_i cost[i, col4row[i]] in fp64; status[p]: 0 ok, 1 infeasible, 2 invalid input
+ * (NaN / -inf entries, as SciPy rejects them; or a leading dimension of 2^30 elements and more).
  * The four arrays-of-pointers / sizes are DEVICE arrays of length n_problems. n_p <= 4096.
  * --------------------------------------------------------------------------------------- */
 int plb_lap_solve_batched(const float *const *cost, const int32_t *n, const int32_t *ld,
