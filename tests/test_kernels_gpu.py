@@ -347,6 +347,21 @@ def test_lap_random_vs_oracle(n):
         assert (o.cpu().numpy() == col).all()
 
 
+def test_lap_groups_wider_than_2048_and_mixed_batch():
+    """Groups of 2049..4096 units take the four-columns-per-thread instantiation of lap_kernel_v3; a small problem in
+    the same launch keeps one warp of the 1024-thread block.  Integer costs: ties everywhere."""
+    ops = _ops()
+    rng = np.random.default_rng(2500)
+    mats = [rng.standard_normal((2500, 2500)).astype(np.float32), rng.integers(0, 7, (40, 40)).astype(np.float32),
+            rng.integers(0, 50, (2100, 2100)).astype(np.float32)]
+    for maximize in (True, False):
+        outs, obj, status = ops.lap_solve_batched([torch.from_numpy(m).cuda() for m in mats], maximize)
+        assert (status.cpu() == 0).all()
+        for m, o in zip(mats, outs):
+            col, _ = O.solve_lsa(m, maximize)
+            assert (o.cpu().numpy() == col).all(), (m.shape, maximize)
+
+
 def test_lap_strided_and_invalid():
     ops = _ops()
     big = torch.randn(40, 64, generator=torch.Generator().manual_seed(6)).cuda()
